@@ -1,0 +1,130 @@
+// uba_device.h — device-side views and kernel launchers shared by uba_kernels.cu and uba_host.cu.
+#ifndef UBA_DEVICE_H_INCLUDED
+#define UBA_DEVICE_H_INCLUDED
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "uba_math.h"
+
+namespace uba {
+
+// Per-window scalars accumulated by the kernels of one LM iteration (zeroed before each).  They
+// are grouped by how a point-sharded multi-GPU run reduces them:
+//   w_lin  [nW][2]  cost, failures of the lineariser      -> summed over ranks with S (after linearise)
+//   w_post [nW][4]  candidate cost, point parts of the model change / step norm / x norm
+//                                                          -> summed over ranks (after back-substitution)
+//   w_loc  [nW][4]  camera parts + solver failures          -> identical on every rank, never reduced
+//   w_max  [nW]     projected-gradient max norm             -> max over ranks
+enum WLin { WL_COST = 0, WL_FAIL = 1, WL_COUNT = 2 };
+enum WPost { WP_COSTNEW = 0, WP_MCPT = 1, WP_STEP2 = 2, WP_X2 = 3, WP_COUNT = 4 };
+enum WLoc { WC_MCCAM = 0, WC_STEP2 = 1, WC_X2 = 2, WC_FAIL = 3, WC_COUNT = 4 };
+
+// Levenberg–Marquardt controller state of one window (device resident).
+struct WinState {
+  double radius;
+  double decrease_factor;
+  double cost;            // cost at the current iterate (from the last linearisation)
+  double gmax;
+  double initial_cost;
+  int32_t cur;            // parity of the current iterate in the double-buffered cams/pts
+  int32_t done;           // 0 running, else uba_termination
+  int32_t iter;           // LM iterations executed
+  int32_t n_success, n_unsuccess, n_invalid, consecutive_invalid;
+  int32_t scale_ready;    // Jacobi scaling (iteration 0) captured
+  int32_t pad_[2];
+};
+
+struct IterRec {  // mirrors uba_iteration
+  double cost, candidate_cost, model_cost_change, relative_decrease, radius, step_norm, gradient_max_norm;
+  int32_t accepted, pad_;
+};
+
+struct SolverCfg {
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double max_radius, min_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+  int32_t max_consecutive_invalid_steps, fixed_iterations, max_iterations, jacobi_scaling, use_bounds;
+};
+
+// Segment-local tiling plan of the fast lineariser (see uba_kernels.cu, k_lin_tile).
+struct TileItem {
+  int32_t window;
+  int32_t pt_begin, pt_end;   // internal point slots
+  int32_t cam_list_off;       // offset into tile_cams: the item's local camera list (window-local indices)
+  int32_t n_local;            // local cameras (free and fixed)
+  int32_t n_local_free;       // the first n_local_free entries of the list are free cameras
+  int32_t pad_[2];
+};
+
+struct DevView {
+  int32_t M, nW, NC, NP;
+  int64_t NO;
+  // windows
+  const int32_t* w_cam_off;   // [nW+1]
+  const int32_t* w_pt_off;    // [nW+1] internal point slots
+  const int32_t* w_free_off;  // [nW+1] offsets into free_list
+  const int64_t* w_red_off;   // [nW+1] offsets into Sacc / A (sum of n^2)
+  const int32_t* free_list;   // global camera index of each free camera, window by window
+  // cameras (global index = w_cam_off[w] + local)
+  double* cams[2];            // [NC][6]
+  double* camR[2];            // [NC][kCamStride]
+  const int32_t* free_cam;    // [NC] compact index in the window's reduced system, or -1
+  const int32_t* cam_win;     // [NC]
+  double* cam_s2;             // [NC][6] Jacobi scale^2
+  double* cam_lam;            // [NC][6] camera damping of this iteration
+  double* cam_y;              // [NC][6] camera solution y_c (step = -y), zeros for fixed cameras
+  // points (internal order)
+  double* pts[2];             // [NP][3]
+  double* pt_s2;              // [NP][3]
+  double* pt_rec;             // [NP][kPtRec]
+  const int32_t* pt_obs_off;  // [NP+1]
+  const int32_t* pt_win;      // [NP]
+  // observations (internal order), SoA
+  const double* feat;         // [M][NO]
+  const int32_t* obs_cam;     // [NO] window-local camera index | (camID != 0) << 30
+  // accumulators
+  double* Sacc;               // per window [n][n], upper block triangle: sum_j Z Z^T
+  double* Bacc;               // [NC][36]
+  double* vacc;               // [NC][6]
+  double* zh;                 // [NC][6]
+  double* w_lin;              // [nW][WL_COUNT]
+  double* w_post;             // [nW][WP_COUNT]
+  double* w_loc;              // [nW][WC_COUNT]
+  double* w_max;              // [nW]
+  double* A;                  // per window [n][n] assembled damped reduced matrix (full), then its factor
+  double* rhs;                // [6 * n_free_total]
+  double* Zbuf;               // [NO][18] scratch of the generic lineariser
+  WinState* ws;               // [nW]
+  IterRec* recs;              // [nW][rec_stride]
+  int32_t rec_stride;
+  int32_t* n_active;          // [1] windows still running
+  Calib calib;
+  LossCfg loss;
+  SolverCfg cfg;
+};
+
+// Optional debug / parity outputs of a linearisation (device pointers, internal order; may be null).
+struct DebugOut {
+  double* residuals;  // [NO][M]
+  double* weights;    // [NO]
+  double* C;          // [NP][9]
+  double* W;          // [NO][18]
+  double* grad_pts;   // [NP][3]
+  double* lam_pts;    // [NP][3]
+};
+
+// launchers (uba_kernels.cu); all asynchronous on `st`; return the number of kernels launched
+int launch_cam_prep(const DevView& V, int parity, cudaStream_t st);
+int launch_lin_generic(const DevView& V, const DebugOut& dbg, cudaStream_t st);
+int launch_assemble(const DevView& V, int max_n, cudaStream_t st);
+// h_win_n: host array [nW] of reduced-system sizes (6 * free cameras)
+int launch_solve(const DevView& V, const int* h_win_n, int max_small_n, cudaStream_t st);
+int solve_small_limit();
+int launch_backsub(const DevView& V, cudaStream_t st);
+int launch_lm_update(const DevView& V, cudaStream_t st);
+int launch_init_state(const DevView& V, double initial_radius, cudaStream_t st);
+int launch_l2_flush(double* buf, size_t n, cudaStream_t st);
+int launch_dfma_probe(double* out, int iters, cudaStream_t st);
+
+}  // namespace uba
+#endif

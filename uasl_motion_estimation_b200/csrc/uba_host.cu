@@ -1,0 +1,866 @@
+// uba_host.cu — host side of libuba: the C ABI of include/uba.h.
+//
+// Mirrors what me::optimisation::BundleAdjuster<M> does around ceres::Solve
+// (reference include/MotionEstimation/optimisation/BundleAdjuster.h):
+//   uba_set_problem / uba_set_batch  ~ constructors + initialiseParameters/Observations (:196-228,:286-376)
+//   uba_optimise                     ~ optimise(fixedFrames) (:378-476)
+//   uba_get_cameras / uba_get_points ~ getCameraPoses / getPoints (:231-237)
+// Everything numerical runs in the kernels of uba_kernels.cu; this file only builds
+// index tables, moves buffers and sequences launches.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/uba.h"
+#include "uba_device.h"
+
+using namespace uba;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- minimal NCCL binding, resolved at run time (libnccl is only needed for sharded runs) ------
+struct Id128 { char internal[UBA_NCCL_UNIQUE_ID_BYTES]; };  // ncclUniqueId
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;
+
+bool load_nccl(NcclApi& api, std::string& err) {
+  if (api.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) { api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+  if (!api.lib) { err = "cannot dlopen libnccl.so.2"; return false; }
+  api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(api.lib, "ncclCommInitRank");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+  api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) { err = "libnccl lacks required symbols"; return false; }
+  return true;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct uba_handle {
+  uba_config cfg;
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  // problem (host tables)
+  int state = 0;  // 0 uninitialised, 1 problem set, 2 optimised
+  int M = 4, nW = 0, NC = 0, NP = 0;
+  int64_t NO = 0;
+  uba_calib calib_in{};
+  std::vector<int32_t> w_cam_off, w_pt_off;        // [nW+1]
+  std::vector<int64_t> w_obs_off;                  // [nW+1]
+  std::vector<int32_t> obs_order;                  // canonical table (global caller obs id per point-major slot)
+  std::vector<int64_t> pt_obs_off_caller;          // [NP+1] canonical CSR (caller point order)
+  std::vector<int32_t> pt_order;                   // [NP] caller point id (global) per internal slot
+  std::vector<int32_t> obs_internal;               // [NO] caller obs id per internal obs slot
+  std::vector<int32_t> pt_obs_off_int;             // [NP+1]
+  std::vector<char> cam_seen;                      // [NC]
+  std::vector<int32_t> cam_win_h, pt_win_h;
+  // prepared for a given fixed_frames
+  int prepared_fixed = -1;
+  std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n;
+  std::vector<int64_t> w_red_off_h;
+  int max_n = 0;
+  // pinned staging (internal order)
+  PinBuf<double> h_cams, h_pts, h_feat, h_out;
+  PinBuf<int32_t> h_obs_cam;
+  // device
+  DevBuf<double> d_cams, d_camR, d_cam_s2, d_cam_lam, d_cam_y, d_pts, d_pt_s2, d_pt_rec, d_feat, d_acc, d_A, d_rhs, d_Zbuf, d_dbg, d_export, d_flush;
+  DevBuf<int32_t> d_w_cam_off, d_w_pt_off, d_w_free_off, d_free_list, d_free_cam, d_cam_win, d_pt_obs_off, d_pt_win, d_obs_cam, d_n_active, d_pt_order;
+  DevBuf<int64_t> d_w_red_off;
+  DevBuf<WinState> d_ws;
+  DevBuf<IterRec> d_recs;
+  size_t acc_sum1 = 0;   // doubles reduced (sum) after linearise: Sacc|Bacc|vacc|zh|w_lin
+  size_t acc_total = 0;  // all accumulator doubles (one memset)
+  size_t off_Bacc = 0, off_vacc = 0, off_zh = 0, off_wlin = 0, off_wpost = 0, off_wmax = 0, off_wloc = 0;
+  DevView V{};
+  std::vector<WinState> ws_h;
+  // comm
+  NcclApi nccl;
+  void* comm = nullptr;
+  int rank = 0, n_ranks = 1;
+  // timing
+  bool profiling = false;
+  uba_timing timing{};
+};
+
+namespace {
+
+int fail(uba_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+#define CU(h, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(h, UBA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+uba::Calib make_calib(const uba_calib& in, int M, bool use_bounds) {
+  uba::Calib k;
+  double b = in.baseline;
+  if (M == 2 && b == 0.0) b = 0.5;  // BundleAdjuster.h:389-390
+  k.fx0 = in.fx0; k.fy0 = in.fy0; k.cx0 = in.cx0; k.cy0 = in.cy0; k.fx1 = in.fx1; k.cx1 = in.cx1; k.baseline = b;
+  k.sigma_inv = 1.0 / std::sqrt(in.feat_var);  // sigma = sqrt(feat_var), :400,:448
+  const double zmax = in.fx0 * b / 0.1, zmin = in.fx0 * b / (2.0 * in.cx0);  // :442-443
+  k.hi[0] = zmax / in.fx0 * in.cx0; k.lo[0] = -k.hi[0];
+  k.hi[1] = zmax / in.fy0 * in.cy0; k.lo[1] = -k.hi[1];
+  k.hi[2] = zmax; k.lo[2] = zmin;
+  (void)use_bounds;
+  return k;
+}
+
+void fill_view_static(uba_handle* h) {
+  DevView& V = h->V;
+  V.M = h->M; V.nW = h->nW; V.NC = h->NC; V.NP = h->NP; V.NO = h->NO;
+  V.w_cam_off = h->d_w_cam_off.p; V.w_pt_off = h->d_w_pt_off.p;
+  V.cams[0] = h->d_cams.p; V.cams[1] = h->d_cams.p + (size_t)h->NC * 6;
+  V.camR[0] = h->d_camR.p; V.camR[1] = h->d_camR.p + (size_t)h->NC * kCamStride;
+  V.cam_win = h->d_cam_win.p; V.cam_s2 = h->d_cam_s2.p; V.cam_lam = h->d_cam_lam.p; V.cam_y = h->d_cam_y.p;
+  V.pts[0] = h->d_pts.p; V.pts[1] = h->d_pts.p + (size_t)h->NP * 3;
+  V.pt_s2 = h->d_pt_s2.p; V.pt_rec = h->d_pt_rec.p; V.pt_obs_off = h->d_pt_obs_off.p; V.pt_win = h->d_pt_win.p;
+  V.feat = h->d_feat.p; V.obs_cam = h->d_obs_cam.p;
+  V.Zbuf = h->d_Zbuf.p;
+  V.ws = h->d_ws.p; V.recs = h->d_recs.p; V.n_active = h->d_n_active.p;
+  V.calib = make_calib(h->calib_in, h->M, h->cfg.use_bounds != 0);
+  V.loss.kind = h->cfg.loss_kind; V.loss.a = h->cfg.loss_scale;
+  SolverCfg& c = V.cfg;
+  c.function_tolerance = h->cfg.function_tolerance; c.gradient_tolerance = h->cfg.gradient_tolerance;
+  c.parameter_tolerance = h->cfg.parameter_tolerance; c.max_radius = h->cfg.max_radius; c.min_radius = h->cfg.min_radius;
+  c.min_relative_decrease = h->cfg.min_relative_decrease; c.min_lm_diagonal = h->cfg.min_lm_diagonal;
+  c.max_lm_diagonal = h->cfg.max_lm_diagonal; c.max_consecutive_invalid_steps = h->cfg.max_consecutive_invalid_steps;
+  c.fixed_iterations = h->cfg.fixed_iterations; c.max_iterations = h->cfg.max_iterations;
+  c.jacobi_scaling = h->cfg.jacobi_scaling; c.use_bounds = h->cfg.use_bounds;
+}
+
+// Tables that depend on fixed_frames: free cameras, reduced-system layout, accumulators.
+int prepare(uba_handle* h, int fixed_frames) {
+  if (fixed_frames < 0) fixed_frames = 0;
+  if (h->prepared_fixed == fixed_frames) return UBA_OK;
+  const int nW = h->nW, NC = h->NC;
+  h->free_cam_h.assign(NC, -1);
+  h->free_list_h.clear();
+  h->w_free_off_h.assign(nW + 1, 0);
+  h->w_red_off_h.assign(nW + 1, 0);
+  h->win_n.assign(nW, 0);
+  h->max_n = 0;
+  for (int w = 0; w < nW; w++) {
+    int nf = 0;
+    for (int gc = h->w_cam_off[w]; gc < h->w_cam_off[w + 1]; gc++) {
+      const int local = gc - h->w_cam_off[w];
+      // constant cameras: camIdx < fixedFrames (BundleAdjuster.h:406-407,:452-454); cameras nobody
+      // observes never enter the ceres::Problem
+      if (local >= fixed_frames && h->cam_seen[gc]) { h->free_cam_h[gc] = nf++; h->free_list_h.push_back(gc); }
+    }
+    h->w_free_off_h[w + 1] = h->w_free_off_h[w] + nf;
+    h->win_n[w] = 6 * nf;
+    h->w_red_off_h[w + 1] = h->w_red_off_h[w] + (int64_t)36 * nf * nf;
+    h->max_n = std::max(h->max_n, 6 * nf);
+  }
+  const size_t nfree = h->free_list_h.size();
+  const size_t red = (size_t)h->w_red_off_h[nW];
+  CU(h, h->d_free_cam.reserve(NC));
+  CU(h, h->d_free_list.reserve(nfree));
+  CU(h, h->d_w_free_off.reserve(nW + 1));
+  CU(h, h->d_w_red_off.reserve(nW + 1));
+  CU(h, cudaMemcpyAsync(h->d_free_cam.p, h->free_cam_h.data(), sizeof(int32_t) * NC, cudaMemcpyHostToDevice, h->stream));
+  if (nfree) CU(h, cudaMemcpyAsync(h->d_free_list.p, h->free_list_h.data(), sizeof(int32_t) * nfree, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_w_free_off.p, h->w_free_off_h.data(), sizeof(int32_t) * (nW + 1), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_w_red_off.p, h->w_red_off_h.data(), sizeof(int64_t) * (nW + 1), cudaMemcpyHostToDevice, h->stream));
+  // accumulator block: [Sacc | Bacc | vacc | zh | w_lin] [w_post] [w_max] [w_loc]
+  h->off_Bacc = red;
+  h->off_vacc = h->off_Bacc + (size_t)NC * 36;
+  h->off_zh = h->off_vacc + (size_t)NC * 6;
+  h->off_wlin = h->off_zh + (size_t)NC * 6;
+  h->acc_sum1 = h->off_wlin + (size_t)nW * WL_COUNT;
+  h->off_wpost = h->acc_sum1;
+  h->off_wmax = h->off_wpost + (size_t)nW * WP_COUNT;
+  h->off_wloc = h->off_wmax + (size_t)nW;
+  h->acc_total = h->off_wloc + (size_t)nW * WC_COUNT;
+  CU(h, h->d_acc.reserve(h->acc_total));
+  CU(h, h->d_A.reserve(red));
+  CU(h, h->d_rhs.reserve(6 * nfree));
+  CU(h, cudaStreamSynchronize(h->stream));
+  DevView& V = h->V;
+  V.free_cam = h->d_free_cam.p; V.free_list = h->d_free_list.p; V.w_free_off = h->d_w_free_off.p; V.w_red_off = h->d_w_red_off.p;
+  V.Sacc = h->d_acc.p; V.Bacc = h->d_acc.p + h->off_Bacc; V.vacc = h->d_acc.p + h->off_vacc; V.zh = h->d_acc.p + h->off_zh;
+  V.w_lin = h->d_acc.p + h->off_wlin; V.w_post = h->d_acc.p + h->off_wpost; V.w_max = h->d_acc.p + h->off_wmax;
+  V.w_loc = h->d_acc.p + h->off_wloc;
+  V.A = h->d_A.p; V.rhs = h->d_rhs.p;
+  h->prepared_fixed = fixed_frames;
+  return UBA_OK;
+}
+
+int allreduce(uba_handle* h, double* buf, size_t count, int op) {
+  if (!h->comm || count == 0) return UBA_OK;
+  const int rc = h->nccl.AllReduce(buf, buf, count, kNcclDouble, op, h->comm, h->stream);
+  if (rc != 0) return fail(h, UBA_ERR_NCCL, "ncclAllReduce failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?");
+  return UBA_OK;
+}
+
+struct PhaseTimer {
+  uba_handle* h; int phase; bool on;
+  PhaseTimer(uba_handle* h_, int phase_) : h(h_), phase(phase_), on(h_->profiling) { if (on) cudaEventRecord(h->ev[0], h->stream); }
+  void stop() {
+    if (!on) return;
+    cudaEventRecord(h->ev[1], h->stream);
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    double* dst[] = {&h->timing.linearize_ms, &h->timing.solve_ms, &h->timing.backsub_ms, &h->timing.update_ms, &h->timing.comm_ms};
+    *dst[phase] += ms;
+    on = false;
+  }
+};
+
+// the linearise + Schur pass (the roofline kernel of the hot path)
+int run_linearize(uba_handle* h, const DebugOut& dbg) {
+  CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
+  PhaseTimer t(h, 0);
+  h->timing.kernel_launches += launch_lin_generic(h->V, dbg, h->stream);
+  h->timing.linearize_launches++;
+  t.stop();
+  if (h->comm) {
+    PhaseTimer tc(h, 4);
+    int rc = allreduce(h, h->d_acc.p, h->acc_sum1, kNcclSum);
+    if (rc) return rc;
+    tc.stop();
+  }
+  return UBA_OK;
+}
+
+int run_iteration(uba_handle* h) {
+  DebugOut none{};
+  int rc = run_linearize(h, none);
+  if (rc) return rc;
+  {
+    PhaseTimer t(h, 1);
+    h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
+    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), solve_small_limit(), h->stream);
+    t.stop();
+  }
+  {
+    PhaseTimer t(h, 2);
+    h->timing.kernel_launches += launch_backsub(h->V, h->stream);
+    t.stop();
+  }
+  if (h->comm) {
+    PhaseTimer tc(h, 4);
+    rc = allreduce(h, h->d_acc.p + h->off_wpost, (size_t)h->nW * WP_COUNT, kNcclSum);
+    if (rc) return rc;
+    rc = allreduce(h, h->d_acc.p + h->off_wmax, (size_t)h->nW, kNcclMax);
+    if (rc) return rc;
+    tc.stop();
+  }
+  {
+    PhaseTimer t(h, 3);
+    h->timing.kernel_launches += launch_lm_update(h->V, h->stream);
+    t.stop();
+  }
+  return UBA_OK;
+}
+
+int start_solve(uba_handle* h, int fixed_frames) {
+  int rc = prepare(h, fixed_frames);
+  if (rc) return rc;
+  h->timing.kernel_launches += launch_init_state(h->V, h->cfg.initial_radius, h->stream);
+  h->timing.kernel_launches += launch_cam_prep(h->V, 0, h->stream);
+  return UBA_OK;
+}
+
+// restore the initial iterate on the device (parity 0) from the pinned staging copy
+int upload_state(uba_handle* h) {
+  CU(h, cudaMemcpyAsync(h->d_cams.p, h->h_cams.p, sizeof(double) * 6 * h->NC, cudaMemcpyHostToDevice, h->stream));
+  if (h->NP) CU(h, cudaMemcpyAsync(h->d_pts.p, h->h_pts.p, sizeof(double) * 3 * h->NP, cudaMemcpyHostToDevice, h->stream));
+  return UBA_OK;
+}
+
+int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t* wp, const int64_t* wo, const double* cams6,
+                  const double* pts3, const double* feats, const int32_t* cam_idx, const int32_t* pt_idx, const int32_t* cam_id,
+                  const uba_calib* calib) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  if (M != 2 && M != 4) return fail(h, UBA_ERR_INVALID_ARGUMENT, "M must be 2 or 4 (got %d)", M);
+  if (nW <= 0 || !wc || !wp || !wo || !calib) return fail(h, UBA_ERR_INVALID_ARGUMENT, "null or empty window tables");
+  const int NC = wc[nW], NP = wp[nW];
+  const int64_t NO = wo[nW];
+  if (NC <= 0 || NP < 0 || NO < 0) return fail(h, UBA_ERR_INVALID_ARGUMENT, "negative or empty sizes");
+  if (NO >= (int64_t)INT32_MAX) return fail(h, UBA_ERR_UNSUPPORTED, "more than 2^31-1 observations in one handle");
+  if (!cams6 || (NP && !pts3) || (NO && (!feats || !cam_idx || !pt_idx))) return fail(h, UBA_ERR_INVALID_ARGUMENT, "null input array");
+  if (!(calib->feat_var > 0.0) || !(calib->fx0 > 0.0) || !(calib->fy0 > 0.0) || !(calib->cx0 > 0.0))
+    return fail(h, UBA_ERR_INVALID_ARGUMENT, "calibration must have positive fx, fy, cx and feat_var");
+  if (M == 4 && calib->baseline == 0.0) return fail(h, UBA_ERR_INVALID_ARGUMENT, "stereo BA needs a non-zero baseline (BundleAdjuster.h:147)");
+  h->state = 0; h->prepared_fixed = -1;
+  h->M = M; h->nW = nW; h->NC = NC; h->NP = NP; h->NO = NO; h->calib_in = *calib;
+  h->w_cam_off.assign(wc, wc + nW + 1); h->w_pt_off.assign(wp, wp + nW + 1); h->w_obs_off.assign(wo, wo + nW + 1);
+  h->obs_order.assign(NO, 0); h->pt_obs_off_caller.assign((size_t)NP + 1, 0); h->pt_order.assign(NP, 0);
+  h->obs_internal.assign(NO, 0); h->pt_obs_off_int.assign((size_t)NP + 1, 0);
+  h->cam_seen.assign(NC, 0); h->cam_win_h.assign(NC, 0); h->pt_win_h.assign(NP, 0);
+  // validate + count
+  int bad = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : bad)
+  for (int w = 0; w < nW; w++) {
+    const int nc = wc[w + 1] - wc[w], np = wp[w + 1] - wp[w];
+    if (nc < 0 || np < 0 || wo[w + 1] < wo[w]) { bad++; continue; }
+    for (int64_t o = wo[w]; o < wo[w + 1]; o++) {
+      if (cam_idx[o] < 0 || cam_idx[o] >= nc || pt_idx[o] < 0 || pt_idx[o] >= np) { bad++; continue; }
+      h->pt_obs_off_caller[(size_t)wp[w] + pt_idx[o] + 1]++;
+      h->cam_seen[wc[w] + cam_idx[o]] = 1;
+    }
+    for (int c = wc[w]; c < wc[w + 1]; c++) h->cam_win_h[c] = w;
+  }
+  if (bad) return fail(h, UBA_ERR_INVALID_ARGUMENT, "camIdx / ptIdx out of range or malformed window offsets (%d offences)", bad);
+  for (int j = 0; j < NP; j++) h->pt_obs_off_caller[j + 1] += h->pt_obs_off_caller[j];
+  // canonical order: point-major (stable), camera-ascending inside a point; and the internal point order
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int w = 0; w < nW; w++) {
+    const int p0 = wp[w], np = wp[w + 1] - wp[w];
+    std::vector<int64_t> fill(np);
+    for (int j = 0; j < np; j++) fill[j] = h->pt_obs_off_caller[p0 + j];
+    for (int64_t o = wo[w]; o < wo[w + 1]; o++) h->obs_order[fill[pt_idx[o]]++] = (int32_t)o;
+    std::vector<int> lo(np, INT_MAX), hi(np, -1);
+    for (int j = 0; j < np; j++) {
+      int32_t* b = &h->obs_order[h->pt_obs_off_caller[p0 + j]];
+      int32_t* e = &h->obs_order[h->pt_obs_off_caller[p0 + j + 1]];
+      // insertion sort by camera (stable; tracks are short and already ascending for reference input)
+      for (int32_t* i = b + 1; i < e; i++) {
+        const int32_t v = *i; int32_t* k = i;
+        while (k > b && cam_idx[*(k - 1)] > cam_idx[v]) { *k = *(k - 1); k--; }
+        *k = v;
+      }
+      if (b < e) { lo[j] = cam_idx[*b]; hi[j] = cam_idx[*(e - 1)]; }
+    }
+    std::vector<int32_t> ids(np);
+    std::iota(ids.begin(), ids.end(), 0);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b2) { if (lo[a] != lo[b2]) return lo[a] < lo[b2]; return hi[a] < hi[b2]; });
+    for (int j = 0; j < np; j++) { h->pt_order[p0 + j] = p0 + ids[j]; h->pt_win_h[p0 + j] = w; }
+  }
+  // internal CSR + observation slots (window ranges coincide with the caller's)
+  for (int s = 0; s < NP; s++) {
+    const int j = h->pt_order[s];
+    h->pt_obs_off_int[s + 1] = h->pt_obs_off_int[s] + (int32_t)(h->pt_obs_off_caller[j + 1] - h->pt_obs_off_caller[j]);
+  }
+  // staging in internal order (pinned)
+  CU(h, h->h_cams.reserve((size_t)NC * 6));
+  CU(h, h->h_pts.reserve((size_t)NP * 3));
+  CU(h, h->h_feat.reserve((size_t)NO * M));
+  CU(h, h->h_obs_cam.reserve((size_t)NO));
+  std::memcpy(h->h_cams.p, cams6, sizeof(double) * 6 * NC);
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < NP; s++) {
+    const int j = h->pt_order[s];
+    h->h_pts.p[(size_t)s * 3] = pts3[(size_t)j * 3]; h->h_pts.p[(size_t)s * 3 + 1] = pts3[(size_t)j * 3 + 1]; h->h_pts.p[(size_t)s * 3 + 2] = pts3[(size_t)j * 3 + 2];
+    const int64_t src = h->pt_obs_off_caller[j];
+    const int32_t dst = h->pt_obs_off_int[s];
+    const int k = h->pt_obs_off_int[s + 1] - dst;
+    for (int q = 0; q < k; q++) {
+      const int32_t o = h->obs_order[src + q];
+      h->obs_internal[dst + q] = o;
+      for (int m = 0; m < M; m++) h->h_feat.p[(size_t)m * NO + dst + q] = feats[(size_t)o * M + m];
+      h->h_obs_cam.p[dst + q] = cam_idx[o] | ((cam_id && cam_id[o] != 0) ? (1 << 30) : 0);
+    }
+  }
+  // device buffers
+  CU(h, h->d_cams.reserve((size_t)NC * 12)); CU(h, h->d_camR.reserve((size_t)NC * kCamStride * 2));
+  CU(h, h->d_cam_s2.reserve((size_t)NC * 6)); CU(h, h->d_cam_lam.reserve((size_t)NC * 6)); CU(h, h->d_cam_y.reserve((size_t)NC * 6));
+  CU(h, h->d_pts.reserve((size_t)NP * 6)); CU(h, h->d_pt_s2.reserve((size_t)NP * 3)); CU(h, h->d_pt_rec.reserve((size_t)NP * kPtRec));
+  CU(h, h->d_feat.reserve((size_t)NO * M)); CU(h, h->d_obs_cam.reserve((size_t)NO)); CU(h, h->d_Zbuf.reserve((size_t)NO * 18));
+  CU(h, h->d_w_cam_off.reserve(nW + 1)); CU(h, h->d_w_pt_off.reserve(nW + 1)); CU(h, h->d_cam_win.reserve(NC));
+  CU(h, h->d_pt_obs_off.reserve((size_t)NP + 1)); CU(h, h->d_pt_win.reserve(std::max(NP, 1))); CU(h, h->d_pt_order.reserve(std::max(NP, 1)));
+  CU(h, h->d_ws.reserve(nW)); CU(h, h->d_n_active.reserve(1));
+  const int rec_stride = std::max(h->cfg.max_iterations, h->cfg.fixed_iterations) + 2;
+  CU(h, h->d_recs.reserve((size_t)nW * rec_stride));
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(h->d_w_cam_off.p, h->w_cam_off.data(), sizeof(int32_t) * (nW + 1), cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_w_pt_off.p, h->w_pt_off.data(), sizeof(int32_t) * (nW + 1), cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_cam_win.p, h->cam_win_h.data(), sizeof(int32_t) * NC, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_pt_obs_off.p, h->pt_obs_off_int.data(), sizeof(int32_t) * ((size_t)NP + 1), cudaMemcpyHostToDevice, st));
+  if (NP) {
+    CU(h, cudaMemcpyAsync(h->d_pt_win.p, h->pt_win_h.data(), sizeof(int32_t) * NP, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->d_pt_order.p, h->pt_order.data(), sizeof(int32_t) * NP, cudaMemcpyHostToDevice, st));
+  }
+  if (NO) {
+    CU(h, cudaMemcpyAsync(h->d_feat.p, h->h_feat.p, sizeof(double) * NO * M, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->d_obs_cam.p, h->h_obs_cam.p, sizeof(int32_t) * NO, cudaMemcpyHostToDevice, st));
+  }
+  int rc = upload_state(h);
+  if (rc) return rc;
+  CU(h, cudaMemsetAsync(h->d_recs.p, 0, sizeof(IterRec) * (size_t)nW * rec_stride, st));
+  CU(h, cudaStreamSynchronize(st));
+  fill_view_static(h);
+  h->V.rec_stride = rec_stride;
+  h->ws_h.assign(nW, WinState{});
+  h->state = 1;
+  return UBA_OK;
+}
+
+// Ceres rejects a problem whose bounded parameter blocks start outside their box
+// ([CERES-UPSTREAM] Program::IsFeasible) -> the reference reports Status::FAILED.
+bool window_feasible(const uba_handle* h, int w) {
+  if (!h->cfg.use_bounds) return true;
+  const uba::Calib& k = h->V.calib;
+  for (int s = h->w_pt_off[w]; s < h->w_pt_off[w + 1]; s++) {
+    if (h->pt_obs_off_int[s + 1] == h->pt_obs_off_int[s]) continue;
+    for (int a = 0; a < 3; a++) {
+      const double x = h->h_pts.p[(size_t)s * 3 + a];
+      if (!(x >= k.lo[a] && x <= k.hi[a])) return false;
+    }
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uba_version(void) { return UBA_VERSION; }
+
+void uba_config_default(uba_config* c) {
+  if (!c) return;
+  std::memset(c, 0, sizeof(*c));
+  c->loss_kind = UBA_LOSS_HUBER;          // new ceres::HuberLoss(1.0), BundleAdjuster.h:397,:447
+  c->loss_scale = 1.0;
+  c->max_iterations = 50;                 // Ceres default
+  c->function_tolerance = 1e-3;           // :419,:466
+  c->gradient_tolerance = 1e-10;
+  c->parameter_tolerance = 1e-8;
+  c->initial_radius = 1e4;
+  c->max_radius = 1e16;
+  c->min_radius = 1e-32;
+  c->min_relative_decrease = 1e-3;
+  c->min_lm_diagonal = 1e-6;
+  c->max_lm_diagonal = 1e32;
+  c->max_consecutive_invalid_steps = 5;
+  c->max_solver_time_s = 1.0;             // :417,:464
+  c->fixed_iterations = 0;
+  c->jacobi_scaling = 1;
+  c->use_bounds = 1;                      // :455-460
+  const char* lr = std::getenv("LOCAL_RANK");
+  c->device = lr ? std::atoi(lr) : 0;
+  c->linearizer = 0;
+  c->compute_covariance = 0;              // CalibrationParameters::compute_cov defaults to false (:42-43)
+}
+
+const char* uba_last_error(const uba_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int uba_create(const uba_config* cfg, uba_handle** out) {
+  if (!out) return fail(nullptr, UBA_ERR_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  uba_config c;
+  if (cfg) c = *cfg; else uba_config_default(&c);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, UBA_ERR_CUDA, "no CUDA device (%s): libuba has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (c.device < 0 || c.device >= ndev) return fail(nullptr, UBA_ERR_INVALID_ARGUMENT, "device %d out of range (%d devices)", c.device, ndev);
+  e = cudaSetDevice(c.device);
+  if (e != cudaSuccess) return fail(nullptr, UBA_ERR_CUDA, "cudaSetDevice(%d): %s", c.device, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, c.device);
+  if (prop.major != 10) return fail(nullptr, UBA_ERR_CUDA, "device %d is sm_%d%d; libuba carries sm_100a code only", c.device, prop.major, prop.minor);
+  uba_handle* h = new uba_handle();
+  h->cfg = c; h->device = c.device;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, UBA_ERR_CUDA, "cudaStreamCreate failed"); }
+  for (auto& ev : h->ev) cudaEventCreate(&ev);
+  *out = h;
+  return UBA_OK;
+}
+
+void uba_destroy(uba_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
+  h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release();
+  h->d_cams.release(); h->d_camR.release(); h->d_cam_s2.release(); h->d_cam_lam.release(); h->d_cam_y.release(); h->d_pts.release();
+  h->d_pt_s2.release(); h->d_pt_rec.release(); h->d_feat.release(); h->d_acc.release(); h->d_A.release(); h->d_rhs.release();
+  h->d_Zbuf.release(); h->d_dbg.release(); h->d_export.release(); h->d_flush.release();
+  h->d_w_cam_off.release(); h->d_w_pt_off.release(); h->d_w_free_off.release(); h->d_free_list.release(); h->d_free_cam.release();
+  h->d_cam_win.release(); h->d_pt_obs_off.release(); h->d_pt_win.release(); h->d_obs_cam.release(); h->d_n_active.release();
+  h->d_pt_order.release(); h->d_w_red_off.release(); h->d_ws.release(); h->d_recs.release();
+  for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int uba_set_batch(uba_handle* h, int M, int n_windows, const int32_t* win_cam_off, const int32_t* win_pt_off,
+                  const int64_t* win_obs_off, const double* cams6, const double* pts3, const double* feats,
+                  const int32_t* cam_idx, const int32_t* pt_idx, const int32_t* cam_id, const uba_calib* calib) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  return build_problem(h, M, n_windows, win_cam_off, win_pt_off, win_obs_off, cams6, pts3, feats, cam_idx, pt_idx, cam_id, calib);
+}
+
+int uba_set_problem(uba_handle* h, int M, int n_cams, int n_pts, int n_obs, const double* cams6, const double* pts3,
+                    const double* feats, const int32_t* cam_idx, const int32_t* pt_idx, const int32_t* cam_id,
+                    const uba_calib* calib) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  if (n_cams <= 0 || n_pts <= 0) {
+    // "[Bundle Adjuster] system should be uninitialised and both cameras and points not empty!" (BundleAdjuster.h:314-316)
+    return fail(h, UBA_ERR_INVALID_ARGUMENT, "cameras and points must not be empty");
+  }
+  const int32_t wc[2] = {0, n_cams}, wp[2] = {0, n_pts};
+  const int64_t wo[2] = {0, n_obs};
+  cudaSetDevice(h->device);
+  return build_problem(h, M, 1, wc, wp, wo, cams6, pts3, feats, cam_idx, pt_idx, cam_id, calib);
+}
+
+int uba_get_sizes(const uba_handle* h, int* n_windows, int* n_cams, int* n_pts, int64_t* n_obs) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  if (n_windows) *n_windows = h->nW;
+  if (n_cams) *n_cams = h->NC;
+  if (n_pts) *n_pts = h->NP;
+  if (n_obs) *n_obs = h->NO;
+  return UBA_OK;
+}
+
+int uba_get_tables(uba_handle* h, int fixed_frames, int32_t* obs_order, int64_t* pt_obs_off, int32_t* pt_order, int32_t* free_cam) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  if (obs_order) std::memcpy(obs_order, h->obs_order.data(), sizeof(int32_t) * h->NO);
+  if (pt_obs_off) std::memcpy(pt_obs_off, h->pt_obs_off_caller.data(), sizeof(int64_t) * ((size_t)h->NP + 1));
+  if (pt_order) std::memcpy(pt_order, h->pt_order.data(), sizeof(int32_t) * h->NP);
+  if (free_cam) {
+    cudaSetDevice(h->device);
+    int rc = prepare(h, fixed_frames);
+    if (rc) return rc;
+    std::memcpy(free_cam, h->free_cam_h.data(), sizeof(int32_t) * h->NC);
+  }
+  return UBA_OK;
+}
+
+int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearization_out* out) {
+  if (!h || !out) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  cudaSetDevice(h->device);
+  const double saved_radius = h->cfg.initial_radius;
+  h->cfg.initial_radius = radius;
+  int rc = upload_state(h);
+  if (!rc) rc = start_solve(h, fixed_frames);
+  h->cfg.initial_radius = saved_radius;
+  if (rc) return rc;
+  const int M = h->M, NC = h->NC, NP = h->NP;
+  const int64_t NO = h->NO;
+  // debug scratch: residuals | weights | C | W | grad_pts | lam_pts
+  const size_t n_res = (size_t)NO * M, n_w = NO, n_C = (size_t)NP * 9, n_W = (size_t)NO * 18, n_g = (size_t)NP * 3, n_l = (size_t)NP * 3;
+  CU(h, h->d_dbg.reserve(n_res + n_w + n_C + n_W + n_g + n_l));
+  CU(h, cudaMemsetAsync(h->d_dbg.p, 0, (n_res + n_w + n_C + n_W + n_g + n_l) * sizeof(double), h->stream));
+  DebugOut D;
+  D.residuals = h->d_dbg.p; D.weights = D.residuals + n_res; D.C = D.weights + n_w; D.W = D.C + n_C; D.grad_pts = D.W + n_W; D.lam_pts = D.grad_pts + n_g;
+  rc = run_linearize(h, D);
+  if (rc) return rc;
+  h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaGetLastError());
+  std::vector<double> tmp;
+  auto fetch = [&](const double* dev, size_t n) -> const double* { tmp.resize(n); cudaMemcpy(tmp.data(), dev, n * sizeof(double), cudaMemcpyDeviceToHost); return tmp.data(); };
+  if (out->residuals) { const double* r = fetch(D.residuals, n_res); for (int64_t s = 0; s < NO; s++) std::memcpy(out->residuals + (size_t)h->obs_internal[s] * M, r + (size_t)s * M, sizeof(double) * M); }
+  if (out->weights) { const double* r = fetch(D.weights, n_w); for (int64_t s = 0; s < NO; s++) out->weights[h->obs_internal[s]] = r[s]; }
+  if (out->W) { const double* r = fetch(D.W, n_W); for (int64_t s = 0; s < NO; s++) std::memcpy(out->W + (size_t)h->obs_internal[s] * 18, r + (size_t)s * 18, sizeof(double) * 18); }
+  if (out->C) { const double* r = fetch(D.C, n_C); for (int s = 0; s < NP; s++) std::memcpy(out->C + (size_t)h->pt_order[s] * 9, r + (size_t)s * 9, sizeof(double) * 9); }
+  if (out->grad_pts) { const double* r = fetch(D.grad_pts, n_g); for (int s = 0; s < NP; s++) std::memcpy(out->grad_pts + (size_t)h->pt_order[s] * 3, r + (size_t)s * 3, sizeof(double) * 3); }
+  if (out->lm_diag_pts) { const double* r = fetch(D.lam_pts, n_l); for (int s = 0; s < NP; s++) std::memcpy(out->lm_diag_pts + (size_t)h->pt_order[s] * 3, r + (size_t)s * 3, sizeof(double) * 3); }
+  if (out->cost) { const double* r = fetch(h->V.w_lin, (size_t)h->nW * WL_COUNT); for (int w = 0; w < h->nW; w++) out->cost[w] = r[(size_t)w * WL_COUNT + WL_COST]; }
+  if (out->grad_cams) { const double* r = fetch(h->V.vacc, (size_t)NC * 6); std::memcpy(out->grad_cams, r, sizeof(double) * 6 * NC); }
+  if (out->lm_diag_cams) {
+    const double* r = fetch(h->V.cam_lam, (size_t)NC * 6);
+    for (int c = 0; c < NC; c++) for (int a = 0; a < 6; a++) out->lm_diag_cams[(size_t)c * 6 + a] = h->free_cam_h[c] >= 0 ? r[(size_t)c * 6 + a] : 0.0;
+  }
+  if (out->B) {
+    const double* r = fetch(h->V.Bacc, (size_t)NC * 36);
+    for (int c = 0; c < NC; c++) for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++)
+      out->B[(size_t)c * 36 + a * 6 + b] = r[(size_t)c * 36 + std::min(a, b) * 6 + std::max(a, b)];
+  }
+  if (out->S) { const double* r = fetch(h->V.A, (size_t)h->w_red_off_h[h->nW]); std::memcpy(out->S, r, sizeof(double) * h->w_red_off_h[h->nW]); }
+  if (out->rhs) { const double* r = fetch(h->V.rhs, h->free_list_h.size() * 6); std::memcpy(out->rhs, r, sizeof(double) * h->free_list_h.size() * 6); }
+  return UBA_OK;
+}
+
+int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  // "[Bundle Adjuster] system should be initiliased to perform optimisation!" (BundleAdjuster.h:381-384,:434-437)
+  if (h->state != 1) return fail(h, UBA_ERR_STATE, "system should be initialised to perform optimisation (state %d)", h->state);
+  cudaSetDevice(h->device);
+  const auto t_start = std::chrono::steady_clock::now();
+  cudaEventRecord(h->ev[2], h->stream);
+  int rc = start_solve(h, fixed_frames);
+  if (rc) return rc;
+  const bool fixedK = h->cfg.fixed_iterations > 0;
+  const int max_it = fixedK ? h->cfg.fixed_iterations : h->cfg.max_iterations;
+  const bool timed = !fixedK && h->cfg.max_solver_time_s > 0.0;
+  // infeasible windows fail before the first iteration
+  std::vector<char> infeasible(h->nW, 0);
+  bool any_infeasible = false;
+  for (int w = 0; w < h->nW; w++) if (!window_feasible(h, w)) { infeasible[w] = 1; any_infeasible = true; }
+  if (any_infeasible) {
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpy(h->ws_h.data(), h->d_ws.p, sizeof(WinState) * h->nW, cudaMemcpyDeviceToHost));
+    int n_act = 0;
+    for (int w = 0; w < h->nW; w++) { if (infeasible[w]) h->ws_h[w].done = UBA_TERM_FAILURE; else n_act++; }
+    CU(h, cudaMemcpy(h->d_ws.p, h->ws_h.data(), sizeof(WinState) * h->nW, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->d_n_active.p, &n_act, sizeof(int), cudaMemcpyHostToDevice));
+  }
+  bool time_capped = false;
+  for (int it = 0; it < max_it; it++) {
+    rc = run_iteration(h);
+    if (rc) return rc;
+    if (!fixedK) {
+      // convergence is decided on the device; the host only needs to know when every window is done
+      int n_act = 0;
+      CU(h, cudaMemcpyAsync(&n_act, h->d_n_active.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+      if (n_act <= 0) break;
+      if (timed && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() >= h->cfg.max_solver_time_s) { time_capped = true; break; }
+    }
+  }
+  cudaEventRecord(h->ev[3], h->stream);
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaGetLastError());
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
+  h->timing.total_ms += ms;
+  CU(h, cudaMemcpy(h->ws_h.data(), h->d_ws.p, sizeof(WinState) * h->nW, cudaMemcpyDeviceToHost));
+  int worst = UBA_OK;
+  for (int w = 0; w < h->nW; w++) {
+    WinState& s = h->ws_h[w];
+    if (s.done == 0) s.done = UBA_TERM_NO_CONVERGENCE;  // iteration or wall-clock cap (:417,:464): still usable
+    (void)time_capped;
+    if (summaries) {
+      uba_summary& o = summaries[w];
+      o.termination = s.done; o.usable = s.done != UBA_TERM_FAILURE; o.iterations = s.iter; o.successful_steps = s.n_success;
+      o.unsuccessful_steps = s.n_unsuccess; o.invalid_steps = s.n_invalid; o.initial_cost = s.initial_cost; o.final_cost = s.cost;
+      o.final_radius = s.radius; o.final_gradient_max_norm = s.gmax;
+    }
+    if (s.done == UBA_TERM_FAILURE) worst = infeasible[w] ? UBA_ERR_INFEASIBLE : UBA_ERR_NUMERICAL;
+  }
+  h->state = 2;
+  if (worst != UBA_OK) fail(h, worst, "at least one window did not produce a usable solution");
+  return worst;
+}
+
+int uba_get_cameras(uba_handle* h, double* cams6) {
+  if (!h || !cams6) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  cudaSetDevice(h->device);
+  if (h->state == 1) { std::memcpy(cams6, h->h_cams.p, sizeof(double) * 6 * h->NC); return UBA_OK; }
+  std::vector<double> both((size_t)h->NC * 12);
+  CU(h, cudaMemcpy(both.data(), h->d_cams.p, sizeof(double) * 12 * h->NC, cudaMemcpyDeviceToHost));
+  for (int c = 0; c < h->NC; c++) {
+    const WinState& s = h->ws_h[h->cam_win_h[c]];
+    const double* src = s.done == UBA_TERM_FAILURE ? h->h_cams.p + (size_t)c * 6 : both.data() + (size_t)s.cur * h->NC * 6 + (size_t)c * 6;
+    std::memcpy(cams6 + (size_t)c * 6, src, sizeof(double) * 6);
+  }
+  return UBA_OK;
+}
+
+int uba_get_points(uba_handle* h, double* pts3) {
+  if (!h || !pts3) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  cudaSetDevice(h->device);
+  const int NP = h->NP;
+  if (h->state == 1) {
+    for (int s = 0; s < NP; s++) std::memcpy(pts3 + (size_t)h->pt_order[s] * 3, h->h_pts.p + (size_t)s * 3, sizeof(double) * 3);
+    return UBA_OK;
+  }
+  CU(h, h->h_out.reserve((size_t)NP * 6));
+  CU(h, cudaMemcpy(h->h_out.p, h->d_pts.p, sizeof(double) * 6 * NP, cudaMemcpyDeviceToHost));
+#pragma omp parallel for schedule(static)
+  for (int s = 0; s < NP; s++) {
+    const WinState& st = h->ws_h[h->pt_win_h[s]];
+    const double* src = st.done == UBA_TERM_FAILURE ? h->h_pts.p + (size_t)s * 3 : h->h_out.p + (size_t)st.cur * NP * 3 + (size_t)s * 3;
+    std::memcpy(pts3 + (size_t)h->pt_order[s] * 3, src, sizeof(double) * 3);
+  }
+  return UBA_OK;
+}
+
+int uba_get_pose_covariances(uba_handle* h, double* cov36) {
+  if (!h || !cov36) return UBA_ERR_INVALID_ARGUMENT;
+  return fail(h, UBA_ERR_UNSUPPORTED, "pose covariance extraction (BundleAdjuster.h:478-528) is not implemented yet");
+}
+
+int uba_get_iterations(uba_handle* h, int window, uba_iteration* out, int max_records, int* n_records) {
+  if (!h || window < 0 || window >= h->nW) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state != 2) return fail(h, UBA_ERR_STATE, "optimise has not run");
+  cudaSetDevice(h->device);
+  const int n = std::min(h->ws_h[window].iter + 1, h->V.rec_stride);
+  if (n_records) *n_records = n;
+  if (out && max_records > 0) {
+    std::vector<IterRec> r(n);
+    CU(h, cudaMemcpy(r.data(), h->d_recs.p + (size_t)window * h->V.rec_stride, sizeof(IterRec) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n && i < max_records; i++) {
+      out[i].cost = r[i].cost; out[i].candidate_cost = r[i].candidate_cost; out[i].model_cost_change = r[i].model_cost_change;
+      out[i].relative_decrease = r[i].relative_decrease; out[i].radius = r[i].radius; out[i].step_norm = r[i].step_norm;
+      out[i].gradient_max_norm = r[i].gradient_max_norm; out[i].accepted = r[i].accepted; out[i].pad_ = 0;
+    }
+  }
+  return UBA_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------
+int uba_comm_unique_id(uba_handle* h, char id[UBA_NCCL_UNIQUE_ID_BYTES]) {
+  if (!h || !id) return UBA_ERR_INVALID_ARGUMENT;
+  std::string err;
+  if (!load_nccl(h->nccl, err)) return fail(h, UBA_ERR_NCCL, "%s", err.c_str());
+  Id128 u; std::memset(&u, 0, sizeof(u));
+  const int rc = h->nccl.GetUniqueId(&u);
+  if (rc != 0) return fail(h, UBA_ERR_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  std::memcpy(id, u.internal, UBA_NCCL_UNIQUE_ID_BYTES);
+  return UBA_OK;
+}
+
+int uba_comm_init(uba_handle* h, const char id[UBA_NCCL_UNIQUE_ID_BYTES], int rank, int n_ranks) {
+  if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return UBA_ERR_INVALID_ARGUMENT;
+  std::string err;
+  if (!load_nccl(h->nccl, err)) return fail(h, UBA_ERR_NCCL, "%s", err.c_str());
+  cudaSetDevice(h->device);
+  Id128 u; std::memcpy(u.internal, id, UBA_NCCL_UNIQUE_ID_BYTES);
+  const int rc = h->nccl.CommInitRank(&h->comm, n_ranks, u, rank);
+  if (rc != 0) { h->comm = nullptr; return fail(h, UBA_ERR_NCCL, "ncclCommInitRank failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?"); }
+  h->rank = rank; h->n_ranks = n_ranks;
+  return UBA_OK;
+}
+
+// ---- timing ------------------------------------------------------------------------------------
+int uba_set_profiling(uba_handle* h, int enabled) { if (!h) return UBA_ERR_INVALID_ARGUMENT; h->profiling = enabled != 0; return UBA_OK; }
+
+int uba_get_timing(uba_handle* h, uba_timing* out, int reset) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  if (out) *out = h->timing;
+  if (reset) std::memset(&h->timing, 0, sizeof(h->timing));
+  return UBA_OK;
+}
+
+static int flush_l2(uba_handle* h) {
+  const size_t n = (size_t)48 << 20;  // 384 MB of doubles > 126 MB L2
+  CU(h, h->d_flush.reserve(n));
+  h->timing.kernel_launches += launch_l2_flush(h->d_flush.p, n, h->stream);
+  return UBA_OK;
+}
+
+int uba_time_linearize(uba_handle* h, int fixed_frames, double radius, int repeats, int do_flush, double* ms_per_pass) {
+  if (!h || repeats <= 0 || !ms_per_pass) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  cudaSetDevice(h->device);
+  const double saved = h->cfg.initial_radius;
+  h->cfg.initial_radius = radius;
+  int rc = upload_state(h);
+  if (!rc) rc = start_solve(h, fixed_frames);
+  h->cfg.initial_radius = saved;
+  if (rc) return rc;
+  DebugOut none{};
+  double total = 0.0;
+  for (int r = 0; r < repeats; r++) {
+    if (do_flush) { rc = flush_l2(h); if (rc) return rc; }
+    CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
+    cudaEventRecord(h->ev[4], h->stream);
+    h->timing.kernel_launches += launch_lin_generic(h->V, none, h->stream);
+    h->timing.linearize_launches++;
+    cudaEventRecord(h->ev[5], h->stream);
+    CU(h, cudaEventSynchronize(h->ev[5]));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+    total += ms;
+  }
+  CU(h, cudaGetLastError());
+  *ms_per_pass = total / repeats;
+  return UBA_OK;
+}
+
+int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int do_flush, double* ms_per_iteration) {
+  if (!h || iterations <= 0 || !ms_per_iteration) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  cudaSetDevice(h->device);
+  const int saved_fixed = h->cfg.fixed_iterations;
+  h->cfg.fixed_iterations = iterations;  // no convergence tests: every iteration runs all phases
+  fill_view_static(h);
+  int rc = upload_state(h);
+  if (!rc) rc = start_solve(h, fixed_frames);
+  double total = 0.0;
+  for (int it = 0; it < iterations && !rc; it++) {
+    if (do_flush) rc = flush_l2(h);
+    if (rc) break;
+    cudaEventRecord(h->ev[4], h->stream);
+    rc = run_iteration(h);
+    cudaEventRecord(h->ev[5], h->stream);
+    if (rc) break;
+    if (cudaEventSynchronize(h->ev[5]) != cudaSuccess) { rc = fail(h, UBA_ERR_CUDA, "event sync failed"); break; }
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+    total += ms;
+  }
+  h->cfg.fixed_iterations = saved_fixed;
+  fill_view_static(h);
+  if (rc) return rc;
+  CU(h, cudaGetLastError());
+  *ms_per_iteration = total / iterations;
+  return UBA_OK;
+}
+
+// fp64 FMA peak probe (TFLOP/s), used for the second roofline ceiling of the lineariser
+int uba_probe_fp64_tflops(uba_handle* h, double* tflops) {
+  if (!h || !tflops) return UBA_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  CU(h, h->d_flush.reserve(1024));
+  const int iters = 200000;
+  launch_dfma_probe(h->d_flush.p, 1000, h->stream);
+  cudaEventRecord(h->ev[4], h->stream);
+  launch_dfma_probe(h->d_flush.p, iters, h->stream);
+  cudaEventRecord(h->ev[5], h->stream);
+  CU(h, cudaEventSynchronize(h->ev[5]));
+  float ms = 0; cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]);
+  const double flops = 2.0 * 8.0 * (double)iters * 256.0 * 148.0 * 8.0;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  h->timing.kernel_launches += 2;
+  return UBA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,869 @@
+// uba_kernels.cu — sm_100a CUDA kernels of the windowed bundle-adjustment inner loop.
+//
+// One LM iteration is the fixed launch sequence
+//   zero accumulators -> linearise (+ per-point Schur elimination) -> assemble reduced system
+//   -> dense Cholesky solve (+ candidate cameras) -> back-substitution + candidate cost -> LM controller
+// over ALL windows of the handle at once; the controller state lives on the device
+// (WinState), so a whole uba_optimise call needs no host round trip between iterations.
+//
+// What the reference does inside ceres::Solve (BundleAdjuster.h:422,:469) maps to:
+//   residual blocks + autodiff Jacobians + loss corrector  -> obs_linearize (uba_math.h)
+//   SchurEliminator (points are the e-blocks)              -> k_lin_generic / k_lin_tile
+//   LevenbergMarquardtStrategy diagonal                    -> lm_lambda, k_assemble
+//   sparse Cholesky of the reduced camera matrix           -> k_chol_small / k_chol_* (dense fp64)
+//   back substitution, candidate evaluation                -> k_backsub
+//   TrustRegionMinimizer accept / reject / radius          -> k_lm_update
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "uba_device.h"
+
+// UBA_EMU is defined ONLY by tests/emu (a serial host emulation of the thread-independent kernels,
+// used to debug host logic on a box without a GPU).  libuba.so is never built with it.
+#ifdef UBA_EMU
+#include "emu_launch.h"
+#else
+#define UBA_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
+#endif
+
+namespace uba {
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  // non-negative doubles order like their bit patterns
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+#ifndef UBA_EMU
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ bool warp_leader() { return (threadIdx.x & 31) == 0; }
+#endif
+
+// Adds v into acc[w][slot]; aggregates over the warp when every lane targets the same window.
+__device__ __forceinline__ void win_add(double* acc, int stride, int w, int slot, double v, bool active) {
+  const unsigned full = 0xffffffffu;
+  const int w0 = __shfl_sync(full, w, 0);
+  const bool uniform = __all_sync(full, w == w0);
+  if (uniform) {
+    const double s = warp_sum(active ? v : 0.0);
+    if (warp_leader() && s != 0.0) atomicAdd(&acc[(size_t)w0 * stride + slot], s);
+  } else if (active && v != 0.0) {
+    atomicAdd(&acc[(size_t)w * stride + slot], v);
+  }
+}
+__device__ __forceinline__ void win_max(double* acc, int w, double v, bool active) {
+  const unsigned full = 0xffffffffu;
+  const int w0 = __shfl_sync(full, w, 0);
+  const bool uniform = __all_sync(full, w == w0);
+  if (uniform) {
+    const double s = warp_max(active ? v : 0.0);
+    if (warp_leader() && s > 0.0) atomic_max_nonneg(&acc[w0], s);
+  } else if (active && v > 0.0) {
+    atomic_max_nonneg(&acc[w], v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera prologue: R, t, G = J_l(r) for every camera of the given parity buffer
+// ---------------------------------------------------------------------------------------------
+__global__ void k_cam_prep(DevView V, int parity) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= V.NC) return;
+  double out[kCamStride];
+  cam_derive(V.cams[parity] + (size_t)c * 6, out);
+  double* dst = V.camR[parity] + (size_t)c * kCamStride;
+#pragma unroll
+  for (int i = 0; i < kCamStride; i++) dst[i] = out[i];
+}
+
+__global__ void k_init_state(DevView V, double initial_radius) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= V.nW) return;
+  WinState s;
+  s.radius = initial_radius; s.decrease_factor = 2.0; s.cost = 0.0; s.gmax = 0.0; s.initial_cost = 0.0;
+  s.cur = 0; s.done = 0; s.iter = 0; s.n_success = 0; s.n_unsuccess = 0; s.n_invalid = 0; s.consecutive_invalid = 0;
+  s.scale_ready = 0; s.pad_[0] = 0; s.pad_[1] = 0;
+  V.ws[w] = s;
+  if (w == 0) *V.n_active = V.nW;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic lineariser: one thread per point, fp64 global atomics for the camera-indexed sums.
+// Works for any track length and any visibility pattern; the tiled kernel (k_lin_tile) is the
+// fast path and this one is its fallback and the parity/debug path (DebugOut).
+// ---------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D) {
+  constexpr int NR = (M == 4) ? 3 : 2;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = p < V.NP;
+  int w = in_range ? V.pt_win[p] : V.pt_win[V.NP - 1];
+  const WinState* st = &V.ws[w];
+  const bool live = in_range && st->done == 0;
+  int o0 = 0, o1 = 0;
+  if (live) { o0 = V.pt_obs_off[p]; o1 = V.pt_obs_off[p + 1]; }
+  const bool active = live && o1 > o0;
+  double cost = 0.0, gmax = 0.0, fail = 0.0;
+  if (active) {
+    const int cur = st->cur;
+    const double radius = st->radius;
+    const int cbase = V.w_cam_off[w];
+    const double* camR = V.camR[cur];
+    const double X[3] = {V.pts[cur][(size_t)p * 3], V.pts[cur][(size_t)p * 3 + 1], V.pts[cur][(size_t)p * 3 + 2]};
+    double C6[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+    for (int o = o0; o < o1; o++) {
+      const int oc = V.obs_cam[o];
+      const int gc = cbase + (oc & 0x3fffffff);
+      double f[M];
+#pragma unroll
+      for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
+      double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
+      const double rho0 = obs_linearize<M>(camR + (size_t)gc * kCamStride, X, f, (oc >> 30) & 1, V.calib, V.loss, rraw, wgt, F, E, rh);
+      cost += 0.5 * rho0;
+#pragma unroll
+      for (int a = 0; a < NR; a++) {
+        C6[0] += E[a][0] * E[a][0]; C6[1] += E[a][0] * E[a][1]; C6[2] += E[a][0] * E[a][2];
+        C6[3] += E[a][1] * E[a][1]; C6[4] += E[a][1] * E[a][2]; C6[5] += E[a][2] * E[a][2];
+        g[0] += E[a][0] * rh[a]; g[1] += E[a][1] * rh[a]; g[2] += E[a][2] * rh[a];
+      }
+      if (V.free_cam[gc] >= 0) {
+        double* B = V.Bacc + (size_t)gc * 36;
+        double* v = V.vacc + (size_t)gc * 6;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          double vr = 0.0;
+#pragma unroll
+          for (int a = 0; a < NR; a++) vr += F[a][r] * rh[a];
+          atomicAdd(&v[r], vr);
+#pragma unroll
+          for (int c = r; c < 6; c++) {
+            double b = 0.0;
+#pragma unroll
+            for (int a = 0; a < NR; a++) b += F[a][r] * F[a][c];
+            atomicAdd(&B[r * 6 + c], b);
+          }
+        }
+      }
+      if (D.residuals) {
+#pragma unroll
+        for (int m = 0; m < M; m++) D.residuals[(size_t)o * M + m] = rraw[m];
+      }
+      if (D.weights) D.weights[o] = wgt;
+    }
+    // Jacobi scale (captured at the first linearisation) and LM damping of the point block
+    double s2[3], lam[3];
+    const double Cd[3] = {C6[0], C6[3], C6[5]};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      if (!st->scale_ready) { s2[c] = jacobi_s2(Cd[c], V.cfg.jacobi_scaling); V.pt_s2[(size_t)p * 3 + c] = s2[c]; }
+      else s2[c] = V.pt_s2[(size_t)p * 3 + c];
+      lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+    }
+    if (D.C) {
+      double* Cp = D.C + (size_t)p * 9;
+      Cp[0] = C6[0]; Cp[1] = C6[1]; Cp[2] = C6[2]; Cp[3] = C6[1]; Cp[4] = C6[3]; Cp[5] = C6[4]; Cp[6] = C6[2]; Cp[7] = C6[4]; Cp[8] = C6[5];
+    }
+    if (D.grad_pts) { D.grad_pts[(size_t)p * 3] = g[0]; D.grad_pts[(size_t)p * 3 + 1] = g[1]; D.grad_pts[(size_t)p * 3 + 2] = g[2]; }
+    if (D.lam_pts) { D.lam_pts[(size_t)p * 3] = lam[0]; D.lam_pts[(size_t)p * 3 + 1] = lam[1]; D.lam_pts[(size_t)p * 3 + 2] = lam[2]; }
+    const double Cdamp[6] = {C6[0] + lam[0], C6[1], C6[2], C6[3] + lam[1], C6[4], C6[5] + lam[2]};
+    double Li[6], h[3];
+    double* rec = V.pt_rec + (size_t)p * kPtRec;
+    if (!point_factor(Cdamp, Li)) {
+      fail = 1.0;
+#pragma unroll
+      for (int i = 0; i < kPtRec; i++) rec[i] = 0.0;
+    } else {
+      linv_mul(Li, g, h);
+#pragma unroll
+      for (int i = 0; i < 6; i++) rec[i] = Li[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { rec[6 + i] = h[i]; rec[9 + i] = g[i]; rec[12 + i] = lam[i]; }
+      rec[15] = 0.0;
+      // projected-gradient max norm, point part
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const double proj = V.cfg.use_bounds ? clampd(X[c] - g[c], V.calib.lo[c], V.calib.hi[c]) : X[c] - g[c];
+        gmax = fmax(gmax, fabs(X[c] - proj));
+      }
+      // second pass: Z = W Linv^T per free-camera observation, Schur outer products
+      const int64_t red = V.w_red_off[w];
+      const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+      double* S = V.Sacc + red;
+      for (int o = o0; o < o1; o++) {
+        const int oc = V.obs_cam[o];
+        const int gc = cbase + (oc & 0x3fffffff);
+        const int fb = V.free_cam[gc];
+        if (fb < 0 && !D.W) continue;
+        double f[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
+        double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
+        obs_linearize<M>(camR + (size_t)gc * kCamStride, X, f, (oc >> 30) & 1, V.calib, V.loss, rraw, wgt, F, E, rh);
+        if (D.W) {
+          double* Wp = D.W + (size_t)o * 18;
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              double s = 0.0;
+#pragma unroll
+              for (int a = 0; a < NR; a++) s += F[a][r] * E[a][c];
+              Wp[r * 3 + c] = fb >= 0 ? s : 0.0;
+            }
+        }
+        if (fb < 0) continue;
+        double Zb[18];
+        obs_schur_factor<NR>(F, E, Li, Zb);
+        double* zo = V.Zbuf + (size_t)o * 18;
+#pragma unroll
+        for (int i = 0; i < 18; i++) zo[i] = Zb[i];
+        double* zh = V.zh + (size_t)gc * 6;
+#pragma unroll
+        for (int r = 0; r < 6; r++) atomicAdd(&zh[r], Zb[r * 3] * h[0] + Zb[r * 3 + 1] * h[1] + Zb[r * 3 + 2] * h[2]);
+        for (int oa = o0; oa <= o; oa++) {
+          const int gca = cbase + (V.obs_cam[oa] & 0x3fffffff);
+          const int fa = V.free_cam[gca];
+          if (fa < 0) continue;
+          double Za[18];
+          if (oa == o) {
+#pragma unroll
+            for (int i = 0; i < 18; i++) Za[i] = Zb[i];
+          } else {
+            const double* za = V.Zbuf + (size_t)oa * 18;
+#pragma unroll
+            for (int i = 0; i < 18; i++) Za[i] = za[i];
+          }
+          // block (fa, fb) with fa <= fb: observations of a point are camera-ascending
+          double* blk = S + (size_t)(6 * fa) * n + 6 * fb;
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++)
+            {
+              double v = Za[r * 3] * Zb[c * 3] + Za[r * 3 + 1] * Zb[c * 3 + 1] + Za[r * 3 + 2] * Zb[c * 3 + 2];
+              if (fa == fb && oa != o)  // one camera seen twice by this point: add the transposed product too
+                v += Zb[r * 3] * Za[c * 3] + Zb[r * 3 + 1] * Za[c * 3 + 1] + Zb[r * 3 + 2] * Za[c * 3 + 2];
+              atomicAdd(&blk[(size_t)r * n + c], v);
+            }
+        }
+      }
+    }
+  }
+  win_add(V.w_lin, WL_COUNT, w, WL_COST, cost, active);
+  win_add(V.w_lin, WL_COUNT, w, WL_FAIL, fail, active);
+  win_max(V.w_max, w, gmax, active);
+}
+
+// ---------------------------------------------------------------------------------------------
+// assemble the damped reduced camera system  A = B + Lambda_c - sum_j Z Z^T,  rhs = v - sum_j Z h
+// grid: (blocks, nW)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_assemble(DevView V) {
+  const int w = blockIdx.y;
+  WinState* st = &V.ws[w];
+  if (st->done) return;
+  const int f0 = V.w_free_off[w];
+  const int nf = V.w_free_off[w + 1] - f0;
+  const int n = 6 * nf;
+  if (n == 0) return;
+  const int64_t red = V.w_red_off[w];
+  const double* S = V.Sacc + red;
+  double* A = V.A + red;
+  double* rhs = V.rhs + (size_t)6 * f0;
+  const double radius = st->radius;
+  const int64_t total = (int64_t)n * n + n;
+  double gmax = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    if (e < (int64_t)n * n) {
+      const int i = (int)(e / n), j = (int)(e % n);
+      const int fa = i / 6, r = i % 6, fb = j / 6, c = j % 6;
+      double val;
+      if (fa == fb) {
+        const int gc = V.free_list[f0 + fa];
+        const double* B = V.Bacc + (size_t)gc * 36;
+        const int rr = r < c ? r : c, cc = r < c ? c : r;
+        val = B[rr * 6 + cc] - S[(size_t)(6 * fa + rr) * n + 6 * fa + cc];
+        if (r == c) {
+          const double d = B[r * 6 + r];
+          double s2;
+          if (!st->scale_ready) { s2 = jacobi_s2(d, V.cfg.jacobi_scaling); V.cam_s2[(size_t)gc * 6 + r] = s2; }
+          else s2 = V.cam_s2[(size_t)gc * 6 + r];
+          const double lam = lm_lambda(d, s2, radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+          V.cam_lam[(size_t)gc * 6 + r] = lam;
+          val += lam;
+        }
+      } else if (fa < fb) {
+        val = -S[(size_t)i * n + j];
+      } else {
+        val = -S[(size_t)j * n + i];
+      }
+      A[(size_t)i * n + j] = val;
+    } else {
+      const int i = (int)(e - (int64_t)n * n);
+      const int gc = V.free_list[f0 + i / 6];
+      const double v = V.vacc[(size_t)gc * 6 + i % 6];
+      rhs[i] = v - V.zh[(size_t)gc * 6 + i % 6];
+      gmax = fmax(gmax, fabs(v));
+    }
+  }
+  gmax = warp_max(gmax);
+  if (warp_leader() && gmax > 0.0) atomic_max_nonneg(&V.w_max[w], gmax);
+}
+
+#ifndef UBA_EMU
+// ---------------------------------------------------------------------------------------------
+// dense Cholesky solve, one CTA per window, matrix resident in shared memory (n <= max_n)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.x;
+  WinState* st = &V.ws[w];
+  if (st->done) return;
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  if (n == 0 || n > max_n) return;
+  const int ld = n + 1;
+  double* a = sm;               // [n][ld]
+  double* y = sm + (size_t)n * ld;  // [n]
+  __shared__ int s_fail;
+  const double* A = V.A + V.w_red_off[w];
+  double* rhs = V.rhs + (size_t)6 * f0;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) s_fail = 0;
+  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j <= i) a[i * ld + j] = A[(size_t)i * n + j]; }
+  for (int i = tid; i < n; i += nt) y[i] = rhs[i];
+  __syncthreads();
+  // right-looking column Cholesky (lower)
+  for (int j = 0; j < n; j++) {
+    if (tid == 0) {
+      const double d = a[j * ld + j];
+      if (!(d > 0.0) || !isfinite(d)) { s_fail = 1; a[j * ld + j] = 1.0; }
+      else a[j * ld + j] = sqrt(d);
+    }
+    __syncthreads();
+    const double dinv = 1.0 / a[j * ld + j];
+    for (int i = j + 1 + tid; i < n; i += nt) a[i * ld + j] *= dinv;
+    __syncthreads();
+    const int m = n - j - 1;
+    // trailing update of the lower triangle: rows i > j, cols j < k <= i
+    for (int e = tid; e < m * m; e += nt) {
+      const int ii = e / m, kk = e % m;
+      if (kk <= ii) { const int i = j + 1 + ii, k = j + 1 + kk; a[i * ld + k] -= a[i * ld + j] * a[k * ld + j]; }
+    }
+    __syncthreads();
+  }
+  // forward / backward substitution by one warp (n is small)
+  if (tid < 32) {
+    for (int i = 0; i < n; i++) {
+      double s = 0.0;
+      for (int k = tid; k < i; k += 32) s += a[i * ld + k] * y[k];
+      s = warp_sum(s);
+      if (tid == 0) y[i] = (y[i] - s) / a[i * ld + i];
+      __syncwarp();
+    }
+    for (int i = n - 1; i >= 0; i--) {
+      double s = 0.0;
+      for (int k = i + 1 + tid; k < n; k += 32) s += a[k * ld + i] * y[k];
+      s = warp_sum(s);
+      if (tid == 0) y[i] = (y[i] - s) / a[i * ld + i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const bool failed = s_fail != 0;
+  for (int i = tid; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
+  // keep the factor for the covariance extraction
+  double* Aout = V.A + V.w_red_off[w];
+  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j <= i) Aout[(size_t)i * n + j] = a[i * ld + j]; }
+  if (tid == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
+}
+
+// ---- large windows: blocked right-looking Cholesky in global memory (lower triangle of A) -----
+constexpr int NB = 32;
+
+__global__ void __launch_bounds__(256) k_chol_diag(DevView V, int w, int j0) {
+  __shared__ double a[NB][NB + 1];
+  __shared__ int s_fail;
+  const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+  double* A = V.A + V.w_red_off[w];
+  const int nb = min(NB, n - j0);
+  const int tid = threadIdx.x;
+  if (tid == 0) s_fail = 0;
+  for (int e = tid; e < nb * nb; e += blockDim.x) { const int i = e / nb, j = e % nb; a[i][j] = A[(size_t)(j0 + i) * n + j0 + j]; }
+  __syncthreads();
+  for (int j = 0; j < nb; j++) {
+    if (tid == 0) {
+      const double d = a[j][j];
+      if (!(d > 0.0) || !isfinite(d)) { s_fail = 1; a[j][j] = 1.0; } else a[j][j] = sqrt(d);
+    }
+    __syncthreads();
+    const double dinv = 1.0 / a[j][j];
+    for (int i = j + 1 + tid; i < nb; i += blockDim.x) a[i][j] *= dinv;
+    __syncthreads();
+    const int m = nb - j - 1;
+    for (int e = tid; e < m * m; e += blockDim.x) {
+      const int ii = e / m, kk = e % m;
+      if (kk <= ii) a[j + 1 + ii][j + 1 + kk] -= a[j + 1 + ii][j] * a[j + 1 + kk][j];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < nb * nb; e += blockDim.x) { const int i = e / nb, j = e % nb; if (j <= i) A[(size_t)(j0 + i) * n + j0 + j] = a[i][j]; }
+  if (tid == 0 && s_fail) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
+}
+
+// rows below the panel: X L^T = A  ->  X   (each CTA: NB rows)
+__global__ void __launch_bounds__(256) k_chol_trsm(DevView V, int w, int j0) {
+  __shared__ double l[NB][NB + 1];
+  __shared__ double x[NB][NB + 1];
+  const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+  double* A = V.A + V.w_red_off[w];
+  const int nb = min(NB, n - j0);
+  const int i0 = j0 + nb + blockIdx.x * NB;
+  if (i0 >= n) return;
+  const int nr = min(NB, n - i0);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < nb * nb; e += blockDim.x) { const int i = e / nb, j = e % nb; l[i][j] = A[(size_t)(j0 + i) * n + j0 + j]; }
+  for (int e = tid; e < nr * nb; e += blockDim.x) { const int i = e / nb, j = e % nb; x[i][j] = A[(size_t)(i0 + i) * n + j0 + j]; }
+  __syncthreads();
+  // each thread (row i < nr) solves its own row sequentially: x[i][:] L^T = a[i][:]
+  if (tid < nr) {
+    for (int j = 0; j < nb; j++) {
+      double s = x[tid][j];
+      for (int k = 0; k < j; k++) s -= x[tid][k] * l[j][k];
+      x[tid][j] = s / l[j][j];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nr * nb; e += blockDim.x) { const int i = e / nb, j = e % nb; A[(size_t)(i0 + i) * n + j0 + j] = x[i][j]; }
+}
+
+// trailing update: A[bi][bj] -= L[bi][panel] L[bj][panel]^T for tiles bi >= bj below the panel
+__global__ void __launch_bounds__(256) k_chol_update(DevView V, int w, int j0) {
+  __shared__ double li[NB][NB + 1];
+  __shared__ double lj[NB][NB + 1];
+  const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+  double* A = V.A + V.w_red_off[w];
+  const int nb = min(NB, n - j0);
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  const int i0 = j0 + nb + bi * NB, c0 = j0 + nb + bj * NB;
+  if (i0 >= n) return;
+  const int nr = min(NB, n - i0), nc = min(NB, n - c0);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < nr * nb; e += blockDim.x) { const int i = e / nb, k = e % nb; li[i][k] = A[(size_t)(i0 + i) * n + j0 + k]; }
+  for (int e = tid; e < nc * nb; e += blockDim.x) { const int i = e / nb, k = e % nb; lj[i][k] = A[(size_t)(c0 + i) * n + j0 + k]; }
+  __syncthreads();
+  for (int e = tid; e < nr * nc; e += blockDim.x) {
+    const int i = e / nc, j = e % nc;
+    if (c0 + j > i0 + i) continue;
+    double s = 0.0;
+    for (int k = 0; k < nb; k++) s += li[i][k] * lj[j][k];
+    A[(size_t)(i0 + i) * n + c0 + j] -= s;
+  }
+}
+
+// blocked forward + backward substitution with the factor in global memory; one CTA
+__global__ void __launch_bounds__(1024) k_trsv_large(DevView V, int w) {
+  extern __shared__ double y[];  // [n]
+  __shared__ double l[NB][NB + 1];
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const double* A = V.A + V.w_red_off[w];
+  double* rhs = V.rhs + (size_t)6 * f0;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < n; i += nt) y[i] = rhs[i];
+  __syncthreads();
+  // forward: L z = b
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    const int nb = min(NB, n - j0);
+    for (int e = tid; e < nb * nb; e += nt) { const int i = e / nb, j = e % nb; l[i][j] = A[(size_t)(j0 + i) * n + j0 + j]; }
+    __syncthreads();
+    if (tid < 32) {
+      for (int i = 0; i < nb; i++) {
+        double s = (tid < i) ? l[i][tid] * y[j0 + tid] : 0.0;
+        s = warp_sum(s);
+        if (tid == 0) y[j0 + i] = (y[j0 + i] - s) / l[i][i];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int i = j0 + nb + tid; i < n; i += nt) {
+      double s = 0.0;
+      const double* row = A + (size_t)i * n + j0;
+      for (int k = 0; k < nb; k++) s += row[k] * y[j0 + k];
+      y[i] -= s;
+    }
+    __syncthreads();
+  }
+  // backward: L^T x = z
+  for (int j0 = ((n - 1) / NB) * NB; j0 >= 0; j0 -= NB) {
+    const int nb = min(NB, n - j0);
+    for (int e = tid; e < nb * nb; e += nt) { const int i = e / nb, j = e % nb; l[i][j] = A[(size_t)(j0 + i) * n + j0 + j]; }
+    __syncthreads();
+    if (tid < 32) {
+      for (int i = nb - 1; i >= 0; i--) {
+        double s = (tid > i && tid < nb) ? l[tid][i] * y[j0 + tid] : 0.0;
+        s = warp_sum(s);
+        if (tid == 0) y[j0 + i] = (y[j0 + i] - s) / l[i][i];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // y[i] -= sum_k L[j0+k][i] * y[j0+k] for i < j0
+    for (int i = tid; i < j0; i += nt) {
+      double s = 0.0;
+      for (int k = 0; k < nb; k++) s += A[(size_t)(j0 + k) * n + i] * y[j0 + k];
+      y[i] -= s;
+    }
+    __syncthreads();
+  }
+  const bool failed = V.w_loc[(size_t)w * WC_COUNT + WC_FAIL] > 0.0;
+  for (int i = tid; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
+}
+
+#else
+constexpr int NB = 32;
+#endif  // !UBA_EMU
+
+// ---------------------------------------------------------------------------------------------
+// solve epilogue: camera step, candidate cameras (+ their R, t, G), camera part of the model change
+// grid: nW blocks
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_solve_epilogue(DevView V) {
+  const int w = blockIdx.x;
+  WinState* st = &V.ws[w];
+  if (st->done) return;
+  const int cur = st->cur, nxt = cur ^ 1;
+  const int c0 = V.w_cam_off[w], c1 = V.w_cam_off[w + 1];
+  const int f0 = V.w_free_off[w];
+  const double* y = V.rhs + (size_t)6 * f0;
+  double mc = 0.0, step2 = 0.0, x2 = 0.0;
+  for (int gc = c0 + threadIdx.x; gc < c1; gc += blockDim.x) {
+    const int f = V.free_cam[gc];
+    double cand[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      const double x = V.cams[cur][(size_t)gc * 6 + a];
+      double yv = 0.0;
+      if (f >= 0) {
+        yv = y[f * 6 + a];
+        mc += yv * V.vacc[(size_t)gc * 6 + a] + V.cam_lam[(size_t)gc * 6 + a] * yv * yv;
+        x2 += x * x;
+      }
+      cand[a] = x - yv;
+      if (f >= 0) step2 += (x - cand[a]) * (x - cand[a]);
+      V.cam_y[(size_t)gc * 6 + a] = yv;
+      V.cams[nxt][(size_t)gc * 6 + a] = cand[a];
+    }
+    double out[kCamStride];
+    cam_derive(cand, out);
+    double* dst = V.camR[nxt] + (size_t)gc * kCamStride;
+#pragma unroll
+    for (int i = 0; i < kCamStride; i++) dst[i] = out[i];
+  }
+  mc = warp_sum(mc); step2 = warp_sum(step2); x2 = warp_sum(x2);
+  if (warp_leader()) {
+    double* acc = V.w_loc + (size_t)w * WC_COUNT;
+    if (mc != 0.0) atomicAdd(&acc[WC_MCCAM], mc);
+    if (step2 != 0.0) atomicAdd(&acc[WC_STEP2], step2);
+    if (x2 != 0.0) atomicAdd(&acc[WC_X2], x2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// back-substitution + candidate point + candidate cost; one thread per point
+// ---------------------------------------------------------------------------------------------
+template <int M>
+__global__ void __launch_bounds__(128) k_backsub(DevView V) {
+  constexpr int NR = (M == 4) ? 3 : 2;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = p < V.NP;
+  int w = in_range ? V.pt_win[p] : V.pt_win[V.NP - 1];
+  const WinState* st = &V.ws[w];
+  const bool live = in_range && st->done == 0;
+  double mc = 0.0, step2 = 0.0, x2 = 0.0, cnew = 0.0;
+  bool active = false;
+  if (live) {
+    const int cur = st->cur, nxt = cur ^ 1;
+    const int o0 = V.pt_obs_off[p], o1 = V.pt_obs_off[p + 1];
+    const double X[3] = {V.pts[cur][(size_t)p * 3], V.pts[cur][(size_t)p * 3 + 1], V.pts[cur][(size_t)p * 3 + 2]};
+    double Xn[3] = {X[0], X[1], X[2]};
+    if (o1 > o0) {
+      active = true;
+      const int cbase = V.w_cam_off[w];
+      const double* camR = V.camR[cur];
+      double t3[3] = {0, 0, 0};
+      for (int o = o0; o < o1; o++) {
+        const int oc = V.obs_cam[o];
+        const int gc = cbase + (oc & 0x3fffffff);
+        if (V.free_cam[gc] < 0) continue;
+        double f[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
+        double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
+        obs_linearize<M>(camR + (size_t)gc * kCamStride, X, f, (oc >> 30) & 1, V.calib, V.loss, rraw, wgt, F, E, rh);
+        const double* yc = V.cam_y + (size_t)gc * 6;
+#pragma unroll
+        for (int a = 0; a < NR; a++) {
+          double fy = 0.0;
+#pragma unroll
+          for (int r = 0; r < 6; r++) fy += F[a][r] * yc[r];
+          t3[0] += E[a][0] * fy; t3[1] += E[a][1] * fy; t3[2] += E[a][2] * fy;
+        }
+      }
+      const double* rec = V.pt_rec + (size_t)p * kPtRec;
+      double Li[6], h[3], g[3], lam[3];
+#pragma unroll
+      for (int i = 0; i < 6; i++) Li[i] = rec[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { h[i] = rec[6 + i]; g[i] = rec[9 + i]; lam[i] = rec[12 + i]; }
+      double u[3], yp[3];
+      linv_mul(Li, t3, u);
+      u[0] = h[0] - u[0]; u[1] = h[1] - u[1]; u[2] = h[2] - u[2];
+      linvT_mul(Li, u, yp);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        double v = X[c] - yp[c];
+        if (V.cfg.use_bounds) v = clampd(v, V.calib.lo[c], V.calib.hi[c]);
+        Xn[c] = v;
+        mc += yp[c] * g[c] + lam[c] * yp[c] * yp[c];
+        step2 += (X[c] - v) * (X[c] - v);
+        x2 += X[c] * X[c];
+      }
+      // candidate cost at (candidate cameras, candidate point)
+      const double* camRn = V.camR[nxt];
+      for (int o = o0; o < o1; o++) {
+        const int oc = V.obs_cam[o];
+        const int gc = cbase + (oc & 0x3fffffff);
+        double f[M];
+#pragma unroll
+        for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
+        double rraw[M];
+        const double s = obs_residual<M>(camRn + (size_t)gc * kCamStride, Xn, f, (oc >> 30) & 1, V.calib, rraw);
+        double rho0, rho1;
+        loss_eval(V.loss, s, rho0, rho1);
+        cnew += 0.5 * rho0;
+      }
+    }
+    V.pts[nxt][(size_t)p * 3] = Xn[0]; V.pts[nxt][(size_t)p * 3 + 1] = Xn[1]; V.pts[nxt][(size_t)p * 3 + 2] = Xn[2];
+  }
+  win_add(V.w_post, WP_COUNT, w, WP_MCPT, mc, active);
+  win_add(V.w_post, WP_COUNT, w, WP_STEP2, step2, active);
+  win_add(V.w_post, WP_COUNT, w, WP_X2, x2, active);
+  win_add(V.w_post, WP_COUNT, w, WP_COSTNEW, cnew, active);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LM controller: [CERES-UPSTREAM] TrustRegionMinimizer + LevenbergMarquardtStrategy rules
+// ---------------------------------------------------------------------------------------------
+__global__ void k_lm_update(DevView V) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= V.nW) return;
+  WinState st = V.ws[w];
+  if (st.done) return;
+  const double* alin = V.w_lin + (size_t)w * WL_COUNT;
+  const double* apost = V.w_post + (size_t)w * WP_COUNT;
+  const double* aloc = V.w_loc + (size_t)w * WC_COUNT;
+  const SolverCfg& C = V.cfg;
+  const double cost = alin[WL_COST];
+  const double gmax = V.w_max[w];
+  IterRec* recs = V.recs + (size_t)w * V.rec_stride;
+  const bool fixedK = C.fixed_iterations > 0;
+  const int max_it = fixedK ? C.fixed_iterations : C.max_iterations;
+  st.cost = cost; st.gmax = gmax;
+  if (st.iter == 0) {
+    st.initial_cost = cost;
+    IterRec r0; r0.cost = cost; r0.candidate_cost = cost; r0.model_cost_change = 0; r0.relative_decrease = 0; r0.radius = st.radius;
+    r0.step_norm = 0; r0.gradient_max_norm = gmax; r0.accepted = 1; r0.pad_ = 0;
+    recs[0] = r0;
+  } else if (st.iter < V.rec_stride && recs[st.iter].accepted == 1) {
+    recs[st.iter].gradient_max_norm = gmax;  // gradient at the iterate accepted last iteration
+  }
+  int done = 0;
+  if (!isfinite(cost)) done = 5;                                      // UBA_TERM_FAILURE
+  else if (!fixedK && gmax <= C.gradient_tolerance) done = 2;         // CONVERGENCE_GRADIENT
+  if (!done) {
+    const int it = st.iter + 1;
+    st.iter = it;
+    IterRec r; r.cost = cost; r.candidate_cost = cost; r.model_cost_change = 0; r.relative_decrease = 0; r.radius = st.radius;
+    r.step_norm = 0; r.gradient_max_norm = gmax; r.accepted = 0; r.pad_ = 0;
+    const double mc = 0.5 * (apost[WP_MCPT] + aloc[WC_MCCAM]);
+    const bool fail = alin[WL_FAIL] > 0.0 || aloc[WC_FAIL] > 0.0;
+    r.model_cost_change = mc;
+    if (fail || !(mc > 0.0)) {
+      r.accepted = -1;
+      st.n_invalid++;
+      st.consecutive_invalid++;
+      if (st.consecutive_invalid >= C.max_consecutive_invalid_steps && !fixedK) done = 5;
+      else st.radius *= 0.5;
+    } else {
+      st.consecutive_invalid = 0;
+      const double cand = apost[WP_COSTNEW];
+      const double step_norm = sqrt(apost[WP_STEP2] + aloc[WC_STEP2]);
+      const double x_norm = sqrt(apost[WP_X2] + aloc[WC_X2]);
+      const double cost_change = cost - cand;
+      const double rel = cost_change / mc;
+      r.candidate_cost = cand; r.step_norm = step_norm; r.relative_decrease = rel;
+      if (!fixedK && step_norm <= C.parameter_tolerance * (x_norm + C.parameter_tolerance)) done = 3;
+      else if (!fixedK && fabs(cost_change) <= C.function_tolerance * cost) done = 1;
+      else if (isfinite(cand) && rel > C.min_relative_decrease) {
+        st.cur ^= 1;
+        st.cost = cand;
+        st.n_success++;
+        r.accepted = 1; r.cost = cand;
+        const double q = 2.0 * rel - 1.0;
+        st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - q * q * q);
+        st.radius = fmin(C.max_radius, st.radius);
+        st.decrease_factor = 2.0;
+      } else {
+        st.n_unsuccess++;
+        st.radius = st.radius / st.decrease_factor;
+        st.decrease_factor *= 2.0;
+        if (!fixedK && st.radius < C.min_radius) done = 6;
+      }
+    }
+    if (it < V.rec_stride) recs[it] = r;
+    if (!done && it >= max_it) done = 4;  // NO_CONVERGENCE: iteration cap
+  }
+  st.scale_ready = 1;
+  st.done = done;
+  V.ws[w] = st;
+  if (done) atomicSub(V.n_active, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------------------
+__global__ void k_l2_flush(double* buf, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = (double)i;
+}
+
+// fp64 FMA throughput probe: 8 independent chains per thread.  out[0] keeps the compiler honest.
+__global__ void __launch_bounds__(256) k_dfma_probe(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+int launch_cam_prep(const DevView& V, int parity, cudaStream_t st) {
+  if (V.NC == 0) return 0;
+  UBA_LAUNCH(k_cam_prep, (V.NC + 127) / 128, 128, 0, st, V, parity);
+  return 1;
+}
+
+int launch_init_state(const DevView& V, double initial_radius, cudaStream_t st) {
+  UBA_LAUNCH(k_init_state, (V.nW + 127) / 128, 128, 0, st, V, initial_radius);
+  return 1;
+}
+
+int launch_lin_generic(const DevView& V, const DebugOut& dbg, cudaStream_t st) {
+  if (V.NP == 0) return 0;
+  const int grid = (V.NP + 127) / 128;
+  if (V.M == 4) UBA_LAUNCH(k_lin_generic<4>, grid, 128, 0, st, V, dbg);
+  else UBA_LAUNCH(k_lin_generic<2>, grid, 128, 0, st, V, dbg);
+  return 1;
+}
+
+int launch_assemble(const DevView& V, int max_n, cudaStream_t st) {
+  if (max_n == 0) return 0;
+  const int64_t total = (int64_t)max_n * max_n + max_n;
+  int bx = (int)((total + 255) / 256);
+  if (bx > 1184) bx = 1184;
+  dim3 grid(bx, V.nW);
+  UBA_LAUNCH(k_assemble, grid, 256, 0, st, V);
+  return 1;
+}
+
+int solve_small_limit() { return 160; }
+
+int launch_solve(const DevView& V, const int* h_win_n, int max_small_n, cudaStream_t st) {
+  int launches = 0;
+  int small_max = 0, n_large = 0;
+  for (int w = 0; w < V.nW; w++) {
+    if (h_win_n[w] <= max_small_n) small_max = h_win_n[w] > small_max ? h_win_n[w] : small_max;
+    else n_large++;
+  }
+#ifdef UBA_EMU
+  for (int w = 0; w < V.nW; w++) uba_emu::dense_solve(V, w);
+  (void)small_max; (void)n_large;
+#else
+  if (small_max > 0) {
+    const size_t smem = ((size_t)small_max * (small_max + 1) + small_max) * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = smem;
+    }
+    UBA_LAUNCH(k_chol_small, V.nW, 256, smem, st, V, max_small_n);
+    launches++;
+  }
+  if (n_large) {
+    for (int w = 0; w < V.nW; w++) {
+      const int n = h_win_n[w];
+      if (n <= max_small_n) continue;
+      for (int j0 = 0; j0 < n; j0 += NB) {
+        const int nb = n - j0 < NB ? n - j0 : NB;
+        UBA_LAUNCH(k_chol_diag, 1, 256, 0, st, V, w, j0);
+        launches++;
+        const int rem = n - j0 - nb;
+        if (rem > 0) {
+          const int tiles = (rem + NB - 1) / NB;
+          UBA_LAUNCH(k_chol_trsm, tiles, 256, 0, st, V, w, j0);
+          UBA_LAUNCH(k_chol_update, dim3(tiles, tiles), 256, 0, st, V, w, j0);
+          launches += 2;
+        }
+      }
+      const size_t smem = (size_t)n * sizeof(double);
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k_trsv_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      UBA_LAUNCH(k_trsv_large, 1, 1024, smem, st, V, w);
+      launches++;
+    }
+  }
+#endif
+  UBA_LAUNCH(k_solve_epilogue, V.nW, 128, 0, st, V);
+  return launches + 1;
+}
+
+int launch_backsub(const DevView& V, cudaStream_t st) {
+  if (V.NP == 0) return 0;
+  const int grid = (V.NP + 127) / 128;
+  if (V.M == 4) UBA_LAUNCH(k_backsub<4>, grid, 128, 0, st, V);
+  else UBA_LAUNCH(k_backsub<2>, grid, 128, 0, st, V);
+  return 1;
+}
+
+int launch_lm_update(const DevView& V, cudaStream_t st) {
+  UBA_LAUNCH(k_lm_update, (V.nW + 127) / 128, 128, 0, st, V);
+  return 1;
+}
+
+int launch_l2_flush(double* buf, size_t n, cudaStream_t st) {
+  UBA_LAUNCH(k_l2_flush, 148 * 4, 256, 0, st, buf, n);
+  return 1;
+}
+
+int launch_dfma_probe(double* out, int iters, cudaStream_t st) {
+  UBA_LAUNCH(k_dfma_probe, 148 * 8, 256, 0, st, out, iters);
+  return 1;
+}
+
+}  // namespace uba

@@ -1,0 +1,95 @@
+"""Synthetic stereo-rig windows of BASELINE.json's five configurations.
+
+Thin wrapper over the C generator ``uba_synth_generate`` (csrc/uba_synth.cpp): seeds are
+``20261018 + 1000*config + window`` and every array comes back in the caller order the
+reference's ``initialiseObservations`` produces (BundleAdjuster.h:364-374): point-major,
+frame-ascending.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+BASE_SEED = 20261018
+
+
+@dataclass
+class Window:
+    M: int
+    cams_gt: np.ndarray
+    cams_init: np.ndarray
+    pts_gt: np.ndarray
+    pts_init: np.ndarray
+    feats: np.ndarray
+    cam_idx: np.ndarray
+    pt_idx: np.ndarray
+    cam_id: np.ndarray
+    fixed_frames: int
+    calib: capi.Calib
+
+    @property
+    def n_cams(self):
+        return self.cams_init.shape[0]
+
+    @property
+    def n_pts(self):
+        return self.pts_init.shape[0]
+
+    @property
+    def n_obs(self):
+        return self.feats.shape[0]
+
+
+# name -> (config id, n_cams, n_pts, track_min, track_max, full_tracks, outlier_fraction, loss, fixed LM iterations)
+CONFIGS = {
+    "c1": dict(config=1, n_cams=10, n_pts=2000, track_min=10, track_max=10, full_tracks=1, outliers=0.0, loss=capi.LOSS_HUBER, iters=10),
+    "c2": dict(config=2, n_cams=20, n_pts=20000, track_min=2, track_max=18, full_tracks=0, outliers=0.0, loss=capi.LOSS_HUBER, iters=10),
+    "c3": dict(config=3, n_cams=10, n_pts=2000, track_min=10, track_max=10, full_tracks=1, outliers=0.0, loss=capi.LOSS_HUBER, iters=10, windows=4096),
+    "c4": dict(config=4, n_cams=200, n_pts=200000, track_min=5, track_max=5, full_tracks=0, outliers=0.0, loss=capi.LOSS_HUBER, iters=10),
+    "c5": dict(config=5, n_cams=100, n_pts=100000, track_min=5, track_max=5, full_tracks=0, outliers=0.3, loss=capi.LOSS_CAUCHY, iters=20),
+}
+
+
+def generate(n_cams, n_pts, track_min, track_max, full_tracks=0, outliers=0.0, seed=BASE_SEED, M=4, fixed_frames=2,
+             calib=None, lib=None, pixel_sigma=0.5, pose_t_sigma=0.05, pose_r_sigma=0.005, point_rel_sigma=0.01) -> Window:
+    lib = lib or capi.default_lib()
+    calib = calib or capi.default_calib(lib)
+    spec = capi.SynthSpec(M=M, n_cams=n_cams, n_pts=n_pts, track_min=track_min, track_max=track_max, full_tracks=full_tracks,
+                          outlier_fraction=outliers, pixel_sigma=pixel_sigma, pose_t_sigma=pose_t_sigma,
+                          pose_r_sigma=pose_r_sigma, point_rel_sigma=point_rel_sigma, fixed_frames=fixed_frames, seed=seed)
+    max_obs = int(n_pts) * int(n_cams if full_tracks else min(track_max, n_cams))
+    cams_gt = np.zeros((n_cams, 6)); cams_init = np.zeros((n_cams, 6))
+    pts_gt = np.zeros((n_pts, 3)); pts_init = np.zeros((n_pts, 3))
+    feats = np.zeros((max(max_obs, 1), M)); cam_idx = np.zeros(max(max_obs, 1), np.int32)
+    pt_idx = np.zeros(max(max_obs, 1), np.int32); cam_id = np.zeros(max(max_obs, 1), np.int32)
+    n = lib.uba_synth_generate(C.byref(spec), C.byref(calib), max_obs, capi.dptr(cams_gt), capi.dptr(cams_init), capi.dptr(pts_gt),
+                               capi.dptr(pts_init), capi.dptr(feats), capi.i32ptr(cam_idx), capi.i32ptr(pt_idx), capi.i32ptr(cam_id))
+    if n < 0:
+        raise capi.UbaError(int(n), "uba_synth_generate failed")
+    n = int(n)
+    return Window(M, cams_gt, cams_init, pts_gt, pts_init, np.ascontiguousarray(feats[:n]), np.ascontiguousarray(cam_idx[:n]),
+                  np.ascontiguousarray(pt_idx[:n]), np.ascontiguousarray(cam_id[:n]), fixed_frames, calib)
+
+
+def config_window(name: str, window: int = 0, scale: float = 1.0, lib=None, M=4) -> Window:
+    """One window of configuration c1..c5; ``scale`` shrinks the point count (parity tests)."""
+    c = CONFIGS[name]
+    n_pts = max(8, int(round(c["n_pts"] * scale)))
+    return generate(c["n_cams"], n_pts, c["track_min"], c["track_max"], c["full_tracks"], c["outliers"],
+                    seed=BASE_SEED + 1000 * c["config"] + window, M=M, lib=lib)
+
+
+def concat_windows(wins) -> dict:
+    """Concatenate windows into uba_set_batch arguments."""
+    wc = np.zeros(len(wins) + 1, np.int32); wp = np.zeros(len(wins) + 1, np.int32); wo = np.zeros(len(wins) + 1, np.int64)
+    for i, w in enumerate(wins):
+        wc[i + 1] = wc[i] + w.n_cams; wp[i + 1] = wp[i] + w.n_pts; wo[i + 1] = wo[i] + w.n_obs
+    return dict(M=wins[0].M, win_cam_off=wc, win_pt_off=wp, win_obs_off=wo,
+                cams6=np.concatenate([w.cams_init for w in wins]), pts3=np.concatenate([w.pts_init for w in wins]),
+                feats=np.concatenate([w.feats for w in wins]), cam_idx=np.concatenate([w.cam_idx for w in wins]),
+                pt_idx=np.concatenate([w.pt_idx for w in wins]), cam_id=np.concatenate([w.cam_id for w in wins]),
+                calib=wins[0].calib)
