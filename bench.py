@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — BA observations/s and LM iterations/s of the windowed bundle-adjustment hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
+
+A step is one full Levenberg–Marquardt iteration over the workload: zero accumulators ->
+residuals + analytic Jacobians + robust weights + per-point Schur elimination -> dense fp64
+Cholesky of the reduced camera system -> back-substitution + candidate cost -> LM controller.
+`value` is observations processed per second with everything resident in HBM (CUDA events on the
+library's stream, max over ranks); `e2e` is the same metric through the C-ABI call sequence a
+caller makes (uba_set_problem -> uba_optimise -> uba_get_*) from host buffers, copies included.
+
+Default workload: c4 (BASELINE.json configs[3], the 1M-observation window north_star's targets are
+quoted on).  N > 1 (torchrun, one rank per GPU): c4/c5 are sharded by point with an NCCL allreduce of
+the reduced camera system ("scaling": "strong"); c3 is sharded by window with no collective ("weak").
+--impl reference times the CPU restatement of the reference's Ceres path (oracle/, all host threads):
+the reference itself cannot be built here (needs Ceres, OpenCV C++, glog; none installed, no network).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "BA observations/sec (full LM iteration: resid+Jacobian+Schur, solve, back-substitution)"
+UNIT = "observations/s"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_workload(name, rank, world, windows, scale):
+    """Returns (list of windows for this rank, total observations over all ranks, scaling, parallelism)."""
+    from uasl_motion_estimation_b200 import sharding, synth
+    if name == "c3":
+        per_rank = windows if windows else 512
+        wins = [synth.config_window("c3", window=rank * per_rank + i, scale=scale) for i in range(per_rank)]
+        n_local = sum(w.n_obs for w in wins)
+        return wins, None, "weak", f"window-sharded x{world}, no collective", n_local
+    win = synth.config_window(name, scale=scale)
+    total = win.n_obs
+    if world > 1:
+        win = sharding.shard_window(win, rank, world)
+        return [win], total, "strong", f"point-sharded x{world}, NCCL allreduce of the reduced camera system", win.n_obs
+    return [win], total, "strong", "single GPU", win.n_obs
+
+
+def algorithmic_work(wins, fixed):
+    """Algorithmic bytes / flops of ONE linearise+Schur pass (formulas of SURVEY.md §8(d), restated in DESIGN.md)."""
+    nbytes = 0.0; flops = 0.0
+    for w in wins:
+        free = w.cam_idx >= fixed
+        k = np.bincount(w.pt_idx[free], minlength=w.n_pts).astype(np.float64)
+        pairs = np.unique(np.stack([w.pt_idx[free].astype(np.int64)], 0), axis=1).shape[1]  # points with free observations
+        ncf = len(np.unique(w.cam_idx[free]))
+        # camera-pair blocks touched: for consecutive tracks the band; computed exactly from the data on small inputs
+        lo = np.full(w.n_pts, 1 << 30); hi = np.full(w.n_pts, -1)
+        np.minimum.at(lo, w.pt_idx[free], w.cam_idx[free]); np.maximum.at(hi, w.pt_idx[free], w.cam_idx[free])
+        span = np.clip(hi - lo, 0, None)[hi >= 0]
+        band = int(span.max()) if span.size else 0
+        nnzb = sum(max(0, ncf - d) for d in range(band + 1))
+        nbytes += 40.0 * w.n_obs + 96.0 * w.n_pts + 8.0 * (36.0 * nnzb + 6.0 * ncf) + 48.0 * w.n_cams
+        flops += 620.0 * w.n_obs + float(np.sum(50.0 + 144.0 * k + 216.0 * k * (k + 1) / 2.0))
+        del pairs
+    return nbytes, flops
+
+
+def h2d_d2h_bytes(wins):
+    h2d = sum(w.feats.nbytes + w.cam_idx.nbytes + w.pt_idx.nbytes + w.cam_id.nbytes + w.cams_init.nbytes + w.pts_init.nbytes for w in wins)
+    d2h = sum(w.cams_init.nbytes + w.pts_init.nbytes for w in wins)
+    return h2d, d2h
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle's LM iteration (Jet autodiff residual blocks, Schur elimination, dense Cholesky,
+    back-substitution, candidate cost) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import oracle_binding as ob
+    from uasl_motion_estimation_b200 import capi, synth
+    ob.build()
+    lib = capi.default_lib()
+    name = args.workload
+    scale = args.scale
+    if name == "c3":
+        wins = [synth.config_window("c3", window=0, scale=scale)]
+        sample = "1 of the batch's 10-frame windows per step"
+    else:
+        wins = [synth.config_window(name, scale=scale)]
+        sample = f"the full {name} window, one LM iteration per step"
+    win = wins[0]
+    cfg = capi.default_config(lib, loss_kind=synth.CONFIGS[name]["loss"])
+    threads = ob.lib().uba_ref_max_threads()
+    for _ in range(args.warmup):
+        ob.time_iteration(win, cfg, 2, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ob.time_iteration(win, cfg, 2, 1)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = win.n_obs / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if name != "c3" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n_cams": win.n_cams, "n_pts": win.n_pts, "n_obs": win.n_obs, "scale": scale},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "lm_iters_per_s": 1.0 / dt,
+            "note": "CPU restatement of the reference's Ceres path (oracle/); Ceres itself is not installable here"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--windows", type=int, default=0, help="c3: windows per GPU (default 512)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the point count (debugging only; 1.0 = BASELINE size)")
+    ap.add_argument("--linearizer", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from uasl_motion_estimation_b200 import capi, synth
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    name = args.workload
+    fixed = 2
+    wins, total_obs, scaling, parallelism, n_local = build_workload(name, rank, world, args.windows, args.scale)
+    loss = synth.CONFIGS[name]["loss"]
+    k_iters = synth.CONFIGS[name]["iters"]
+    cfg = capi.default_config(loss_kind=loss, fixed_iterations=k_iters, device=local, linearizer=args.linearizer)
+    h = capi.Handle(cfg)
+    sharded = world > 1 and name != "c3"
+    if sharded:
+        uid = [h.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(uid[0], rank, world)
+
+    def set_problem():
+        if len(wins) == 1:
+            w = wins[0]
+            h.set_problem(w.M, w.cams_init, w.pts_init, w.feats, w.cam_idx, w.pt_idx, w.cam_id, w.calib)
+        else:
+            h.set_batch(**synth.concat_windows(wins))
+
+    set_problem()
+    if total_obs is None:  # c3: every rank holds the same number of windows
+        t = torch.tensor([n_local], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        total_obs = int(t.item())
+
+    # ---- device-resident throughput: K LM iterations, CUDA events per iteration, L2 flushed in between ----
+    h.time_iteration(fixed, iterations=args.warmup, flush_l2=True)
+    sampler = ClockSampler(local); sampler.start()
+    h.timing(reset=True)
+    barrier()
+    ms_iter = h.time_iteration(fixed, iterations=args.steps, flush_l2=True)
+    barrier()
+    launches = h.timing()["kernel_launches"] - args.steps  # minus the L2-flush kernels
+    clocks = sampler.stop()
+    # ---- the linearise+Schur pass alone (the roofline kernel) ----
+    ms_lin = h.time_linearize(fixed, 1e4, repeats=max(args.steps, 5), flush_l2=True)
+    t = torch.tensor([ms_iter, ms_lin], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_iter, ms_lin = float(t[0]), float(t[1])
+    value = total_obs / (ms_iter * 1e-3)
+
+    # ---- end to end through the C ABI from host buffers ----
+    h2d, d2h = h2d_d2h_bytes(wins)
+    e2e_ms = []
+    for rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        set_problem()
+        rc, sums = h.optimise(fixed)
+        cams = h.cameras(); pts = h.points()
+        torch.cuda.synchronize()
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+        barrier()
+    t = torch.tensor([min(e2e_ms[1:])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_obs * k_iters / (float(t[0]) * 1e-3)
+
+    # ---- roofline of the dominant kernel ----
+    hbm_peak, peak_src = measured_peaks()
+    nbytes, flops = algorithmic_work(wins, fixed)
+    fp64_peak = h.probe_fp64_tflops()
+    achieved_gbs = nbytes / (ms_lin * 1e-3) / 1e9
+    achieved_tf = flops / (ms_lin * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "linearise+Schur pass", "kernel_ms": ms_lin,
+                "algorithmic_bytes": nbytes, "algorithmic_flops": flops,
+                "fp64": {"achieved_tflops": achieved_tf, "peak_tflops": fp64_peak, "frac": achieved_tf / fp64_peak,
+                         "peak_source": "measured here (DFMA micro-kernel, uba_probe_fp64_tflops)"},
+                "binding": "fp64" if flops / (fp64_peak * 1e12) > nbytes / (hbm_peak * 1e9) else "hbm"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_iter, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": name, "n_windows_per_gpu": len(wins), "n_obs_total": int(total_obs), "n_obs_per_gpu": int(n_local),
+                       "n_cams": wins[0].n_cams, "fixed_frames": fixed, "loss": {1: "huber", 2: "cauchy", 0: "trivial"}[loss],
+                       "lm_iterations_e2e": k_iters, "parallelism": parallelism, "l2": "flushed between timed iterations (384 MB write)",
+                       "scale": args.scale},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // k_iters), "d2h_bytes_per_step": int(d2h // k_iters),
+                    "ms_per_call": float(t[0]), "lm_iterations_per_call": k_iters},
+            "lm_iters_per_s": 1e3 / ms_iter, "linearize_obs_per_s": total_obs / (ms_lin * 1e-3), "roofline": roofline}
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        import oracle_binding as ob
+        ob.build()
+        cw = wins[0]
+        ccfg = capi.default_config(loss_kind=loss)
+        tt, tl = ob.time_iteration(cw, ccfg, fixed, 1)
+        reps = int(max(1, min(5, 15.0 / max(tt, 1e-3))))
+        tt, tl = ob.time_iteration(cw, ccfg, fixed, reps)
+        line["cpu_baseline"] = {"value": cw.n_obs / tt, "unit": UNIT, "cores": ob.lib().uba_ref_max_threads(), "kind": "port",
+                                "sample": f"{reps} LM iteration(s) of one {name} window ({cw.n_obs} observations) through the oracle",
+                                "ms_per_step": tt * 1e3}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

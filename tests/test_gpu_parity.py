@@ -1,0 +1,160 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on a B200.
+
+Tolerances are north_star's: residual vectors and normal-equation blocks <= 1e-9 relative, final
+poses / points after a fixed number of LM iterations <= 1e-6 relative, index tables bit-exact.
+"""
+import numpy as np
+import pytest
+
+from uasl_motion_estimation_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+BLOCK_TOL = 1e-9
+STATE_TOL = 1e-6
+BLOCKS = ("residuals", "weights", "cost", "grad_cams", "grad_pts", "B", "C", "W", "S", "rhs", "lm_diag_cams", "lm_diag_pts")
+
+
+def rel(a, b):
+    a = np.asarray(a, float).reshape(-1); b = np.asarray(b, float).reshape(-1)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def make(lib, name, scale, M=4, linearizer=0, **cfgkw):
+    win = synth.config_window(name, scale=scale, lib=lib, M=M)
+    cfg = capi.default_config(lib, loss_kind=synth.CONFIGS[name]["loss"], linearizer=linearizer, **cfgkw)
+    h = capi.Handle(cfg, lib=lib)
+    h.set_problem(M, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+    return win, cfg, h
+
+
+CASES = [("c1", 1.0, 4), ("c2", 0.1, 4), ("c4", 0.01, 4), ("c5", 0.02, 4), ("c1", 0.25, 2), ("c2", 0.05, 2)]
+
+
+@pytest.mark.parametrize("linearizer", [1, 2])
+@pytest.mark.parametrize("name,scale,M", CASES)
+def test_linearization_blocks(gpu_lib, oracle, name, scale, M, linearizer):
+    win, cfg, h = make(gpu_lib, name, scale, M, linearizer)
+    t = h.tables(2); r = oracle.tables(win.n_cams, win.n_pts, win.cam_idx, win.pt_idx, 2)
+    for k in t:
+        assert np.array_equal(t[k], r[k]), k
+    g = h.linearize(2, 1e4); r = oracle.linearize(win, cfg, 2, 1e4)
+    for k in BLOCKS:
+        assert rel(g[k], r[k]) < BLOCK_TOL, (k, rel(g[k], r[k]))
+    assert h.timing()["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("linearizer", [1, 2])
+@pytest.mark.parametrize("name,scale,M,iters", [("c1", 1.0, 4, 10), ("c2", 0.1, 4, 10), ("c4", 0.01, 4, 10), ("c5", 0.02, 4, 20), ("c1", 0.25, 2, 8)])
+def test_fixed_iteration_trajectory(gpu_lib, oracle, name, scale, M, iters, linearizer):
+    win, cfg, h = make(gpu_lib, name, scale, M, linearizer, fixed_iterations=iters)
+    rc, sums = h.optimise(2)
+    o = oracle.optimise(win, cfg, 2)
+    assert rc == 0 and o["rc"] == 0
+    gi = h.iterations(0)
+    assert [a["accepted"] for a in gi] == [b["accepted"] for b in o["iterations"]]
+    for a, b in zip(gi, o["iterations"]):
+        assert a["cost"] == pytest.approx(b["cost"], rel=1e-7)
+        assert a["model_cost_change"] == pytest.approx(b["model_cost_change"], rel=1e-5, abs=1e-12)
+    assert rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
+    assert sums[0].final_cost == pytest.approx(o["summary"]["final_cost"], rel=1e-8)
+
+
+def test_reference_termination_rules(gpu_lib, oracle):
+    win, cfg, h = make(gpu_lib, "c1", 1.0, max_solver_time_s=0.0)
+    rc, sums = h.optimise(2)
+    o = oracle.optimise(win, cfg, 2)
+    assert sums[0].termination == o["summary"]["termination"] == 1
+    assert sums[0].iterations == o["summary"]["iterations"]
+    assert rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
+
+
+def test_large_window_dense_solver_path(gpu_lib, oracle):
+    """200 keyframes -> reduced system 1188 x 1188: the blocked global-memory Cholesky."""
+    win, cfg, h = make(gpu_lib, "c4", 0.05, fixed_iterations=3)
+    assert 6 * int((h.tables(2)["free_cam"] >= 0).sum()) > 160
+    rc, sums = h.optimise(2)
+    o = oracle.optimise(win, cfg, 2)
+    assert rc == 0
+    assert [a["accepted"] for a in h.iterations(0)] == [b["accepted"] for b in o["iterations"]]
+    assert rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
+
+
+def test_batch_of_windows(gpu_lib, oracle):
+    wins = [synth.config_window("c1", window=i, scale=0.05 + 0.01 * i, lib=gpu_lib) for i in range(6)]
+    cfg = capi.default_config(gpu_lib, max_solver_time_s=0.0)
+    h = capi.Handle(cfg, lib=gpu_lib)
+    h.set_batch(**synth.concat_windows(wins))
+    rc, sums = h.optimise(2)
+    assert rc == 0
+    cams = h.cameras(); pts = h.points()
+    c0 = p0 = 0
+    for w, win in enumerate(wins):
+        o = oracle.optimise(win, cfg, 2)
+        assert sums[w].iterations == o["summary"]["iterations"] and sums[w].termination == o["summary"]["termination"]
+        assert rel(cams[c0:c0 + win.n_cams], o["cams"]) < STATE_TOL
+        assert rel(pts[p0:p0 + win.n_pts], o["pts"]) < STATE_TOL
+        c0 += win.n_cams; p0 += win.n_pts
+
+
+def test_shuffled_observations_ragged_and_empty_points(gpu_lib, oracle):
+    win = synth.config_window("c2", scale=0.05, lib=gpu_lib)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(win.n_obs)
+    keep = perm[win.pt_idx[perm] % 7 != 3]
+    sub = synth.Window(4, win.cams_gt, win.cams_init, win.pts_gt, win.pts_init, np.ascontiguousarray(win.feats[keep]),
+                       np.ascontiguousarray(win.cam_idx[keep]), np.ascontiguousarray(win.pt_idx[keep]),
+                       np.ascontiguousarray(win.cam_id[keep]), 2, win.calib)
+    cfg = capi.default_config(gpu_lib, fixed_iterations=5)
+    h = capi.Handle(cfg, lib=gpu_lib)
+    h.set_problem(4, sub.cams_init, sub.pts_init, sub.feats, sub.cam_idx, sub.pt_idx, sub.cam_id, sub.calib)
+    g = h.linearize(2, 1e4); r = oracle.linearize(sub, cfg, 2, 1e4)
+    for k in BLOCKS:
+        assert rel(g[k], r[k]) < BLOCK_TOL, k
+    rc, _ = h.optimise(2)
+    o = oracle.optimise(sub, cfg, 2)
+    assert rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
+    untouched = np.flatnonzero(np.bincount(sub.pt_idx, minlength=sub.n_pts) == 0)
+    np.testing.assert_array_equal(h.points()[untouched], sub.pts_init[untouched])
+
+
+def test_errors_and_infeasible_start(gpu_lib):
+    win = synth.config_window("c1", scale=0.05, lib=gpu_lib)
+    h = capi.Handle(capi.default_config(gpu_lib), lib=gpu_lib)
+    bad = win.cam_idx.copy(); bad[5] = -1
+    with pytest.raises(capi.UbaError) as e:
+        h.set_problem(4, win.cams_init, win.pts_init, win.feats, bad, win.pt_idx, None, win.calib)
+    assert e.value.code == capi.UBA_ERR_INVALID_ARGUMENT
+    pts = win.pts_init.copy(); pts[3, 2] = 1e9
+    h.set_problem(4, win.cams_init, pts, win.feats, win.cam_idx, win.pt_idx, None, win.calib)
+    rc, sums = h.optimise(2, check=False)
+    assert rc == capi.UBA_ERR_INFEASIBLE and sums[0].usable == 0
+    np.testing.assert_array_equal(h.points(), pts)
+
+
+@pytest.mark.parametrize("name", ["c4", "c5"])
+def test_full_size_properties(gpu_lib, oracle, name):
+    """BASELINE.json's full sizes: size-independent properties instead of a full oracle LM run."""
+    win, cfg, h = make(gpu_lib, name, 1.0, fixed_iterations=synth.CONFIGS[name]["iters"])
+    g = h.linearize(2, 1e4, want=("cost", "S", "rhs", "grad_cams", "residuals"))
+    # cost and residuals against the oracle's residual-only evaluation (cheap even at 1M observations)
+    assert g["cost"][0] == pytest.approx(oracle.cost(win, cfg, win.cams_init, win.pts_init), rel=1e-11)
+    S = g["S"]
+    assert np.abs(S - S.T).max() <= 1e-12 * np.abs(S).max()
+    np.linalg.cholesky(S)  # positive definite
+    # linearisation is idempotent (atomics may reorder sums: tolerance, not bitwise)
+    g2 = h.linearize(2, 1e4, want=("S", "rhs"))
+    assert rel(g2["S"], S) < 1e-12 and rel(g2["rhs"], g["rhs"]) < 1e-12
+    # directional derivative of the oracle's cost == gradient . direction
+    rng = np.random.default_rng(3)
+    d = rng.normal(size=(win.n_cams, 6)) * np.array([1e-3] * 3 + [1e-4] * 3); d[:2] = 0
+    eps = 1e-4
+    fd = (oracle.cost(win, cfg, win.cams_init + eps * d, win.pts_init) - oracle.cost(win, cfg, win.cams_init - eps * d, win.pts_init)) / (2 * eps)
+    if cfg.loss_kind == capi.LOSS_HUBER:  # Huber's kink makes the FD check only approximate
+        assert np.sum(g["grad_cams"] * d) == pytest.approx(fd, rel=1e-3)
+    rc, sums = h.optimise(2)
+    its = h.iterations(0)
+    assert rc == 0 and sums[0].final_cost < 0.2 * sums[0].initial_cost
+    costs = [it["cost"] for it in its]
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(costs, costs[1:]))  # monotonic: only accepted steps move x
+    assert sums[0].final_cost == pytest.approx(oracle.cost(win, cfg, h.cameras(), h.points()), rel=1e-10)

@@ -1,0 +1,138 @@
+"""Host logic of libuba (index tables, launch sequencing, LM controller, error behaviour) exercised on
+the CPU through tests/emu — a serial emulation of the thread-independent kernels.  The parity tests
+proper are the -m gpu tests in test_gpu_parity.py; these make the same comparisons at small sizes so
+host-side regressions are caught without a GPU."""
+import numpy as np
+import pytest
+
+from uasl_motion_estimation_b200 import capi, synth
+
+
+def rel(a, b):
+    a = np.asarray(a, float).reshape(-1); b = np.asarray(b, float).reshape(-1)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def make(lib, name, scale, M=4, **cfgkw):
+    win = synth.config_window(name, scale=scale, lib=lib, M=M)
+    cfg = capi.default_config(lib, loss_kind=synth.CONFIGS[name]["loss"], **cfgkw)
+    h = capi.Handle(cfg, lib=lib)
+    h.set_problem(M, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+    return win, cfg, h
+
+
+@pytest.mark.parametrize("name,scale", [("c1", 0.02), ("c2", 0.004), ("c4", 0.001), ("c5", 0.002)])
+def test_tables_bit_exact(emu_lib, oracle, name, scale):
+    win, cfg, h = make(emu_lib, name, scale)
+    for fixed in (0, 2, 3):
+        t = h.tables(fixed); r = oracle.tables(win.n_cams, win.n_pts, win.cam_idx, win.pt_idx, fixed)
+        for k in t:
+            assert np.array_equal(t[k], r[k]), (k, fixed)
+    # the reference's own ordering (point-major, frame-ascending) is the identity
+    assert np.array_equal(h.tables(2)["obs_order"], np.arange(win.n_obs))
+
+
+def test_tables_with_shuffled_observations_and_empty_points(emu_lib, oracle):
+    win = synth.config_window("c2", scale=0.004, lib=emu_lib)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(win.n_obs)
+    keep = perm[win.pt_idx[perm] % 7 != 3]  # points 3, 10, 17, ... lose every observation
+    ci, pi, f = win.cam_idx[keep], win.pt_idx[keep], win.feats[keep]
+    h = capi.Handle(capi.default_config(emu_lib), lib=emu_lib)
+    h.set_problem(4, win.cams_init, win.pts_init, f, ci, pi, None, win.calib)
+    t = h.tables(2); r = oracle.tables(win.n_cams, win.n_pts, ci, pi, 2)
+    for k in t:
+        assert np.array_equal(t[k], r[k]), k
+    assert (np.diff(t["pt_obs_off"])[3::7] == 0).all()
+
+
+@pytest.mark.parametrize("name,scale,M", [("c1", 0.02, 4), ("c2", 0.004, 4), ("c4", 0.001, 4), ("c5", 0.002, 4), ("c1", 0.02, 2), ("c2", 0.004, 2)])
+def test_linearization_blocks(emu_lib, oracle, name, scale, M):
+    win, cfg, h = make(emu_lib, name, scale, M)
+    g = h.linearize(2, 1e4); r = oracle.linearize(win, cfg, 2, 1e4)
+    for k in ("residuals", "weights", "cost", "grad_cams", "grad_pts", "B", "C", "W", "S", "rhs", "lm_diag_cams", "lm_diag_pts"):
+        assert rel(g[k], r[k]) < 1e-9, k
+
+
+@pytest.mark.parametrize("name,scale,M", [("c1", 0.02, 4), ("c2", 0.004, 4), ("c4", 0.001, 4), ("c1", 0.02, 2)])
+def test_fixed_iteration_trajectory(emu_lib, oracle, name, scale, M):
+    win, cfg, h = make(emu_lib, name, scale, M, fixed_iterations=6)
+    rc, sums = h.optimise(2)
+    o = oracle.optimise(win, cfg, 2)
+    assert rc == 0 and o["rc"] == 0
+    assert rel(h.cameras(), o["cams"]) < 1e-6 and rel(h.points(), o["pts"]) < 1e-6
+    gi = h.iterations(0)
+    assert len(gi) == len(o["iterations"]) == 7
+    for a, b in zip(gi, o["iterations"]):
+        assert a["accepted"] == b["accepted"]
+        assert a["cost"] == pytest.approx(b["cost"], rel=1e-7)
+        assert a["radius"] == pytest.approx(b["radius"], rel=1e-5)
+        assert a["model_cost_change"] == pytest.approx(b["model_cost_change"], rel=1e-6, abs=1e-12)
+
+
+def test_reference_termination_rules(emu_lib, oracle):
+    """Default options (function_tolerance 1e-3, Ceres defaults): same termination, same iterate."""
+    win, cfg, h = make(emu_lib, "c1", 0.02, max_solver_time_s=0.0)
+    rc, sums = h.optimise(2)
+    o = oracle.optimise(win, cfg, 2)
+    s = sums[0].as_dict()
+    assert s["termination"] == o["summary"]["termination"] == 1  # CONVERGENCE_FUNCTION
+    assert s["iterations"] == o["summary"]["iterations"]
+    assert rel(h.cameras(), o["cams"]) < 1e-6 and rel(h.points(), o["pts"]) < 1e-6
+
+
+def test_batch_of_windows_matches_single_windows(emu_lib, oracle):
+    wins = [synth.config_window("c1", window=i, scale=0.01 + 0.002 * i, lib=emu_lib) for i in range(4)]
+    cfg = capi.default_config(emu_lib, max_solver_time_s=0.0)
+    h = capi.Handle(cfg, lib=emu_lib)
+    h.set_batch(**synth.concat_windows(wins))
+    rc, sums = h.optimise(2)
+    assert rc == 0
+    cams = h.cameras(); pts = h.points()
+    c0 = p0 = 0
+    for w, win in enumerate(wins):
+        o = oracle.optimise(win, cfg, 2)
+        assert sums[w].iterations == o["summary"]["iterations"] and sums[w].termination == o["summary"]["termination"]
+        assert rel(cams[c0:c0 + win.n_cams], o["cams"]) < 1e-6
+        assert rel(pts[p0:p0 + win.n_pts], o["pts"]) < 1e-6
+        c0 += win.n_cams; p0 += win.n_pts
+
+
+def test_state_machine_and_errors(emu_lib):
+    h = capi.Handle(capi.default_config(emu_lib), lib=emu_lib)
+    with pytest.raises(capi.UbaError) as e:
+        h.n_windows = 1; h.optimise(2)
+    assert e.value.code == capi.UBA_ERR_STATE  # "system should be initialised" (BundleAdjuster.h:381-384)
+    win = synth.config_window("c1", scale=0.01, lib=emu_lib)
+    bad = win.cam_idx.copy(); bad[5] = win.n_cams  # the reference has no upper-bound check (OOB read)
+    with pytest.raises(capi.UbaError) as e:
+        h.set_problem(4, win.cams_init, win.pts_init, win.feats, bad, win.pt_idx, None, win.calib)
+    assert e.value.code == capi.UBA_ERR_INVALID_ARGUMENT
+    with pytest.raises(capi.UbaError):
+        h.set_problem(3, win.cams_init, win.pts_init, win.feats[:, :3], win.cam_idx, win.pt_idx, None, win.calib)
+    h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, None, win.calib)
+    np.testing.assert_array_equal(h.points(), win.pts_init)  # getters before optimise return the inputs
+    rc, _ = h.optimise(2)
+    assert rc == 0
+    with pytest.raises(capi.UbaError) as e:  # single use, like the reference (BundleAdjuster.h:7)
+        h.optimise(2)
+    assert e.value.code == capi.UBA_ERR_STATE
+
+
+def test_infeasible_start_is_a_failure_and_restores_inputs(emu_lib):
+    win = synth.config_window("c1", scale=0.01, lib=emu_lib)
+    win.pts_init[3, 2] = 1e9
+    h = capi.Handle(capi.default_config(emu_lib), lib=emu_lib)
+    h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, None, win.calib)
+    rc, sums = h.optimise(2, check=False)
+    assert rc == capi.UBA_ERR_INFEASIBLE and sums[0].usable == 0 and sums[0].termination == 5
+    np.testing.assert_array_equal(h.points(), win.pts_init)
+    np.testing.assert_array_equal(h.cameras(), win.cams_init)
+
+
+def test_all_cameras_fixed_moves_only_points(emu_lib, oracle):
+    win, cfg, h = make(emu_lib, "c1", 0.01, fixed_iterations=3)
+    rc, _ = h.optimise(win.n_cams)
+    o = oracle.optimise(win, cfg, win.n_cams)
+    np.testing.assert_array_equal(h.cameras(), win.cams_init)
+    assert rel(h.points(), o["pts"]) < 1e-6

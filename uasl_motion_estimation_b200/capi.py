@@ -142,7 +142,7 @@ def load(path: str | os.PathLike | None = None) -> C.CDLL:
     if not p.exists():
         raise ImportError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           f"(nvcc, sm_100a).  uasl_motion_estimation_b200 has no CPU implementation.")
-    lib = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(str(p))
     for name, res, args in _SIGNATURES:
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res

@@ -187,11 +187,25 @@ void fill_view_static(uba_handle* h) {
   c.jacobi_scaling = h->cfg.jacobi_scaling; c.use_bounds = h->cfg.use_bounds;
 }
 
+int allreduce(uba_handle* h, double* buf, size_t count, int op);
+
 // Tables that depend on fixed_frames: free cameras, reduced-system layout, accumulators.
 int prepare(uba_handle* h, int fixed_frames) {
   if (fixed_frames < 0) fixed_frames = 0;
   if (h->prepared_fixed == fixed_frames) return UBA_OK;
   const int nW = h->nW, NC = h->NC;
+  if (h->comm) {
+    // point-sharded: a camera is in the problem if ANY rank observes it -> max over ranks
+    std::vector<double> seen(NC);
+    for (int c = 0; c < NC; c++) seen[c] = h->cam_seen[c] ? 1.0 : 0.0;
+    CU(h, h->d_cam_lam.reserve((size_t)NC * 6));
+    CU(h, cudaMemcpyAsync(h->d_cam_lam.p, seen.data(), sizeof(double) * NC, cudaMemcpyHostToDevice, h->stream));
+    int rc = allreduce(h, h->d_cam_lam.p, NC, kNcclMax);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(seen.data(), h->d_cam_lam.p, sizeof(double) * NC, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < NC; c++) h->cam_seen[c] = seen[c] > 0.0;
+  }
   h->free_cam_h.assign(NC, -1);
   h->free_list_h.clear();
   h->w_free_off_h.assign(nW + 1, 0);
