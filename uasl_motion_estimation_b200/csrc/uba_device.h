@@ -46,15 +46,20 @@ struct SolverCfg {
   int32_t max_consecutive_invalid_steps, fixed_iterations, max_iterations, jacobi_scaling, use_bounds;
 };
 
-// Segment-local tiling plan of the fast lineariser (see uba_kernels.cu, k_lin_tile).
-struct TileItem {
+// Segment-local tiling plan of the fast lineariser (see uba_kernels.cu, k_lin_tile).  A part is a
+// contiguous range of internal point slots whose cameras all belong to one short, ascending "local
+// camera list"; the fixed cameras (camIdx < fixedFrames) are its first n_fixed entries.
+struct TilePart {
   int32_t window;
   int32_t pt_begin, pt_end;   // internal point slots
-  int32_t cam_list_off;       // offset into tile_cams: the item's local camera list (window-local indices)
-  int32_t n_local;            // local cameras (free and fixed)
-  int32_t n_local_free;       // the first n_local_free entries of the list are free cameras
+  int32_t cam_list_off;       // offset into tile_cams (window-local camera indices, ascending)
+  int32_t n_local;            // local cameras, <= kTileMaxLocal
+  int32_t n_fixed;            // leading fixed cameras; free ones: n_local - n_fixed <= kTileMaxFree
   int32_t pad_[2];
 };
+constexpr int kTileThreads = 256;
+constexpr int kTileMaxLocal = 32;
+constexpr int kTileMaxFree = 21;   // 21*22/2 = 231 camera-pair blocks <= kTileThreads
 
 struct DevView {
   int32_t M, nW, NC, NP;
@@ -94,6 +99,13 @@ struct DevView {
   double* A;                  // per window [n][n] assembled damped reduced matrix (full), then its factor
   double* rhs;                // [6 * n_free_total]
   double* Zbuf;               // [NO][18] scratch of the generic lineariser
+  // tiled lineariser plan
+  const TilePart* parts;      // [n_parts]
+  int32_t n_parts;
+  const int32_t* tile_cams;   // local camera lists
+  const uint32_t* pt_mask;    // [NP] bit s: the point observes slot s of its part's list (0: not a tile point)
+  const int32_t* gen_pts;     // [n_gen] internal point slots handled by the generic lineariser
+  int32_t n_gen;
   WinState* ws;               // [nW]
   IterRec* recs;              // [nW][rec_stride]
   int32_t rec_stride;
@@ -115,7 +127,9 @@ struct DebugOut {
 
 // launchers (uba_kernels.cu); all asynchronous on `st`; return the number of kernels launched
 int launch_cam_prep(const DevView& V, int parity, cudaStream_t st);
-int launch_lin_generic(const DevView& V, const DebugOut& dbg, cudaStream_t st);
+// only_listed: process V.gen_pts instead of every point
+int launch_lin_generic(const DevView& V, const DebugOut& dbg, bool only_listed, cudaStream_t st);
+int launch_lin_tile(const DevView& V, cudaStream_t st);
 int launch_assemble(const DevView& V, int max_n, cudaStream_t st);
 // h_win_n: host array [nW] of reduced-system sizes (6 * free cameras)
 int launch_solve(const DevView& V, const int* h_win_n, int max_small_n, cudaStream_t st);

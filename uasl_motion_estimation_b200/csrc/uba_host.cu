@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -113,6 +114,13 @@ struct uba_handle {
   std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n;
   std::vector<int64_t> w_red_off_h;
   int max_n = 0;
+  bool use_tile = false;
+  std::vector<TilePart> parts_h;
+  std::vector<int32_t> tile_cams_h, gen_pts_h;
+  std::vector<uint32_t> pt_mask_h;
+  DevBuf<TilePart> d_parts;
+  DevBuf<uint32_t> d_pt_mask;
+  DevBuf<int32_t> d_tile_cams, d_gen_pts;
   // pinned staging (internal order)
   PinBuf<double> h_cams, h_pts, h_feat, h_out;
   PinBuf<int32_t> h_obs_cam;
@@ -189,6 +197,79 @@ void fill_view_static(uba_handle* h) {
 
 int allreduce(uba_handle* h, double* buf, size_t count, int op);
 
+// Plan of the tiled lineariser: walk the internal point order (sorted by lowest / highest camera)
+// and cut it into items whose points share one short ascending camera list; points that do not fit
+// (too long a track, a camera seen twice) go to the generic lineariser.
+void build_tile_plan(uba_handle* h, int fixed_frames) {
+  const double tau = 0.85;  // every point of an item sees at least tau of the item's cameras
+  h->parts_h.clear(); h->tile_cams_h.clear(); h->gen_pts_h.clear();
+  h->pt_mask_h.assign(h->NP, 0u);
+  size_t tile_points = 0;
+  struct Item { int w, begin, end, cam_off, nl, nfx; };
+  std::vector<Item> items;
+  std::vector<int> uni, merged, cams_p;
+  for (int w = 0; w < h->nW; w++) {
+    const int s0 = h->w_pt_off[w], s1 = h->w_pt_off[w + 1];
+    int item_begin = -1, min_len = 0;
+    uni.clear();
+    auto close_item = [&](int end) {
+      if (item_begin < 0) return;
+      Item it{w, item_begin, end, (int)h->tile_cams_h.size(), (int)uni.size(), 0};
+      for (int c : uni) { h->tile_cams_h.push_back(c); if (c < fixed_frames) it.nfx++; }
+      for (int s = item_begin; s < end; s++) {
+        if (h->pt_mask_h[s] != 1u) { h->pt_mask_h[s] = 0u; continue; }  // 1u marks a tile point until here
+        unsigned m = 0;
+        for (int o = h->pt_obs_off_int[s]; o < h->pt_obs_off_int[s + 1]; o++) {
+          const int c = h->h_obs_cam.p[o] & 0x3fffffff;
+          m |= 1u << (unsigned)(std::lower_bound(uni.begin(), uni.end(), c) - uni.begin());
+        }
+        h->pt_mask_h[s] = m;
+        tile_points++;
+      }
+      items.push_back(it);
+      item_begin = -1;
+    };
+    for (int s = s0; s < s1; s++) {
+      const int o0 = h->pt_obs_off_int[s], k = h->pt_obs_off_int[s + 1] - o0;
+      if (k == 0) continue;
+      cams_p.clear();
+      bool ascending = true;
+      int nfree = 0;
+      for (int q = 0; q < k; q++) {
+        const int c = h->h_obs_cam.p[o0 + q] & 0x3fffffff;
+        if (q && c <= cams_p.back()) ascending = false;
+        cams_p.push_back(c);
+        if (c >= fixed_frames) nfree++;
+      }
+      if (!ascending || k > kTileMaxLocal || nfree > kTileMaxFree) { h->gen_pts_h.push_back(s); continue; }
+      bool ok = item_begin >= 0;
+      if (ok) {
+        merged.clear();
+        std::set_union(uni.begin(), uni.end(), cams_p.begin(), cams_p.end(), std::back_inserter(merged));
+        int nf = 0;
+        for (int c : merged) if (c >= fixed_frames) nf++;
+        ok = (int)merged.size() <= kTileMaxLocal && nf <= kTileMaxFree && std::min(min_len, k) >= tau * (double)merged.size();
+      }
+      if (!ok) { close_item(s); uni = cams_p; min_len = k; item_begin = s; }
+      else { uni.swap(merged); min_len = std::min(min_len, k); }
+      h->pt_mask_h[s] = 1u;
+    }
+    close_item(s1);
+  }
+  // parts: aim at a few CTAs per SM, never less than 4 chunks of points per CTA
+  const size_t target_parts = 4 * 148;
+  for (const Item& it : items) {
+    const int Pc = kTileThreads / it.nl;
+    int part_pts = std::max<size_t>(4 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
+    part_pts = ((part_pts + Pc - 1) / Pc) * Pc;
+    for (int b = it.begin; b < it.end; b += part_pts) {
+      TilePart p{};
+      p.window = it.w; p.pt_begin = b; p.pt_end = std::min(it.end, b + part_pts); p.cam_list_off = it.cam_off; p.n_local = it.nl; p.n_fixed = it.nfx;
+      h->parts_h.push_back(p);
+    }
+  }
+}
+
 // Tables that depend on fixed_frames: free cameras, reduced-system layout, accumulators.
 int prepare(uba_handle* h, int fixed_frames) {
   if (fixed_frames < 0) fixed_frames = 0;
@@ -248,8 +329,24 @@ int prepare(uba_handle* h, int fixed_frames) {
   CU(h, h->d_acc.reserve(h->acc_total));
   CU(h, h->d_A.reserve(red));
   CU(h, h->d_rhs.reserve(6 * nfree));
+  // lineariser choice: 1 = generic only; otherwise the tiled kernel plus the generic one for leftovers
+  h->use_tile = h->cfg.linearizer != 1;
+#ifdef UBA_EMU
+  h->use_tile = false;  // the tiled kernel needs real thread blocks
+#endif
+  if (h->use_tile) {
+    build_tile_plan(h, fixed_frames);
+    CU(h, h->d_parts.reserve(h->parts_h.size())); CU(h, h->d_tile_cams.reserve(h->tile_cams_h.size()));
+    CU(h, h->d_pt_mask.reserve(std::max(h->NP, 1))); CU(h, h->d_gen_pts.reserve(h->gen_pts_h.size()));
+    if (!h->parts_h.empty()) CU(h, cudaMemcpyAsync(h->d_parts.p, h->parts_h.data(), sizeof(TilePart) * h->parts_h.size(), cudaMemcpyHostToDevice, h->stream));
+    if (!h->tile_cams_h.empty()) CU(h, cudaMemcpyAsync(h->d_tile_cams.p, h->tile_cams_h.data(), sizeof(int32_t) * h->tile_cams_h.size(), cudaMemcpyHostToDevice, h->stream));
+    if (h->NP) CU(h, cudaMemcpyAsync(h->d_pt_mask.p, h->pt_mask_h.data(), sizeof(uint32_t) * h->NP, cudaMemcpyHostToDevice, h->stream));
+    if (!h->gen_pts_h.empty()) CU(h, cudaMemcpyAsync(h->d_gen_pts.p, h->gen_pts_h.data(), sizeof(int32_t) * h->gen_pts_h.size(), cudaMemcpyHostToDevice, h->stream));
+  }
   CU(h, cudaStreamSynchronize(h->stream));
   DevView& V = h->V;
+  V.parts = h->d_parts.p; V.n_parts = h->use_tile ? (int)h->parts_h.size() : 0; V.tile_cams = h->d_tile_cams.p; V.pt_mask = h->d_pt_mask.p;
+  V.gen_pts = h->d_gen_pts.p; V.n_gen = h->use_tile ? (int)h->gen_pts_h.size() : 0;
   V.free_cam = h->d_free_cam.p; V.free_list = h->d_free_list.p; V.w_free_off = h->d_w_free_off.p; V.w_red_off = h->d_w_red_off.p;
   V.Sacc = h->d_acc.p; V.Bacc = h->d_acc.p + h->off_Bacc; V.vacc = h->d_acc.p + h->off_vacc; V.zh = h->d_acc.p + h->off_zh;
   V.w_lin = h->d_acc.p + h->off_wlin; V.w_post = h->d_acc.p + h->off_wpost; V.w_max = h->d_acc.p + h->off_wmax;
@@ -280,11 +377,28 @@ struct PhaseTimer {
   }
 };
 
+// Debug outputs (residuals, W, C, ...) only exist in the generic kernel, so a parity dump runs it over
+// every point and, when the tiled kernel is selected, runs the tiled kernel for the accumulators.
+int launch_linearizers(uba_handle* h, const DebugOut& dbg) {
+  const bool want_dbg = dbg.residuals || dbg.weights || dbg.C || dbg.W || dbg.grad_pts || dbg.lam_pts;
+  if (!h->use_tile) return launch_lin_generic(h->V, dbg, false, h->stream);
+  int n = 0;
+  if (want_dbg) {
+    // generic pass for the per-observation dumps, then discard what it accumulated
+    n += launch_lin_generic(h->V, dbg, false, h->stream);
+    cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream);
+  }
+  n += launch_lin_tile(h->V, h->stream);
+  DebugOut none{};
+  n += launch_lin_generic(h->V, none, true, h->stream);
+  return n;
+}
+
 // the linearise + Schur pass (the roofline kernel of the hot path)
 int run_linearize(uba_handle* h, const DebugOut& dbg) {
   CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
   PhaseTimer t(h, 0);
-  h->timing.kernel_launches += launch_lin_generic(h->V, dbg, h->stream);
+  h->timing.kernel_launches += launch_linearizers(h, dbg);
   h->timing.linearize_launches++;
   t.stop();
   if (h->comm) {
@@ -818,7 +932,7 @@ int uba_time_linearize(uba_handle* h, int fixed_frames, double radius, int repea
     if (do_flush) { rc = flush_l2(h); if (rc) return rc; }
     CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
     cudaEventRecord(h->ev[4], h->stream);
-    h->timing.kernel_launches += launch_lin_generic(h->V, none, h->stream);
+    h->timing.kernel_launches += launch_linearizers(h, none);
     h->timing.linearize_launches++;
     cudaEventRecord(h->ev[5], h->stream);
     CU(h, cudaEventSynchronize(h->ev[5]));

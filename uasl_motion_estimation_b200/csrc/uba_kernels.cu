@@ -104,11 +104,13 @@ __global__ void k_init_state(DevView V, double initial_radius) {
 // fast path and this one is its fallback and the parity/debug path (DebugOut).
 // ---------------------------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D) {
+__global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D, int only_listed) {
   constexpr int NR = (M == 4) ? 3 : 2;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = p < V.NP;
-  int w = in_range ? V.pt_win[p] : V.pt_win[V.NP - 1];
+  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int count = only_listed ? V.n_gen : V.NP;
+  const bool in_range = tix < count;
+  const int p = only_listed ? V.gen_pts[in_range ? tix : count - 1] : (in_range ? tix : count - 1);
+  int w = V.pt_win[p];
   const WinState* st = &V.ws[w];
   const bool live = in_range && st->done == 0;
   int o0 = 0, o1 = 0;
@@ -264,6 +266,295 @@ __global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D) {
   win_add(V.w_lin, WL_COUNT, w, WL_FAIL, fail, active);
   win_max(V.w_max, w, gmax, active);
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// tiled lineariser (the fast path): one CTA per part (TilePart).  No global atomics in the loop:
+//   * every thread owns output tiles in REGISTERS for the whole part —
+//       phase 1 role: thread (point-in-chunk, camera slot) owns the 6x6 camera block B and the
+//                     gradient v of its slot;
+//       phase 2 role: thread (camera-pair block, K-group) owns one 6x6 block of sum_j Z_a Z_b^T
+//                     (and sum_j Z_a h_j on the diagonal);
+//   * per chunk of points, the Schur factors Z = W L^-T (6x3 per observation) are staged in
+//     shared memory and consumed by the phase-2 threads (a small SYRK over the chunk's points);
+//   * one flush per part: tiles are summed across threads through shared memory and only the sums
+//     go to global memory (fp64 red.global.add).
+// Observations of a chunk are read with coalesced 8-byte loads from the SoA feature arrays (point-
+// sorted order makes the (point, slot) thread grid hit consecutive observations).
+// ---------------------------------------------------------------------------------------------
+#ifndef UBA_EMU
+constexpr int kZStride = 19;   // doubles per staged Z (18 + 1 pad: conflict-free 64-bit stores)
+constexpr int kFlushStride = 43;
+
+template <int M>
+__global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
+  constexpr int NR = (M == 4) ? 3 : 2;
+  constexpr int NT = kTileThreads;
+  extern __shared__ double sm[];
+  const TilePart part = V.parts[blockIdx.x];
+  const int w = part.window;
+  const WinState* st = &V.ws[w];
+  if (st->done) return;
+  const int t = threadIdx.x;
+  const int nl = part.n_local, nfx = part.n_fixed, nlf = nl - nfx;
+  const int cur = st->cur;
+  const double radius = st->radius;
+  const bool scale_ready = st->scale_ready != 0;
+  const int cbase = V.w_cam_off[w];
+  // shared memory carve-up
+  double* camS = sm;                                  // [kTileMaxLocal][kCamStride]
+  double* CgS = camS + kTileMaxLocal * kCamStride;    // [NT][9]   per point: C (6, upper) and g (3)
+  double* hS = CgS + NT * 9;                          // [NT][3]
+  unsigned* maskS = reinterpret_cast<unsigned*>(hS + NT * 3);  // [NT]
+  double* big = reinterpret_cast<double*>(maskS + NT);        // union { Es [NT][9] | Zs [NT][kZStride] | flush [NT][kFlushStride] }
+  __shared__ int s_free[kTileMaxLocal];               // compact index of each local slot (-1 fixed)
+  __shared__ int s_gc[kTileMaxLocal];                 // global camera index of each local slot
+
+  for (int i = t; i < nl * kCamStride; i += NT) {
+    const int sl = i / kCamStride, k = i % kCamStride;
+    const int gc = cbase + V.tile_cams[part.cam_list_off + sl];
+    camS[i] = V.camR[cur][(size_t)gc * kCamStride + k];
+    if (k == 0) { s_gc[sl] = gc; s_free[sl] = V.free_cam[gc]; }
+  }
+  // phase-1 role
+  const int Pc = NT / nl;
+  const int pl = t / nl, sl = t - pl * nl;
+  const bool p1_thread = pl < Pc;
+  const bool my_free = sl >= nfx;
+  // phase-2 role: block (a, b), a <= b, among the nlf free slots; K-group kg
+  const int nblk = nlf * (nlf + 1) / 2;
+  const int G = nblk ? NT / nblk : 0;
+  const int kg = nblk ? t / nblk : 0;
+  const bool p2_thread = nblk && kg < G;
+  int ba = 0, bb = 0;
+  if (p2_thread) {
+    int r = t - kg * nblk;
+    while (r >= nlf - ba) { r -= nlf - ba; ba++; }
+    bb = ba + r;
+  }
+  const bool diag = ba == bb;
+  double acc[36], zacc[6], Bq[21], vq[6];
+#pragma unroll
+  for (int i = 0; i < 36; i++) acc[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { zacc[i] = 0.0; vq[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 21; i++) Bq[i] = 0.0;
+  double cost = 0.0, gmax = 0.0, fail = 0.0;
+  __syncthreads();
+
+  for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += Pc) {
+    const int np = min(Pc, part.pt_end - c0);
+    // ---- phase 1a: linearise my observation -------------------------------------------------
+    const bool have_pt = p1_thread && pl < np;
+    const int p = c0 + pl;
+    unsigned mask = 0;
+    double X[3] = {0, 0, 0};
+    double Wm[18];
+    bool seen = false;
+    if (have_pt) {
+      mask = V.pt_mask[p];
+      if (sl == 0) maskS[pl] = mask;
+      seen = (mask >> sl) & 1u;
+      if (mask) { X[0] = V.pts[cur][(size_t)p * 3]; X[1] = V.pts[cur][(size_t)p * 3 + 1]; X[2] = V.pts[cur][(size_t)p * 3 + 2]; }
+    }
+    if (seen) {
+      const int o = V.pt_obs_off[p] + __popc(mask & ((1u << sl) - 1u));
+      double f[M];
+#pragma unroll
+      for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
+      const int cid = (M == 2) ? ((V.obs_cam[o] >> 30) & 1) : 0;
+      double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
+      const double rho0 = obs_linearize<M>(camS + sl * kCamStride, X, f, cid, V.calib, V.loss, rraw, wgt, F, E, rh);
+      cost += 0.5 * rho0;
+      double* es = big + t * 9;
+      double c6[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < NR; a++) {
+        c6[0] += E[a][0] * E[a][0]; c6[1] += E[a][0] * E[a][1]; c6[2] += E[a][0] * E[a][2];
+        c6[3] += E[a][1] * E[a][1]; c6[4] += E[a][1] * E[a][2]; c6[5] += E[a][2] * E[a][2];
+        g3[0] += E[a][0] * rh[a]; g3[1] += E[a][1] * rh[a]; g3[2] += E[a][2] * rh[a];
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) es[i] = c6[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) es[6 + i] = g3[i];
+      if (my_free) {
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+          for (int a = 0; a < NR; a++) vq[r] += F[a][r] * rh[a];
+#pragma unroll
+          for (int c = r; c < 6; c++) {
+#pragma unroll
+            for (int a = 0; a < NR; a++) Bq[q] += F[a][r] * F[a][c];
+            q++;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int a = 0; a < NR; a++) sacc += F[a][r] * E[a][c];
+            Wm[r * 3 + c] = sacc;
+          }
+      }
+    }
+    __syncthreads();
+    // ---- phase 1b: per-point sums of E^T E and E^T r over the point's observations ---------------
+    for (int idx = t; idx < np * 9; idx += NT) {
+      const int q = idx / 9, e = idx - q * 9;
+      unsigned m = maskS[q];
+      double sacc = 0.0;
+      while (m) {
+        const int s2i = __ffs(m) - 1;
+        m &= m - 1;
+        sacc += big[(q * nl + s2i) * 9 + e];
+      }
+      CgS[idx] = sacc;
+    }
+    __syncthreads();
+    // ---- phase 1d: damping, 3x3 factor (redundantly per slot thread), Z = W L^-T -----------------
+    if (have_pt && mask && (seen || sl == (int)__ffs(mask) - 1)) {
+      const double* cg = CgS + pl * 9;
+      const double Cd[3] = {cg[0], cg[3], cg[5]};
+      double s2[3], lam[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        s2[c] = scale_ready ? V.pt_s2[(size_t)p * 3 + c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
+        lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+      }
+      const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
+      const double g[3] = {cg[6], cg[7], cg[8]};
+      double Li[6], h[3] = {0, 0, 0};
+      const bool ok = point_factor(Cdamp, Li);
+      if (ok) linv_mul(Li, g, h);
+      const bool writer = sl == (int)__ffs(mask) - 1;
+      if (writer) {
+        double* rec = V.pt_rec + (size_t)p * kPtRec;
+        if (!ok) {
+          fail += 1.0;
+#pragma unroll
+          for (int i = 0; i < kPtRec; i++) rec[i] = 0.0;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; i++) rec[i] = Li[i];
+#pragma unroll
+          for (int i = 0; i < 3; i++) { rec[6 + i] = h[i]; rec[9 + i] = g[i]; rec[12 + i] = lam[i]; }
+          rec[15] = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const double proj = V.cfg.use_bounds ? clampd(X[c] - g[c], V.calib.lo[c], V.calib.hi[c]) : X[c] - g[c];
+            gmax = fmax(gmax, fabs(X[c] - proj));
+          }
+        }
+        if (!scale_ready) { V.pt_s2[(size_t)p * 3] = s2[0]; V.pt_s2[(size_t)p * 3 + 1] = s2[1]; V.pt_s2[(size_t)p * 3 + 2] = s2[2]; }
+        hS[pl * 3] = h[0]; hS[pl * 3 + 1] = h[1]; hS[pl * 3 + 2] = h[2];
+      }
+      if (seen && my_free) {
+        double* z = big + (size_t)(pl * nlf + (sl - nfx)) * kZStride;
+        if (ok) {
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            // Z[r][m] = sum_{c<=m} W[r][c] Linv[m][c]
+            z[r * 3 + 0] = Wm[r * 3] * Li[0];
+            z[r * 3 + 1] = Wm[r * 3] * Li[1] + Wm[r * 3 + 1] * Li[2];
+            z[r * 3 + 2] = Wm[r * 3] * Li[3] + Wm[r * 3 + 1] * Li[4] + Wm[r * 3 + 2] * Li[5];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 18; i++) z[i] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: camera-pair blocks, acc += Z_a Z_b^T over my K-group's points ------------------
+    if (p2_thread) {
+      for (int q = kg; q < np; q += G) {
+        const unsigned m = maskS[q] >> nfx;
+        if (!((m >> ba) & 1u) || !((m >> bb) & 1u)) continue;
+        const double* za = big + (size_t)(q * nlf + ba) * kZStride;
+        const double* zb = big + (size_t)(q * nlf + bb) * kZStride;
+        double A[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) A[i] = za[i];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          const double b0 = zb[c * 3], b1 = zb[c * 3 + 1], b2 = zb[c * 3 + 2];
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc[r * 6 + c] += A[r * 3] * b0 + A[r * 3 + 1] * b1 + A[r * 3 + 2] * b2;
+        }
+        if (diag) {
+          const double h0 = hS[q * 3], h1 = hS[q * 3 + 1], h2 = hS[q * 3 + 2];
+#pragma unroll
+          for (int r = 0; r < 6; r++) zacc[r] += A[r * 3] * h0 + A[r * 3 + 1] * h1 + A[r * 3 + 2] * h2;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- flush: Schur tiles --------------------------------------------------------------------
+  const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+  double* S = V.Sacc + V.w_red_off[w];
+  if (p2_thread) {
+    double* o = big + (size_t)t * kFlushStride;
+#pragma unroll
+    for (int i = 0; i < 36; i++) o[i] = acc[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) o[36 + i] = zacc[i];
+  }
+  __syncthreads();
+  for (int idx = t; idx < nblk * 42; idx += NT) {
+    const int blk = idx / 42, e = idx - blk * 42;
+    double sacc = 0.0;
+    for (int k2 = 0; k2 < G; k2++) sacc += big[(size_t)(k2 * nblk + blk) * kFlushStride + e];
+    int a = 0, r = blk;
+    while (r >= nlf - a) { r -= nlf - a; a++; }
+    const int b = a + r;
+    const int fa = s_free[nfx + a], fb = s_free[nfx + b];
+    if (e < 36) {
+      if (sacc != 0.0) atomicAdd(&S[(size_t)(6 * fa + e / 6) * n + 6 * fb + e % 6], sacc);
+    } else if (a == b) {
+      if (sacc != 0.0) atomicAdd(&V.zh[(size_t)s_gc[nfx + a] * 6 + (e - 36)], sacc);
+    }
+  }
+  __syncthreads();
+  // ---- flush: camera blocks B and gradients v ----------------------------------------------------
+  if (p1_thread && my_free) {
+    double* o = big + (size_t)t * 27;
+#pragma unroll
+    for (int i = 0; i < 21; i++) o[i] = Bq[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) o[21 + i] = vq[i];
+  }
+  __syncthreads();
+  for (int idx = t; idx < nlf * 27; idx += NT) {
+    const int s2i = nfx + idx / 27, e = idx % 27;
+    double sacc = 0.0;
+    for (int q = 0; q < Pc; q++) sacc += big[(size_t)(q * nl + s2i) * 27 + e];
+    if (sacc == 0.0) continue;
+    const int gc = s_gc[s2i];
+    if (e < 21) {
+      int r = 0, k2 = e;
+      while (k2 >= 6 - r) { k2 -= 6 - r; r++; }
+      atomicAdd(&V.Bacc[(size_t)gc * 36 + r * 6 + r + k2], sacc);
+    } else {
+      atomicAdd(&V.vacc[(size_t)gc * 6 + (e - 21)], sacc);
+    }
+  }
+  // ---- per-window scalars ------------------------------------------------------------------------
+  cost = warp_sum(cost); fail = warp_sum(fail); gmax = warp_max(gmax);
+  if (warp_leader()) {
+    if (cost != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_COST], cost);
+    if (fail != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_FAIL], fail);
+    if (gmax > 0.0) atomic_max_nonneg(&V.w_max[w], gmax);
+  }
+}
+#endif  // !UBA_EMU
 
 // ---------------------------------------------------------------------------------------------
 // assemble the damped reduced camera system  A = B + Lambda_c - sum_j Z Z^T,  rhs = v - sum_j Z h
@@ -775,12 +1066,42 @@ int launch_init_state(const DevView& V, double initial_radius, cudaStream_t st) 
   return 1;
 }
 
-int launch_lin_generic(const DevView& V, const DebugOut& dbg, cudaStream_t st) {
-  if (V.NP == 0) return 0;
-  const int grid = (V.NP + 127) / 128;
-  if (V.M == 4) UBA_LAUNCH(k_lin_generic<4>, grid, 128, 0, st, V, dbg);
-  else UBA_LAUNCH(k_lin_generic<2>, grid, 128, 0, st, V, dbg);
+int launch_lin_generic(const DevView& V, const DebugOut& dbg, bool only_listed, cudaStream_t st) {
+  const int count = only_listed ? V.n_gen : V.NP;
+  if (count == 0) return 0;
+  const int grid = (count + 127) / 128;
+  const int listed = only_listed ? 1 : 0;
+  if (V.M == 4) UBA_LAUNCH(k_lin_generic<4>, grid, 128, 0, st, V, dbg, listed);
+  else UBA_LAUNCH(k_lin_generic<2>, grid, 128, 0, st, V, dbg, listed);
   return 1;
+}
+
+
+size_t lin_tile_smem_bytes() {
+#ifdef UBA_EMU
+  return 0;
+#else
+  return sizeof(double) * (kTileMaxLocal * kCamStride + kTileThreads * 9 + kTileThreads * 3 + kTileThreads / 2 + kTileThreads * kFlushStride);
+#endif
+}
+
+int launch_lin_tile(const DevView& V, cudaStream_t st) {
+  if (V.n_parts == 0) return 0;
+#ifdef UBA_EMU
+  (void)st;
+  return 0;
+#else
+  const size_t smem = lin_tile_smem_bytes();
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_lin_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_lin_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  if (V.M == 4) UBA_LAUNCH(k_lin_tile<4>, V.n_parts, kTileThreads, smem, st, V);
+  else UBA_LAUNCH(k_lin_tile<2>, V.n_parts, kTileThreads, smem, st, V);
+  return 1;
+#endif
 }
 
 int launch_assemble(const DevView& V, int max_n, cudaStream_t st) {
