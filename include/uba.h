@@ -92,6 +92,7 @@ typedef struct uba_config {
   int32_t device;                  /* CUDA device ordinal; default 0 (or LOCAL_RANK under torchrun) */
   int32_t linearizer;              /* 0 auto, 1 generic (global fp64 atomics), 2 segment-local tiles */
   int32_t compute_covariance;      /* CalibrationParameters::compute_cov (:40); default 0 */
+  int32_t solver;                  /* 0 auto (banded LDL^T for large block-banded systems), 1 dense Cholesky only */
 } uba_config;
 
 /* Per-window result of uba_optimise (ceres::Solver::Summary, as far as the reference uses it). */

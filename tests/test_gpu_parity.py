@@ -69,9 +69,10 @@ def test_reference_termination_rules(gpu_lib, oracle):
     assert rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
 
 
-def test_large_window_dense_solver_path(gpu_lib, oracle):
-    """200 keyframes -> reduced system 1188 x 1188: the blocked global-memory Cholesky."""
-    win, cfg, h = make(gpu_lib, "c4", 0.05, fixed_iterations=3)
+@pytest.mark.parametrize("solver", [0, 1])
+def test_large_window_solver_paths(gpu_lib, oracle, solver):
+    """200 keyframes -> reduced system 1188 x 1188: banded LDL^T (solver 0) and blocked dense Cholesky (solver 1)."""
+    win, cfg, h = make(gpu_lib, "c4", 0.05, fixed_iterations=3, solver=solver)
     assert 6 * int((h.tables(2)["free_cam"] >= 0).sum()) > 160
     rc, sums = h.optimise(2)
     o = oracle.optimise(win, cfg, 2)

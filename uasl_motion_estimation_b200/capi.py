@@ -46,7 +46,7 @@ class Config(C.Structure):
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
                 ("max_consecutive_invalid_steps", C.c_int32), ("max_solver_time_s", C.c_double),
                 ("fixed_iterations", C.c_int32), ("jacobi_scaling", C.c_int32), ("use_bounds", C.c_int32),
-                ("device", C.c_int32), ("linearizer", C.c_int32), ("compute_covariance", C.c_int32)]
+                ("device", C.c_int32), ("linearizer", C.c_int32), ("compute_covariance", C.c_int32), ("solver", C.c_int32)]
 
 
 class Summary(C.Structure):

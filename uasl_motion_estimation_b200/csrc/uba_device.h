@@ -70,6 +70,8 @@ struct DevView {
   const int32_t* w_free_off;  // [nW+1] offsets into free_list
   const int64_t* w_red_off;   // [nW+1] offsets into Sacc / A (sum of n^2)
   const int32_t* free_list;   // global camera index of each free camera, window by window
+  const int32_t* w_beta;      // [nW] > 0: the reduced system is banded with this scalar half-bandwidth and
+                              //      is solved by k_chol_banded (k_assemble then only builds lambda and rhs)
   // cameras (global index = w_cam_off[w] + local)
   double* cams[2];            // [NC][6]
   double* camR[2];            // [NC][kCamStride]
@@ -131,8 +133,9 @@ int launch_cam_prep(const DevView& V, int parity, cudaStream_t st);
 int launch_lin_generic(const DevView& V, const DebugOut& dbg, bool only_listed, cudaStream_t st);
 int launch_lin_tile(const DevView& V, cudaStream_t st);
 int launch_assemble(const DevView& V, int max_n, cudaStream_t st);
-// h_win_n: host array [nW] of reduced-system sizes (6 * free cameras)
-int launch_solve(const DevView& V, const int* h_win_n, int max_small_n, cudaStream_t st);
+// h_win_n: host array [nW] of reduced-system sizes (6 * free cameras); h_win_beta: [nW] banded half-bandwidth or 0
+int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st);
+constexpr int kBandMaxBeta = 63;
 int solve_small_limit();
 int launch_backsub(const DevView& V, cudaStream_t st);
 int launch_lm_update(const DevView& V, cudaStream_t st);

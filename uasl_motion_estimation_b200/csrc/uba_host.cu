@@ -111,7 +111,8 @@ struct uba_handle {
   std::vector<int32_t> cam_win_h, pt_win_h;
   // prepared for a given fixed_frames
   int prepared_fixed = -1;
-  std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n;
+  std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n, win_beta;
+  DevBuf<int32_t> d_w_beta;
   std::vector<int64_t> w_red_off_h;
   int max_n = 0;
   bool use_tile = false;
@@ -139,6 +140,11 @@ struct uba_handle {
   NcclApi nccl;
   void* comm = nullptr;
   int rank = 0, n_ranks = 1;
+  // CUDA graph of one LM iteration (re-captured whenever the device view changes)
+#ifndef UBA_EMU
+  cudaGraphExec_t graph_exec = nullptr;
+#endif
+  int64_t graph_kernels = 0;
   // timing
   bool profiling = false;
   uba_timing timing{};
@@ -172,7 +178,16 @@ uba::Calib make_calib(const uba_calib& in, int M, bool use_bounds) {
   return k;
 }
 
+void drop_graph(uba_handle* h) {
+#ifndef UBA_EMU
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+#else
+  (void)h;
+#endif
+}
+
 void fill_view_static(uba_handle* h) {
+  drop_graph(h);
   DevView& V = h->V;
   V.M = h->M; V.nW = h->nW; V.NC = h->NC; V.NP = h->NP; V.NO = h->NO;
   V.w_cam_off = h->d_w_cam_off.p; V.w_pt_off = h->d_w_pt_off.p;
@@ -257,10 +272,10 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     close_item(s1);
   }
   // parts: aim at a few CTAs per SM, never less than 4 chunks of points per CTA
-  const size_t target_parts = 4 * 148;
+  const size_t target_parts = 2 * 148;
   for (const Item& it : items) {
     const int Pc = kTileThreads / it.nl;
-    int part_pts = std::max<size_t>(4 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
+    int part_pts = std::max<size_t>(8 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
     part_pts = ((part_pts + Pc - 1) / Pc) * Pc;
     for (int b = it.begin; b < it.end; b += part_pts) {
       TilePart p{};
@@ -274,6 +289,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
 int prepare(uba_handle* h, int fixed_frames) {
   if (fixed_frames < 0) fixed_frames = 0;
   if (h->prepared_fixed == fixed_frames) return UBA_OK;
+  drop_graph(h);
   const int nW = h->nW, NC = h->NC;
   if (h->comm) {
     // point-sharded: a camera is in the problem if ANY rank observes it -> max over ranks
@@ -306,12 +322,44 @@ int prepare(uba_handle* h, int fixed_frames) {
     h->w_red_off_h[w + 1] = h->w_red_off_h[w] + (int64_t)36 * nf * nf;
     h->max_n = std::max(h->max_n, 6 * nf);
   }
+  // block half-bandwidth of each window's reduced system (largest spread of free cameras inside a track);
+  // big windows with a narrow band (c4, c5) go to the banded solver
+  h->win_beta.assign(nW, 0);
+  for (int w = 0; w < nW; w++) {
+    if (h->win_n[w] <= solve_small_limit()) continue;
+    int bw = 0;
+    for (int s2 = h->w_pt_off[w]; s2 < h->w_pt_off[w + 1]; s2++) {
+      int lo = INT_MAX, hi = -1;
+      for (int o = h->pt_obs_off_int[s2]; o < h->pt_obs_off_int[s2 + 1]; o++) {
+        const int f = h->free_cam_h[h->w_cam_off[w] + (h->h_obs_cam.p[o] & 0x3fffffff)];
+        if (f >= 0) { lo = std::min(lo, f); hi = std::max(hi, f); }
+      }
+      if (hi >= 0) bw = std::max(bw, hi - lo);
+    }
+    if (h->comm) {  // every rank must take the same path: the band is the max over ranks
+      double v = bw;
+      CU(h, h->d_cam_lam.reserve(std::max<size_t>((size_t)NC * 6, 1)));
+      CU(h, cudaMemcpyAsync(h->d_cam_lam.p, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      int rc = allreduce(h, h->d_cam_lam.p, 1, kNcclMax);
+      if (rc) return rc;
+      CU(h, cudaMemcpyAsync(&v, h->d_cam_lam.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+      bw = (int)v;
+    }
+    const int beta = 6 * bw + 5;
+    if (beta <= kBandMaxBeta && h->cfg.solver != 1) h->win_beta[w] = beta;
+  }
+#ifdef UBA_EMU
+  h->win_beta.assign(nW, 0);  // the emulation only has the dense stand-in solver
+#endif
   const size_t nfree = h->free_list_h.size();
   const size_t red = (size_t)h->w_red_off_h[nW];
   CU(h, h->d_free_cam.reserve(NC));
   CU(h, h->d_free_list.reserve(nfree));
   CU(h, h->d_w_free_off.reserve(nW + 1));
   CU(h, h->d_w_red_off.reserve(nW + 1));
+  CU(h, h->d_w_beta.reserve(nW));
+  CU(h, cudaMemcpyAsync(h->d_w_beta.p, h->win_beta.data(), sizeof(int32_t) * nW, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_free_cam.p, h->free_cam_h.data(), sizeof(int32_t) * NC, cudaMemcpyHostToDevice, h->stream));
   if (nfree) CU(h, cudaMemcpyAsync(h->d_free_list.p, h->free_list_h.data(), sizeof(int32_t) * nfree, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_w_free_off.p, h->w_free_off_h.data(), sizeof(int32_t) * (nW + 1), cudaMemcpyHostToDevice, h->stream));
@@ -347,6 +395,7 @@ int prepare(uba_handle* h, int fixed_frames) {
   DevView& V = h->V;
   V.parts = h->d_parts.p; V.n_parts = h->use_tile ? (int)h->parts_h.size() : 0; V.tile_cams = h->d_tile_cams.p; V.pt_mask = h->d_pt_mask.p;
   V.gen_pts = h->d_gen_pts.p; V.n_gen = h->use_tile ? (int)h->gen_pts_h.size() : 0;
+  V.w_beta = h->d_w_beta.p;
   V.free_cam = h->d_free_cam.p; V.free_list = h->d_free_list.p; V.w_free_off = h->d_w_free_off.p; V.w_red_off = h->d_w_red_off.p;
   V.Sacc = h->d_acc.p; V.Bacc = h->d_acc.p + h->off_Bacc; V.vacc = h->d_acc.p + h->off_vacc; V.zh = h->d_acc.p + h->off_zh;
   V.w_lin = h->d_acc.p + h->off_wlin; V.w_post = h->d_acc.p + h->off_wpost; V.w_max = h->d_acc.p + h->off_wmax;
@@ -417,7 +466,7 @@ int run_iteration(uba_handle* h) {
   {
     PhaseTimer t(h, 1);
     h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
-    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), solve_small_limit(), h->stream);
+    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), h->win_beta.data(), solve_small_limit(), h->stream);
     t.stop();
   }
   {
@@ -439,6 +488,34 @@ int run_iteration(uba_handle* h) {
     t.stop();
   }
   return UBA_OK;
+}
+
+// One LM iteration, replayed from a CUDA graph when nothing needs host attention in between
+// (no per-phase profiling, no NCCL on this handle).
+int run_iteration_fast(uba_handle* h) {
+#ifndef UBA_EMU
+  if (!h->profiling && !h->comm) {
+    if (!h->graph_exec) {
+      cudaGraph_t g = nullptr;
+      const int64_t before = h->timing.kernel_launches, lin_before = h->timing.linearize_launches;
+      CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = run_iteration(h);
+      const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+      h->graph_kernels = h->timing.kernel_launches - before;
+      h->timing.kernel_launches = before; h->timing.linearize_launches = lin_before;
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) return fail(h, UBA_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+      const cudaError_t e2 = cudaGraphInstantiate(&h->graph_exec, g, 0);
+      cudaGraphDestroy(g);
+      if (e2 != cudaSuccess) { h->graph_exec = nullptr; return fail(h, UBA_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e2)); }
+    }
+    CU(h, cudaGraphLaunch(h->graph_exec, h->stream));
+    h->timing.kernel_launches += h->graph_kernels;
+    h->timing.linearize_launches++;
+    return UBA_OK;
+  }
+#endif
+  return run_iteration(h);
 }
 
 int start_solve(uba_handle* h, int fixed_frames) {
@@ -619,6 +696,7 @@ void uba_config_default(uba_config* c) {
   c->device = lr ? std::atoi(lr) : 0;
   c->linearizer = 0;
   c->compute_covariance = 0;              // CalibrationParameters::compute_cov defaults to false (:42-43)
+  c->solver = 0;
 }
 
 const char* uba_last_error(const uba_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -650,6 +728,7 @@ void uba_destroy(uba_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graph(h);
   if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
   h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release();
   h->d_cams.release(); h->d_camR.release(); h->d_cam_s2.release(); h->d_cam_lam.release(); h->d_cam_y.release(); h->d_pts.release();
@@ -729,7 +808,11 @@ int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearizat
   D.residuals = h->d_dbg.p; D.weights = D.residuals + n_res; D.C = D.weights + n_w; D.W = D.C + n_C; D.grad_pts = D.W + n_W; D.lam_pts = D.grad_pts + n_g;
   rc = run_linearize(h, D);
   if (rc) return rc;
+  // the parity dump wants the dense damped matrix even for windows the banded solver would handle
+  std::vector<int32_t> zeros(h->nW, 0);
+  CU(h, cudaMemcpyAsync(h->d_w_beta.p, zeros.data(), sizeof(int32_t) * h->nW, cudaMemcpyHostToDevice, h->stream));
   h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
+  CU(h, cudaMemcpyAsync(h->d_w_beta.p, h->win_beta.data(), sizeof(int32_t) * h->nW, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaGetLastError());
   std::vector<double> tmp;
@@ -782,7 +865,7 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
   }
   bool time_capped = false;
   for (int it = 0; it < max_it; it++) {
-    rc = run_iteration(h);
+    rc = run_iteration_fast(h);
     if (rc) return rc;
     if (!fixedK) {
       // convergence is decided on the device; the host only needs to know when every window is done
@@ -958,7 +1041,7 @@ int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int do_f
     if (do_flush) rc = flush_l2(h);
     if (rc) break;
     cudaEventRecord(h->ev[4], h->stream);
-    rc = run_iteration(h);
+    rc = run_iteration_fast(h);
     cudaEventRecord(h->ev[5], h->stream);
     if (rc) break;
     if (cudaEventSynchronize(h->ev[5]) != cudaSuccess) { rc = fail(h, UBA_ERR_CUDA, "event sync failed"); break; }

@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
   double* camS = sm;                                  // [kTileMaxLocal][kCamStride]
   double* CgS = camS + kTileMaxLocal * kCamStride;    // [NT][9]   per point: C (6, upper) and g (3)
   double* hS = CgS + NT * 9;                          // [NT][3]
-  unsigned* maskS = reinterpret_cast<unsigned*>(hS + NT * 3);  // [NT]
+  double* LiS = hS + NT * 3;                          // [NT][6] inverse Cholesky factor of each point block
+  unsigned* maskS = reinterpret_cast<unsigned*>(LiS + NT * 6);  // [NT]
   double* big = reinterpret_cast<double*>(maskS + NT);        // union { Es [NT][9] | Zs [NT][kZStride] | flush [NT][kFlushStride] }
   __shared__ int s_free[kTileMaxLocal];               // compact index of each local slot (-1 fixed)
   __shared__ int s_gc[kTileMaxLocal];                 // global camera index of each local slot
@@ -371,9 +372,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
       double c6[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
 #pragma unroll
       for (int a = 0; a < NR; a++) {
-        c6[0] += E[a][0] * E[a][0]; c6[1] += E[a][0] * E[a][1]; c6[2] += E[a][0] * E[a][2];
-        c6[3] += E[a][1] * E[a][1]; c6[4] += E[a][1] * E[a][2]; c6[5] += E[a][2] * E[a][2];
-        g3[0] += E[a][0] * rh[a]; g3[1] += E[a][1] * rh[a]; g3[2] += E[a][2] * rh[a];
+        c6[0] = fma(E[a][0], E[a][0], c6[0]); c6[1] = fma(E[a][0], E[a][1], c6[1]); c6[2] = fma(E[a][0], E[a][2], c6[2]);
+        c6[3] = fma(E[a][1], E[a][1], c6[3]); c6[4] = fma(E[a][1], E[a][2], c6[4]); c6[5] = fma(E[a][2], E[a][2], c6[5]);
+        g3[0] = fma(E[a][0], rh[a], g3[0]); g3[1] = fma(E[a][1], rh[a], g3[1]); g3[2] = fma(E[a][2], rh[a], g3[2]);
       }
 #pragma unroll
       for (int i = 0; i < 6; i++) es[i] = c6[i];
@@ -384,11 +385,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
 #pragma unroll
         for (int r = 0; r < 6; r++) {
 #pragma unroll
-          for (int a = 0; a < NR; a++) vq[r] += F[a][r] * rh[a];
+          for (int a = 0; a < NR; a++) vq[r] = fma(F[a][r], rh[a], vq[r]);
 #pragma unroll
           for (int c = r; c < 6; c++) {
 #pragma unroll
-            for (int a = 0; a < NR; a++) Bq[q] += F[a][r] * F[a][c];
+            for (int a = 0; a < NR; a++) Bq[q] = fma(F[a][r], F[a][c], Bq[q]);
             q++;
           }
         }
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
           for (int c = 0; c < 3; c++) {
             double sacc = 0.0;
 #pragma unroll
-            for (int a = 0; a < NR; a++) sacc += F[a][r] * E[a][c];
+            for (int a = 0; a < NR; a++) sacc = fma(F[a][r], E[a][c], sacc);
             Wm[r * 3 + c] = sacc;
           }
       }
@@ -417,29 +418,33 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
       CgS[idx] = sacc;
     }
     __syncthreads();
-    // ---- phase 1d: damping, 3x3 factor (redundantly per slot thread), Z = W L^-T -----------------
-    if (have_pt && mask && (seen || sl == (int)__ffs(mask) - 1)) {
-      const double* cg = CgS + pl * 9;
-      const double Cd[3] = {cg[0], cg[3], cg[5]};
-      double s2[3], lam[3];
+    // ---- phase 1c: one thread per point: damping, 3x3 factor, h = L^-1 g, point record -----------
+    if (t < np) {
+      const unsigned pm = maskS[t];
+      if (pm) {
+        const int pp = c0 + t;
+        const double* cg = CgS + t * 9;
+        const double Cd[3] = {cg[0], cg[3], cg[5]};
+        const double Xp[3] = {V.pts[cur][(size_t)pp * 3], V.pts[cur][(size_t)pp * 3 + 1], V.pts[cur][(size_t)pp * 3 + 2]};
+        double s2[3], lam[3];
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        s2[c] = scale_ready ? V.pt_s2[(size_t)p * 3 + c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
-        lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
-      }
-      const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
-      const double g[3] = {cg[6], cg[7], cg[8]};
-      double Li[6], h[3] = {0, 0, 0};
-      const bool ok = point_factor(Cdamp, Li);
-      if (ok) linv_mul(Li, g, h);
-      const bool writer = sl == (int)__ffs(mask) - 1;
-      if (writer) {
-        double* rec = V.pt_rec + (size_t)p * kPtRec;
+        for (int c = 0; c < 3; c++) {
+          s2[c] = scale_ready ? V.pt_s2[(size_t)pp * 3 + c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
+          lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+        }
+        const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
+        const double g[3] = {cg[6], cg[7], cg[8]};
+        double Li[6] = {0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
+        const bool ok = point_factor(Cdamp, Li);
+        double* rec = V.pt_rec + (size_t)pp * kPtRec;
         if (!ok) {
           fail += 1.0;
 #pragma unroll
+          for (int i = 0; i < 6; i++) Li[i] = 0.0;
+#pragma unroll
           for (int i = 0; i < kPtRec; i++) rec[i] = 0.0;
         } else {
+          linv_mul(Li, g, h);
 #pragma unroll
           for (int i = 0; i < 6; i++) rec[i] = Li[i];
 #pragma unroll
@@ -447,27 +452,28 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
           rec[15] = 0.0;
 #pragma unroll
           for (int c = 0; c < 3; c++) {
-            const double proj = V.cfg.use_bounds ? clampd(X[c] - g[c], V.calib.lo[c], V.calib.hi[c]) : X[c] - g[c];
-            gmax = fmax(gmax, fabs(X[c] - proj));
+            const double proj = V.cfg.use_bounds ? clampd(Xp[c] - g[c], V.calib.lo[c], V.calib.hi[c]) : Xp[c] - g[c];
+            gmax = fmax(gmax, fabs(Xp[c] - proj));
           }
         }
-        if (!scale_ready) { V.pt_s2[(size_t)p * 3] = s2[0]; V.pt_s2[(size_t)p * 3 + 1] = s2[1]; V.pt_s2[(size_t)p * 3 + 2] = s2[2]; }
-        hS[pl * 3] = h[0]; hS[pl * 3 + 1] = h[1]; hS[pl * 3 + 2] = h[2];
+        if (!scale_ready) { V.pt_s2[(size_t)pp * 3] = s2[0]; V.pt_s2[(size_t)pp * 3 + 1] = s2[1]; V.pt_s2[(size_t)pp * 3 + 2] = s2[2]; }
+#pragma unroll
+        for (int i = 0; i < 6; i++) LiS[t * 6 + i] = Li[i];
+        hS[t * 3] = h[0]; hS[t * 3 + 1] = h[1]; hS[t * 3 + 2] = h[2];
       }
-      if (seen && my_free) {
-        double* z = big + (size_t)(pl * nlf + (sl - nfx)) * kZStride;
-        if (ok) {
+    }
+    __syncthreads();
+    // ---- phase 1d: Z = W L^-T for my observation (zero if the point block was not positive definite)
+    if (seen && my_free) {
+      const double* Li = LiS + pl * 6;
+      const double l0 = Li[0], l1 = Li[1], l2 = Li[2], l3 = Li[3], l4 = Li[4], l5 = Li[5];
+      double* z = big + (size_t)(pl * nlf + (sl - nfx)) * kZStride;
 #pragma unroll
-          for (int r = 0; r < 6; r++) {
-            // Z[r][m] = sum_{c<=m} W[r][c] Linv[m][c]
-            z[r * 3 + 0] = Wm[r * 3] * Li[0];
-            z[r * 3 + 1] = Wm[r * 3] * Li[1] + Wm[r * 3 + 1] * Li[2];
-            z[r * 3 + 2] = Wm[r * 3] * Li[3] + Wm[r * 3 + 1] * Li[4] + Wm[r * 3 + 2] * Li[5];
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 18; i++) z[i] = 0.0;
-        }
+      for (int r = 0; r < 6; r++) {
+        // Z[r][m] = sum_{c<=m} W[r][c] Linv[m][c]
+        z[r * 3 + 0] = Wm[r * 3] * l0;
+        z[r * 3 + 1] = fma(Wm[r * 3], l1, Wm[r * 3 + 1] * l2);
+        z[r * 3 + 2] = fma(Wm[r * 3], l3, fma(Wm[r * 3 + 1], l4, Wm[r * 3 + 2] * l5));
       }
     }
     __syncthreads();
@@ -485,12 +491,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
         for (int c = 0; c < 6; c++) {
           const double b0 = zb[c * 3], b1 = zb[c * 3 + 1], b2 = zb[c * 3 + 2];
 #pragma unroll
-          for (int r = 0; r < 6; r++) acc[r * 6 + c] += A[r * 3] * b0 + A[r * 3 + 1] * b1 + A[r * 3 + 2] * b2;
+          for (int r = 0; r < 6; r++) acc[r * 6 + c] = fma(A[r * 3], b0, fma(A[r * 3 + 1], b1, fma(A[r * 3 + 2], b2, acc[r * 6 + c])));
         }
         if (diag) {
           const double h0 = hS[q * 3], h1 = hS[q * 3 + 1], h2 = hS[q * 3 + 2];
 #pragma unroll
-          for (int r = 0; r < 6; r++) zacc[r] += A[r * 3] * h0 + A[r * 3 + 1] * h1 + A[r * 3 + 2] * h2;
+          for (int r = 0; r < 6; r++) zacc[r] = fma(A[r * 3], h0, fma(A[r * 3 + 1], h1, fma(A[r * 3 + 2], h2, zacc[r])));
         }
       }
     }
@@ -573,11 +579,13 @@ __global__ void k_assemble(DevView V) {
   double* A = V.A + red;
   double* rhs = V.rhs + (size_t)6 * f0;
   const double radius = st->radius;
-  const int64_t total = (int64_t)n * n + n;
+  const bool banded = V.w_beta[w] > 0;  // k_chol_banded assembles its own matrix entries: only lambda + rhs here
+  const int64_t nmat = banded ? (int64_t)n : (int64_t)n * n;
+  const int64_t total = nmat + n;
   double gmax = 0.0;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    if (e < (int64_t)n * n) {
-      const int i = (int)(e / n), j = (int)(e % n);
+    if (e < nmat) {
+      const int i = banded ? (int)e : (int)(e / n), j = banded ? (int)e : (int)(e % n);
       const int fa = i / 6, r = i % 6, fb = j / 6, c = j % 6;
       double val;
       if (fa == fb) {
@@ -599,9 +607,9 @@ __global__ void k_assemble(DevView V) {
       } else {
         val = -S[(size_t)j * n + i];
       }
-      A[(size_t)i * n + j] = val;
+      if (!banded) A[(size_t)i * n + j] = val;
     } else {
-      const int i = (int)(e - (int64_t)n * n);
+      const int i = (int)(e - nmat);
       const int gc = V.free_list[f0 + i / 6];
       const double v = V.vacc[(size_t)gc * 6 + i % 6];
       rhs[i] = v - V.zh[(size_t)gc * 6 + i % 6];
@@ -623,7 +631,7 @@ __global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n) {
   if (st->done) return;
   const int f0 = V.w_free_off[w];
   const int n = 6 * (V.w_free_off[w + 1] - f0);
-  if (n == 0 || n > max_n) return;
+  if (n == 0 || n > max_n || V.w_beta[w] > 0) return;
   const int ld = n + 1;
   double* a = sm;               // [n][ld]
   double* y = sm + (size_t)n * ld;  // [n]
@@ -762,6 +770,122 @@ __global__ void __launch_bounds__(256) k_chol_update(DevView V, int w, int j0) {
     for (int k = 0; k < nb; k++) s += li[i][k] * lj[j][k];
     A[(size_t)(i0 + i) * n + c0 + j] -= s;
   }
+}
+
+
+// ---- banded reduced systems (large windows whose camera co-visibility is a band: c4, c5) ------
+// Sequential band LDL^T in shared memory, one CTA, ONE barrier per scalar column:
+//   a_ik -= a_ij a_kj / a_jj  for j < k <= i <= j + beta   (the pivot reciprocal is recomputed by
+//   every thread, so no broadcast step is needed), the right-hand side is eliminated in the same
+//   step, and the unit-lower column l_ij = a_ij / a_jj goes to global memory for the backward pass.
+// The matrix is never materialised densely: entries are assembled on the fly from the Schur
+// accumulator, the camera blocks B and the LM damping.  Rows live in a ring of kBandRing rows.
+constexpr int kBandRing = 128;
+constexpr int kBandLoad = 32;
+
+__device__ __forceinline__ double reduced_entry(const DevView& V, int f0, int n, const double* S, int i, int j) {
+  // symmetric entry (i, j), i >= j, read from the upper block triangle of S
+  const int fr = j / 6, r = j - fr * 6, fc = i / 6, c = i - fc * 6;
+  if (fr == fc) {
+    const int gc = V.free_list[f0 + fr];
+    double val = V.Bacc[(size_t)gc * 36 + r * 6 + c] - S[(size_t)(6 * fr + r) * n + 6 * fr + c];
+    if (r == c) val += V.cam_lam[(size_t)gc * 6 + r];
+    return val;
+  }
+  return -S[(size_t)j * n + i];
+}
+
+__global__ void __launch_bounds__(256) k_chol_banded(DevView V, int w, int beta) {
+  extern __shared__ double sm[];
+  const WinState* st = &V.ws[w];
+  if (st->done) return;
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const int bw1 = beta + 1;
+  double* ring = sm;                          // [kBandRing][bw1]: row i holds A[i][i-beta .. i]
+  double* y = ring + (size_t)kBandRing * bw1; // [n]
+  __shared__ int s_fail;
+  const double* S = V.Sacc + V.w_red_off[w];
+  double* rhs = V.rhs + (size_t)6 * f0;
+  double* Lb = V.A + V.w_red_off[w];          // [n][bw1]: column j -> {1/a_jj, l_{j+1,j}, ..., l_{j+beta,j}}
+  const int t = threadIdx.x, nt = blockDim.x;
+  if (t == 0) s_fail = 0;
+  for (int i = t; i < n; i += nt) y[i] = rhs[i];
+  auto load_rows = [&](int r0, int r1) {
+    for (int e = t; e < (r1 - r0) * bw1; e += nt) {
+      const int i = r0 + e / bw1, c = e % bw1;
+      const int k = i - beta + c;
+      ring[(size_t)(i % kBandRing) * bw1 + c] = (i < n && k >= 0) ? reduced_entry(V, f0, n, S, i, k) : 0.0;
+    }
+  };
+  // rows are (re)loaded one slot short of the ring so that the row of the column just finished is never overwritten
+  load_rows(0, min(n, kBandRing - 1));
+  // my (di, dk) pairs of the trailing update, 1 <= dk <= di <= beta
+  const int npairs = beta * (beta + 1) / 2;
+  constexpr int kMaxPer = (kBandMaxBeta * (kBandMaxBeta + 1) / 2 + 255) / 256;
+  int pdi[kMaxPer], pdk[kMaxPer];
+#pragma unroll
+  for (int q = 0; q < kMaxPer; q++) {
+    const int e = t + q * 256;
+    int di = 0, dk = 0;
+    if (e < npairs) {
+      di = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((di + 1) * (di + 2) / 2 <= e) di++;
+      while (di * (di + 1) / 2 > e) di--;
+      dk = e - di * (di + 1) / 2 + 1;
+      di += 1;
+    }
+    pdi[q] = di; pdk[q] = dk;
+  }
+  for (int j = 0; j < n; j++) {
+    if (j > 0 && (j % kBandLoad) == 0) load_rows(j + kBandRing - kBandLoad - 1, min(n, j + kBandRing - 1));
+    __syncthreads();
+    const double piv = ring[(size_t)(j % kBandRing) * bw1 + beta];
+    if (t == 0 && (!(piv > 0.0) || !isfinite(piv))) s_fail = 1;
+    const double inv = 1.0 / piv;
+    const double yj = y[j];
+#pragma unroll
+    for (int q = 0; q < kMaxPer; q++) {
+      const int di = pdi[q], dk = pdk[q];
+      const int i = j + di, k = j + dk;
+      if (di && i < n) {
+        const double aij = ring[(size_t)(i % kBandRing) * bw1 + (beta - di)];
+        const double akj = ring[(size_t)(k % kBandRing) * bw1 + (beta - dk)];
+        ring[(size_t)(i % kBandRing) * bw1 + (beta - di + dk)] -= aij * akj * inv;
+      }
+    }
+    // right-hand side and the column of the unit-lower factor
+    if (t < beta) {
+      const int i = j + 1 + t;
+      if (i < n) {
+        const double l = ring[(size_t)(i % kBandRing) * bw1 + (beta - 1 - t)] * inv;
+        y[i] -= l * yj;
+        Lb[(size_t)j * bw1 + 1 + t] = l;
+      } else {
+        Lb[(size_t)j * bw1 + 1 + t] = 0.0;
+      }
+    } else if (t == beta) {
+      Lb[(size_t)j * bw1] = inv;
+    }
+  }
+  __syncthreads();
+  // D^-1, then the backward pass  L^T x = v  (column oriented, one warp, y stays in shared memory)
+  for (int i = t; i < n; i += nt) y[i] *= Lb[(size_t)i * bw1];
+  __syncthreads();
+  if (t < 32) {
+    for (int i = n - 1; i > 0; i--) {
+      const double xi = y[i];
+      for (int d = t + 1; d <= beta; d += 32) {
+        const int j = i - d;
+        if (j >= 0) y[j] -= Lb[(size_t)j * bw1 + d] * xi;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const bool failed = s_fail != 0;
+  for (int i = t; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
+  if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
 
 // blocked forward + backward substitution with the factor in global memory; one CTA
@@ -1081,7 +1205,7 @@ size_t lin_tile_smem_bytes() {
 #ifdef UBA_EMU
   return 0;
 #else
-  return sizeof(double) * (kTileMaxLocal * kCamStride + kTileThreads * 9 + kTileThreads * 3 + kTileThreads / 2 + kTileThreads * kFlushStride);
+  return sizeof(double) * (kTileMaxLocal * kCamStride + kTileThreads * 9 + kTileThreads * 3 + kTileThreads * 6 + kTileThreads / 2 + kTileThreads * kFlushStride);
 #endif
 }
 
@@ -1116,11 +1240,12 @@ int launch_assemble(const DevView& V, int max_n, cudaStream_t st) {
 
 int solve_small_limit() { return 160; }
 
-int launch_solve(const DevView& V, const int* h_win_n, int max_small_n, cudaStream_t st) {
+int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st) {
   int launches = 0;
   int small_max = 0, n_large = 0;
   for (int w = 0; w < V.nW; w++) {
-    if (h_win_n[w] <= max_small_n) small_max = h_win_n[w] > small_max ? h_win_n[w] : small_max;
+    if (h_win_beta[w] > 0) n_large++;
+    else if (h_win_n[w] <= max_small_n) small_max = h_win_n[w] > small_max ? h_win_n[w] : small_max;
     else n_large++;
   }
 #ifdef UBA_EMU
@@ -1140,6 +1265,14 @@ int launch_solve(const DevView& V, const int* h_win_n, int max_small_n, cudaStre
   if (n_large) {
     for (int w = 0; w < V.nW; w++) {
       const int n = h_win_n[w];
+      if (h_win_beta[w] > 0) {
+        const int beta = h_win_beta[w];
+        const size_t smem = ((size_t)kBandRing * (beta + 1) + n) * sizeof(double);
+        cudaFuncSetAttribute(k_chol_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        UBA_LAUNCH(k_chol_banded, 1, 256, smem, st, V, w, beta);
+        launches++;
+        continue;
+      }
       if (n <= max_small_n) continue;
       for (int j0 = 0; j0 < n; j0 += NB) {
         const int nb = n - j0 < NB ? n - j0 : NB;
