@@ -275,7 +275,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   const size_t target_parts = 2 * 148;
   for (const Item& it : items) {
     const int Pc = kTileThreads / it.nl;
-    int part_pts = std::max<size_t>(8 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
+    int part_pts = std::max<size_t>(2 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
     part_pts = ((part_pts + Pc - 1) / Pc) * Pc;
     for (int b = it.begin; b < it.end; b += part_pts) {
       TilePart p{};
@@ -1053,6 +1053,14 @@ int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int do_f
   if (rc) return rc;
   CU(h, cudaGetLastError());
   *ms_per_iteration = total / iterations;
+  return UBA_OK;
+}
+
+// debug: first `count` doubles of the generic lineariser's scratch (kernel instrumentation builds only)
+int uba_debug_read_zbuf(uba_handle* h, double* out, int count) {
+  if (!h || !out) return UBA_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  CU(h, cudaMemcpy(out, h->d_Zbuf.p, sizeof(double) * count, cudaMemcpyDeviceToHost));
   return UBA_OK;
 }
 

@@ -562,6 +562,30 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
 }
 #endif  // !UBA_EMU
 
+// LM damping of camera column r of camera gc (B_rr = d); the Jacobi scale is captured at iteration 0.
+__device__ __forceinline__ double cam_damping(const DevView& V, const WinState* st, int gc, int r, double d, bool store) {
+  double s2;
+  if (!st->scale_ready) { s2 = jacobi_s2(d, V.cfg.jacobi_scaling); if (store) V.cam_s2[(size_t)gc * 6 + r] = s2; }
+  else s2 = V.cam_s2[(size_t)gc * 6 + r];
+  const double lam = lm_lambda(d, s2, st->radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+  if (store) V.cam_lam[(size_t)gc * 6 + r] = lam;
+  return lam;
+}
+
+// symmetric entry (i, j), i >= j, of the damped reduced camera matrix, read from the upper block
+// triangle of the Schur accumulator, the camera blocks B and the LM damping
+__device__ __forceinline__ double reduced_entry(const DevView& V, const WinState* st, int f0, int n, const double* S, int i, int j) {
+  const int fr = j / 6, r = j - fr * 6, fc = i / 6, c = i - fc * 6;
+  if (fr == fc) {
+    const int gc = V.free_list[f0 + fr];
+    const double b = V.Bacc[(size_t)gc * 36 + r * 6 + c];
+    double val = b - S[(size_t)(6 * fr + r) * n + 6 * fr + c];
+    if (r == c) val += cam_damping(V, st, gc, r, b, false);
+    return val;
+  }
+  return -S[(size_t)j * n + i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // assemble the damped reduced camera system  A = B + Lambda_c - sum_j Z Z^T,  rhs = v - sum_j Z h
 // grid: (blocks, nW)
@@ -578,8 +602,8 @@ __global__ void k_assemble(DevView V) {
   const double* S = V.Sacc + red;
   double* A = V.A + red;
   double* rhs = V.rhs + (size_t)6 * f0;
-  const double radius = st->radius;
-  const bool banded = V.w_beta[w] > 0;  // k_chol_banded assembles its own matrix entries: only lambda + rhs here
+  // banded windows: pass 1 (this loop) builds lambda on the diagonal + rhs; pass 2 (below) writes the band
+  const bool banded = V.w_beta[w] > 0;
   const int64_t nmat = banded ? (int64_t)n : (int64_t)n * n;
   const int64_t total = nmat + n;
   double gmax = 0.0;
@@ -593,15 +617,7 @@ __global__ void k_assemble(DevView V) {
         const double* B = V.Bacc + (size_t)gc * 36;
         const int rr = r < c ? r : c, cc = r < c ? c : r;
         val = B[rr * 6 + cc] - S[(size_t)(6 * fa + rr) * n + 6 * fa + cc];
-        if (r == c) {
-          const double d = B[r * 6 + r];
-          double s2;
-          if (!st->scale_ready) { s2 = jacobi_s2(d, V.cfg.jacobi_scaling); V.cam_s2[(size_t)gc * 6 + r] = s2; }
-          else s2 = V.cam_s2[(size_t)gc * 6 + r];
-          const double lam = lm_lambda(d, s2, radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
-          V.cam_lam[(size_t)gc * 6 + r] = lam;
-          val += lam;
-        }
+        if (r == c) val += cam_damping(V, st, gc, r, B[r * 6 + r], true);
       } else if (fa < fb) {
         val = -S[(size_t)i * n + j];
       } else {
@@ -618,73 +634,149 @@ __global__ void k_assemble(DevView V) {
   }
   gmax = warp_max(gmax);
   if (warp_leader() && gmax > 0.0) atomic_max_nonneg(&V.w_max[w], gmax);
+  if (banded) {
+    // compact band copy for k_chol_banded: Ab[i][c] = A[i][i - beta + c], stored after the factor rows
+    const int beta = V.w_beta[w], bw1 = beta + 1;
+    double* Ab = A + (size_t)n * bw1;
+    const int64_t nb = (int64_t)n * bw1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nb; e += (int64_t)gridDim.x * blockDim.x) {
+      const int i = (int)(e / bw1), c = (int)(e - (int64_t)i * bw1);
+      const int k = i - beta + c;
+      Ab[e] = k >= 0 ? reduced_entry(V, st, f0, n, S, i, k) : 0.0;
+    }
+  }
 }
 
 #ifndef UBA_EMU
 // ---------------------------------------------------------------------------------------------
 // dense Cholesky solve, one CTA per window, matrix resident in shared memory (n <= max_n)
 // ---------------------------------------------------------------------------------------------
+// 6x6 Cholesky of a diagonal block held in registers (lower triangle of L[6][6]), one thread,
+// right-looking so that only rsqrt -> mul -> fma sits on the dependent chain of each pivot.
+// inv[c] = 1 / L_cc.  Returns false on a non-positive pivot.
+__device__ __forceinline__ bool chol6(double (&L)[6][6], double (&inv)[6]) {
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    double d = L[c][c];
+    if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }
+    const double iv = rsqrt(d);
+    inv[c] = iv;
+    L[c][c] = d * iv;
+#pragma unroll
+    for (int r = 0; r < 6; r++) if (r > c) L[r][c] *= iv;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int k = 0; k < 6; k++) if (r > c && k > c && k <= r) L[r][k] = fma(-L[r][c], L[k][c], L[r][k]);
+  }
+  return ok;
+}
+
+// Dense Cholesky solve, one CTA per window, matrix resident in shared memory (n = 6 nf <= max_n).
+// Left-looking by 6-wide block columns (a camera block): per block column one dot-product update of
+// the column (all threads), one serial 6x6 factor (one thread), one triangular solve of the rows
+// below (thread per row).  The right-hand side rides along as row n, so the forward substitution is
+// free; the backward substitution is blocked the same way.  Barriers: 3 + 2 per BLOCK column.
 __global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n) {
   extern __shared__ double sm[];
   const int w = blockIdx.x;
   WinState* st = &V.ws[w];
   if (st->done) return;
   const int f0 = V.w_free_off[w];
-  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const int nf = V.w_free_off[w + 1] - f0;
+  const int n = 6 * nf;
   if (n == 0 || n > max_n || V.w_beta[w] > 0) return;
-  const int ld = n + 1;
-  double* a = sm;               // [n][ld]
-  double* y = sm + (size_t)n * ld;  // [n]
+  const int ld = n + 1;                 // odd: conflict-free column walks
+  double* a = sm;                       // [n + 1][ld], row n = right-hand side
+  double* invd = sm + (size_t)(n + 1) * ld;  // [n] 1 / L_cc
   __shared__ int s_fail;
-  const double* A = V.A + V.w_red_off[w];
+  double* A = V.A + V.w_red_off[w];
   double* rhs = V.rhs + (size_t)6 * f0;
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) s_fail = 0;
-  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j <= i) a[i * ld + j] = A[(size_t)i * n + j]; }
-  for (int i = tid; i < n; i += nt) y[i] = rhs[i];
+  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; if (j <= i) a[i * ld + j] = A[(size_t)i * n + j]; }
+  for (int i = tid; i < n; i += nt) a[n * ld + i] = rhs[i];
   __syncthreads();
-  // right-looking column Cholesky (lower)
-  for (int j = 0; j < n; j++) {
+  for (int kb = 0; kb < nf; kb++) {
+    const int c0 = 6 * kb;
+    // (1) left-looking update of block column kb (rows c0 .. n, the rhs row included)
+    if (kb > 0) {
+      for (int e = tid; e < (n + 1 - c0) * 6; e += nt) {
+        const int i = c0 + e / 6, c = c0 + e % 6;
+        if (c <= i) {
+          const double* ri = a + i * ld;
+          const double* rc = a + c * ld;
+          double s0 = 0.0, s1 = 0.0;
+          int m = 0;
+          for (; m + 1 < c0; m += 2) { s0 = fma(ri[m], rc[m], s0); s1 = fma(ri[m + 1], rc[m + 1], s1); }
+          if (m < c0) s0 = fma(ri[m], rc[m], s0);
+          a[i * ld + c] -= s0 + s1;
+        }
+      }
+      __syncthreads();
+    }
+    // (2) serial 6x6 factor of the diagonal block
     if (tid == 0) {
-      const double d = a[j * ld + j];
-      if (!(d > 0.0) || !isfinite(d)) { s_fail = 1; a[j * ld + j] = 1.0; }
-      else a[j * ld + j] = sqrt(d);
+      double L[6][6], iv[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) L[r][c] = c <= r ? a[(c0 + r) * ld + c0 + c] : 0.0;
+      if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        invd[c0 + r] = iv[r];
+#pragma unroll
+        for (int c = 0; c < 6; c++) if (c <= r) a[(c0 + r) * ld + c0 + c] = L[r][c];
+      }
     }
     __syncthreads();
-    const double dinv = 1.0 / a[j * ld + j];
-    for (int i = j + 1 + tid; i < n; i += nt) a[i * ld + j] *= dinv;
-    __syncthreads();
-    const int m = n - j - 1;
-    // trailing update of the lower triangle: rows i > j, cols j < k <= i
-    for (int e = tid; e < m * m; e += nt) {
-      const int ii = e / m, kk = e % m;
-      if (kk <= ii) { const int i = j + 1 + ii, k = j + 1 + kk; a[i * ld + k] -= a[i * ld + j] * a[k * ld + j]; }
+    // (3) rows below (and the rhs row): X L_kk^T = A
+    for (int i = c0 + 6 + tid; i <= n; i += nt) {
+      double x[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        double v = a[i * ld + c0 + c];
+#pragma unroll
+        for (int m = 0; m < 6; m++) if (m < c) v = fma(-x[m], a[(c0 + c) * ld + c0 + m], v);
+        x[c] = v * invd[c0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) a[i * ld + c0 + c] = x[c];
     }
     __syncthreads();
   }
-  // forward / backward substitution by one warp (n is small)
-  if (tid < 32) {
-    for (int i = 0; i < n; i++) {
-      double s = 0.0;
-      for (int k = tid; k < i; k += 32) s += a[i * ld + k] * y[k];
-      s = warp_sum(s);
-      if (tid == 0) y[i] = (y[i] - s) / a[i * ld + i];
-      __syncwarp();
+  // backward substitution L^T x = z (z sits in row n), blocked
+  double* z = a + n * ld;
+  for (int kb = nf - 1; kb >= 0; kb--) {
+    const int c0 = 6 * kb;
+    if (tid == 0) {
+#pragma unroll
+      double xb[6];
+#pragma unroll
+      for (int c = 5; c >= 0; c--) {
+        double v = z[c0 + c];
+#pragma unroll
+        for (int m = 0; m < 6; m++) if (m > c) v = fma(-a[(c0 + m) * ld + c0 + c], xb[m], v);
+        xb[c] = v * invd[c0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) z[c0 + c] = xb[c];
     }
-    for (int i = n - 1; i >= 0; i--) {
-      double s = 0.0;
-      for (int k = i + 1 + tid; k < n; k += 32) s += a[k * ld + i] * y[k];
-      s = warp_sum(s);
-      if (tid == 0) y[i] = (y[i] - s) / a[i * ld + i];
-      __syncwarp();
+    __syncthreads();
+    for (int i = tid; i < c0; i += nt) {
+      double v = z[i];
+#pragma unroll
+      for (int c = 0; c < 6; c++) v = fma(-a[(c0 + c) * ld + i], z[c0 + c], v);
+      z[i] = v;
     }
+    __syncthreads();
   }
-  __syncthreads();
   const bool failed = s_fail != 0;
-  for (int i = tid; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
-  // keep the factor for the covariance extraction
-  double* Aout = V.A + V.w_red_off[w];
-  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e % n; if (j <= i) Aout[(size_t)i * n + j] = a[i * ld + j]; }
+  for (int i = tid; i < n; i += nt) rhs[i] = failed ? 0.0 : z[i];
+  // keep the factor (lower triangle) for the covariance extraction
+  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; if (j <= i) A[(size_t)i * n + j] = a[i * ld + j]; }
   if (tid == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
 
@@ -780,21 +872,17 @@ __global__ void __launch_bounds__(256) k_chol_update(DevView V, int w, int j0) {
 //   step, and the unit-lower column l_ij = a_ij / a_jj goes to global memory for the backward pass.
 // The matrix is never materialised densely: entries are assembled on the fly from the Schur
 // accumulator, the camera blocks B and the LM damping.  Rows live in a ring of kBandRing rows.
-constexpr int kBandRing = 128;
-constexpr int kBandLoad = 32;
+constexpr int kBandRing = 126;  // multiple of 6: a block of rows never straddles the wrap
 
-__device__ __forceinline__ double reduced_entry(const DevView& V, int f0, int n, const double* S, int i, int j) {
-  // symmetric entry (i, j), i >= j, read from the upper block triangle of S
-  const int fr = j / 6, r = j - fr * 6, fc = i / 6, c = i - fc * 6;
-  if (fr == fc) {
-    const int gc = V.free_list[f0 + fr];
-    double val = V.Bacc[(size_t)gc * 36 + r * 6 + c] - S[(size_t)(6 * fr + r) * n + 6 * fr + c];
-    if (r == c) val += V.cam_lam[(size_t)gc * 6 + r];
-    return val;
-  }
-  return -S[(size_t)j * n + i];
-}
-
+// Band Cholesky by 6-wide block columns (right-looking), one CTA.  Per block column:
+//   (2) one thread: serial 6x6 factor of the diagonal block (register resident, right-looking);
+//   (3) thread per row below the block inside the band (+ one thread for the rhs "row"): X L_kk^T = A;
+//   (4) trailing update of the band window (PER (row,row) pairs per thread, 6 FMAs each), rhs update,
+//       factor rows out to global memory (Lt[i] = {1/L_ii, L_{i,i-1}, ..., L_{i,i-beta}}).
+// Three barriers per BLOCK column.  The band was assembled by k_assemble (Ab); rows stream through a
+// ring of kBandRing rows in shared memory.  The backward substitution is blocked the same way with the
+// factor rows staged back through shared memory.
+template <int PER>
 __global__ void __launch_bounds__(256) k_chol_banded(DevView V, int w, int beta) {
   extern __shared__ double sm[];
   const WinState* st = &V.ws[w];
@@ -802,87 +890,204 @@ __global__ void __launch_bounds__(256) k_chol_banded(DevView V, int w, int beta)
   const int f0 = V.w_free_off[w];
   const int n = 6 * (V.w_free_off[w + 1] - f0);
   const int bw1 = beta + 1;
+  const int ring_size = kBandRing * bw1;
   double* ring = sm;                          // [kBandRing][bw1]: row i holds A[i][i-beta .. i]
-  double* y = ring + (size_t)kBandRing * bw1; // [n]
+  double* y = ring + ring_size;               // [n + beta + 7] (tail zero-padded)
   __shared__ int s_fail;
-  const double* S = V.Sacc + V.w_red_off[w];
+  __shared__ double s_inv[6], s_z[6];
   double* rhs = V.rhs + (size_t)6 * f0;
-  double* Lb = V.A + V.w_red_off[w];          // [n][bw1]: column j -> {1/a_jj, l_{j+1,j}, ..., l_{j+beta,j}}
+  double* Lt = V.A + V.w_red_off[w];
+  const double* Ab = Lt + (size_t)n * bw1;
   const int t = threadIdx.x, nt = blockDim.x;
   if (t == 0) s_fail = 0;
-  for (int i = t; i < n; i += nt) y[i] = rhs[i];
+  for (int i = t; i < n + beta + 7; i += nt) y[i] = i < n ? rhs[i] : 0.0;
+  // rows beyond n are zero-filled, so the elimination needs no bounds checks
   auto load_rows = [&](int r0, int r1) {
     for (int e = t; e < (r1 - r0) * bw1; e += nt) {
-      const int i = r0 + e / bw1, c = e % bw1;
-      const int k = i - beta + c;
-      ring[(size_t)(i % kBandRing) * bw1 + c] = (i < n && k >= 0) ? reduced_entry(V, f0, n, S, i, k) : 0.0;
+      const int i = r0 + e / bw1;
+      ring[(i % kBandRing) * bw1 + e % bw1] = i < n ? Ab[(size_t)r0 * bw1 + e] : 0.0;
     }
   };
-  // rows are (re)loaded one slot short of the ring so that the row of the column just finished is never overwritten
-  load_rows(0, min(n, kBandRing - 1));
-  // my (di, dk) pairs of the trailing update, 1 <= dk <= di <= beta
+  load_rows(0, kBandRing);
+  // trailing-update pairs (ti >= tk) over the beta rows below the block
   const int npairs = beta * (beta + 1) / 2;
-  constexpr int kMaxPer = (kBandMaxBeta * (kBandMaxBeta + 1) / 2 + 255) / 256;
-  int pdi[kMaxPer], pdk[kMaxPer];
+  int pti[PER], ptk[PER];
 #pragma unroll
-  for (int q = 0; q < kMaxPer; q++) {
+  for (int q = 0; q < PER; q++) {
     const int e = t + q * 256;
-    int di = 0, dk = 0;
+    int ti = -1, tk = 0;
     if (e < npairs) {
-      di = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((di + 1) * (di + 2) / 2 <= e) di++;
-      while (di * (di + 1) / 2 > e) di--;
-      dk = e - di * (di + 1) / 2 + 1;
-      di += 1;
+      int d0 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((d0 + 1) * (d0 + 2) / 2 <= e) d0++;
+      while (d0 * (d0 + 1) / 2 > e) d0--;
+      ti = d0; tk = e - d0 * (d0 + 1) / 2;
     }
-    pdi[q] = di; pdk[q] = dk;
+    pti[q] = ti; ptk[q] = tk;
   }
-  for (int j = 0; j < n; j++) {
-    if (j > 0 && (j % kBandLoad) == 0) load_rows(j + kBandRing - kBandLoad - 1, min(n, j + kBandRing - 1));
-    __syncthreads();
-    const double piv = ring[(size_t)(j % kBandRing) * bw1 + beta];
-    if (t == 0 && (!(piv > 0.0) || !isfinite(piv))) s_fail = 1;
-    const double inv = 1.0 / piv;
-    const double yj = y[j];
+  const int nblk = n / 6;
+  int o0 = 0;                                 // ring offset of row c0 (blocks never straddle the wrap)
+#ifdef UBA_BAND_TIMING
+  long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tq = clock64();
+#define TICK(k) { const long long now_ = clock64(); tm[k] += now_ - tq; tq = now_; }
+#else
+#define TICK(k)
+#endif
+  for (int kb = 0; kb < nblk; kb++) {
+    const int c0 = 6 * kb;
+    // ring reload (30 rows every 5 blocks): global loads are issued here and land in registers while the
+    // block is processed; they are written to the (dead) ring slots just before the block's last barrier
+    constexpr int kPre = (30 * (kBandMaxBeta + 1) + 255) / 256;
+    double pre[kPre];
+    const bool reload = kb > 0 && (kb % 5) == 0;
+    if (reload) {
+      const int r0 = c0 + kBandRing - 30;
 #pragma unroll
-    for (int q = 0; q < kMaxPer; q++) {
-      const int di = pdi[q], dk = pdk[q];
-      const int i = j + di, k = j + dk;
-      if (di && i < n) {
-        const double aij = ring[(size_t)(i % kBandRing) * bw1 + (beta - di)];
-        const double akj = ring[(size_t)(k % kBandRing) * bw1 + (beta - dk)];
-        ring[(size_t)(i % kBandRing) * bw1 + (beta - di + dk)] -= aij * akj * inv;
+      for (int q = 0; q < kPre; q++) {
+        const int e = t + q * 256;
+        const int i = r0 + e / bw1;
+        pre[q] = (e < 30 * bw1 && i < n) ? Ab[(size_t)r0 * bw1 + e] : 0.0;
       }
     }
-    // right-hand side and the column of the unit-lower factor
-    if (t < beta) {
-      const int i = j + 1 + t;
-      if (i < n) {
-        const double l = ring[(size_t)(i % kBandRing) * bw1 + (beta - 1 - t)] * inv;
-        y[i] -= l * yj;
-        Lb[(size_t)j * bw1 + 1 + t] = l;
+    TICK(0)
+    const double* blk = ring + o0;            // rows c0 .. c0+5: entry (c0+r, c0+c) at blk[r*bw1 + beta - r + c]
+    // (2) serial factor of the diagonal block
+    if (t == 0) {
+      double L[6][6], iv[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) L[r][c] = c <= r ? blk[r * bw1 + beta - r + c] : 0.0;
+      if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        s_inv[r] = iv[r];
+#pragma unroll
+        for (int c = 0; c < 6; c++) if (c <= r) ring[o0 + r * bw1 + beta - r + c] = L[r][c];
+      }
+    }
+    TICK(1)
+    __syncthreads();
+    TICK(2)
+    // (3) rows below the block inside the band, and the rhs: X L_kk^T = A (right-looking in registers)
+    if (t <= beta) {
+      const bool is_rhs = t == beta;
+      int orow = o0 + (6 + t) * bw1; if (orow >= ring_size) orow -= ring_size;
+      double* row = ring + orow;
+      const int base = beta - 6 - t;          // column offset of (i, c0); entries with base + c < 0 lie outside the band
+      double x[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((base + c >= 0) ? row[base + c] : 0.0);
+#pragma unroll
+      for (int c = 0; c < 6; c++) {
+        x[c] *= s_inv[c];
+#pragma unroll
+        for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], blk[m * bw1 + beta - m + c], x[m]);
+      }
+      if (is_rhs) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
       } else {
-        Lb[(size_t)j * bw1 + 1 + t] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) if (base + c >= 0) row[base + c] = x[c];
       }
-    } else if (t == beta) {
-      Lb[(size_t)j * bw1] = inv;
+    }
+    TICK(3)
+    __syncthreads();
+    TICK(4)
+    // (4) trailing update of the band window, rhs update, factor rows out
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+      const int ti = pti[q], tk = ptk[q];
+      if (ti >= 0) {
+        int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
+        int ok = o0 + (6 + tk) * bw1; if (ok >= ring_size) ok -= ring_size;
+        const double* ri = ring + oi + (beta - 6 - ti);
+        const double* rk = ring + ok + (beta - 6 - tk);
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) if (beta - 6 - ti + c >= 0) acc = fma(ri[c], rk[c], acc);
+        ring[oi + (beta - ti + tk)] -= acc;
+      }
+    }
+    if (t >= 64 && t < 64 + beta) {
+      // rhs: y_i -= sum_c L[i][c0+c] z_c ; and row i of the factor (this block's columns) to global memory
+      const int tt = t - 64, i = c0 + 6 + tt;
+      int orow = o0 + (6 + tt) * bw1; if (orow >= ring_size) orow -= ring_size;
+      const double* row = ring + orow;
+      const int base = beta - 6 - tt;
+      double acc = 0.0;
+#pragma unroll
+      for (int c = 0; c < 6; c++)
+        if (base + c >= 0) {
+          const double l = row[base + c];
+          acc = fma(l, s_z[c], acc);
+          if (i < n) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
+        }
+      y[i] -= acc;
+    } else if (t >= 160 && t < 166) {
+      // rows of the diagonal block
+      const int r = t - 160;
+      Lt[(size_t)(c0 + r) * bw1] = s_inv[r];
+      for (int c = 0; c < r; c++) Lt[(size_t)(c0 + r) * bw1 + (r - c)] = blk[r * bw1 + beta - r + c];
+    }
+    if (reload) {
+      const int r0 = c0 + kBandRing - 30;
+#pragma unroll
+      for (int q = 0; q < kPre; q++) {
+        const int e = t + q * 256;
+        if (e < 30 * bw1) ring[((r0 + e / bw1) % kBandRing) * bw1 + e % bw1] = pre[q];
+      }
+    }
+    TICK(5)
+    __syncthreads();
+    TICK(6)
+    o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
+  }
+#ifdef UBA_BAND_TIMING
+  if (t == 0 || t == 1 || t == 70 || t == 200) { for (int k = 0; k < 8; k++) V.Zbuf[(t == 0 ? 0 : t == 1 ? 8 : t == 70 ? 16 : 24) + k] = (double)tm[k]; }
+  tq = clock64();
+#endif
+  // backward substitution L^T x = z, blocked; factor rows staged through shared memory in chunks
+  constexpr int kChunk = 126;
+  for (int i1 = n; i1 > 0; i1 -= kChunk) {
+    const int i0 = max(0, i1 - kChunk);
+    for (int e = t; e < (i1 - i0) * bw1; e += nt) {
+      const int i = i0 + e / bw1, c = e % bw1;
+      ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
+    }
+    __syncthreads();
+    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6) {
+      const double* blk = ring + (c0 - i0) * bw1;   // row c0 + m at blk + m*bw1: [0] = 1/L, [d] = L[c0+m][c0+m-d]
+      if (t == 0) {
+        double xb[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
+#pragma unroll
+        for (int c = 5; c >= 0; c--) {
+          xb[c] *= blk[c * bw1];
+#pragma unroll
+          for (int m = 0; m < 6; m++) if (m < c) xb[m] = fma(-blk[c * bw1 + (c - m)], xb[c], xb[m]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_z[c] = xb[c]; }
+      }
+      __syncthreads();
+      if (t < beta) {
+        const int j = c0 - 1 - t;
+        if (j >= 0) {
+          double v = y[j];
+#pragma unroll
+          for (int c = 0; c < 6; c++) { const int d = c0 + c - j; if (d <= beta) v = fma(-blk[c * bw1 + d], s_z[c], v); }
+          y[j] = v;
+        }
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
-  // D^-1, then the backward pass  L^T x = v  (column oriented, one warp, y stays in shared memory)
-  for (int i = t; i < n; i += nt) y[i] *= Lb[(size_t)i * bw1];
-  __syncthreads();
-  if (t < 32) {
-    for (int i = n - 1; i > 0; i--) {
-      const double xi = y[i];
-      for (int d = t + 1; d <= beta; d += 32) {
-        const int j = i - d;
-        if (j >= 0) y[j] -= Lb[(size_t)j * bw1 + d] * xi;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
+#ifdef UBA_BAND_TIMING
+  if (t == 0) V.Zbuf[32] = (double)(clock64() - tq);
+#endif
   const bool failed = s_fail != 0;
   for (int i = t; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
   if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
@@ -1253,7 +1458,7 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
   (void)small_max; (void)n_large;
 #else
   if (small_max > 0) {
-    const size_t smem = ((size_t)small_max * (small_max + 1) + small_max) * sizeof(double);
+    const size_t smem = ((size_t)(small_max + 1) * (small_max + 1) + small_max) * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
       cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1267,9 +1472,12 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
       const int n = h_win_n[w];
       if (h_win_beta[w] > 0) {
         const int beta = h_win_beta[w];
-        const size_t smem = ((size_t)kBandRing * (beta + 1) + n) * sizeof(double);
-        cudaFuncSetAttribute(k_chol_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        UBA_LAUNCH(k_chol_banded, 1, 256, smem, st, V, w, beta);
+        const size_t smem = ((size_t)kBandRing * (beta + 1) + n + beta + 8) * sizeof(double);
+        const int per = (beta * (beta + 1) / 2 + 255) / 256;
+        if (per <= 1) { cudaFuncSetAttribute(k_chol_banded<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<1>, 1, 256, smem, st, V, w, beta); }
+        else if (per <= 2) { cudaFuncSetAttribute(k_chol_banded<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<2>, 1, 256, smem, st, V, w, beta); }
+        else if (per <= 4) { cudaFuncSetAttribute(k_chol_banded<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<4>, 1, 256, smem, st, V, w, beta); }
+        else { cudaFuncSetAttribute(k_chol_banded<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<8>, 1, 256, smem, st, V, w, beta); }
         launches++;
         continue;
       }
