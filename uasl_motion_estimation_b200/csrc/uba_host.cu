@@ -108,6 +108,8 @@ struct uba_handle {
   std::vector<int32_t> obs_internal;               // [NO] caller obs id per internal obs slot
   std::vector<int32_t> pt_obs_off_int;             // [NP+1]
   std::vector<char> cam_seen;                      // [NC]
+  std::vector<int32_t> pt_lo, pt_hi;               // [NP] lowest / highest camera of each internal point slot (-1: none)
+  std::vector<char> pt_contig;                     // [NP] the track is a run of consecutive cameras, strictly ascending
   std::vector<int32_t> cam_win_h, pt_win_h;
   // prepared for a given fixed_frames
   int prepared_fixed = -1;
@@ -226,17 +228,25 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   for (int w = 0; w < h->nW; w++) {
     const int s0 = h->w_pt_off[w], s1 = h->w_pt_off[w + 1];
     int item_begin = -1, min_len = 0;
+    bool uni_range = true;   // the union is the camera range [ulo, uhi] (true as long as only contiguous tracks were merged)
+    int ulo = 0, uhi = -1;
     uni.clear();
     auto close_item = [&](int end) {
       if (item_begin < 0) return;
+      if (uni_range) { uni.clear(); for (int c = ulo; c <= uhi; c++) uni.push_back(c); }
       Item it{w, item_begin, end, (int)h->tile_cams_h.size(), (int)uni.size(), 0};
       for (int c : uni) { h->tile_cams_h.push_back(c); if (c < fixed_frames) it.nfx++; }
       for (int s = item_begin; s < end; s++) {
         if (h->pt_mask_h[s] != 1u) { h->pt_mask_h[s] = 0u; continue; }  // 1u marks a tile point until here
         unsigned m = 0;
-        for (int o = h->pt_obs_off_int[s]; o < h->pt_obs_off_int[s + 1]; o++) {
-          const int c = h->h_obs_cam.p[o] & 0x3fffffff;
-          m |= 1u << (unsigned)(std::lower_bound(uni.begin(), uni.end(), c) - uni.begin());
+        if (uni_range) {
+          const int k = h->pt_hi[s] - h->pt_lo[s] + 1;
+          m = (k >= 32 ? 0xffffffffu : ((1u << k) - 1u)) << (unsigned)(h->pt_lo[s] - ulo);
+        } else {
+          for (int o = h->pt_obs_off_int[s]; o < h->pt_obs_off_int[s + 1]; o++) {
+            const int c = h->h_obs_cam.p[o] & 0x3fffffff;
+            m |= 1u << (unsigned)(std::lower_bound(uni.begin(), uni.end(), c) - uni.begin());
+          }
         }
         h->pt_mask_h[s] = m;
         tile_points++;
@@ -247,6 +257,25 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     for (int s = s0; s < s1; s++) {
       const int o0 = h->pt_obs_off_int[s], k = h->pt_obs_off_int[s + 1] - o0;
       if (k == 0) continue;
+      const int lo = h->pt_lo[s], hi = h->pt_hi[s];
+      if (h->pt_contig[s]) {
+        const int nfree = hi - std::max(lo, fixed_frames) + 1;
+        if (k > kTileMaxLocal || nfree > kTileMaxFree) { h->gen_pts_h.push_back(s); continue; }
+        bool ok = item_begin >= 0 && uni_range;
+        int nlo = lo, nhi = hi;
+        if (ok) {
+          nlo = std::min(ulo, lo); nhi = std::max(uhi, hi);
+          // a gap between the union and the track would put cameras in the list that nobody sees
+          const bool touching = lo <= uhi + 1 && hi >= ulo - 1;
+          const int size = nhi - nlo + 1, nf = nhi - std::max(nlo, fixed_frames) + 1;
+          ok = touching && size <= kTileMaxLocal && nf <= kTileMaxFree && std::min(min_len, k) >= tau * (double)size;
+        }
+        if (!ok) { close_item(s); uni_range = true; ulo = lo; uhi = hi; min_len = k; item_begin = s; }
+        else { ulo = nlo; uhi = nhi; min_len = std::min(min_len, k); }
+        h->pt_mask_h[s] = 1u;
+        continue;
+      }
+      // general track: explicit camera list
       cams_p.clear();
       bool ascending = true;
       int nfree = 0;
@@ -259,6 +288,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       if (!ascending || k > kTileMaxLocal || nfree > kTileMaxFree) { h->gen_pts_h.push_back(s); continue; }
       bool ok = item_begin >= 0;
       if (ok) {
+        if (uni_range) { uni.clear(); for (int c = ulo; c <= uhi; c++) uni.push_back(c); }
         merged.clear();
         std::set_union(uni.begin(), uni.end(), cams_p.begin(), cams_p.end(), std::back_inserter(merged));
         int nf = 0;
@@ -267,6 +297,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       }
       if (!ok) { close_item(s); uni = cams_p; min_len = k; item_begin = s; }
       else { uni.swap(merged); min_len = std::min(min_len, k); }
+      uni_range = false;
       h->pt_mask_h[s] = 1u;
     }
     close_item(s1);
@@ -328,13 +359,17 @@ int prepare(uba_handle* h, int fixed_frames) {
   for (int w = 0; w < nW; w++) {
     if (h->win_n[w] <= solve_small_limit()) continue;
     int bw = 0;
+    // free indices grow with the camera index, so the spread of a track is free(hi) - free(first free camera >= lo)
+    std::vector<int> next_free(h->w_cam_off[w + 1] - h->w_cam_off[w] + 1, -1);
+    for (int c = h->w_cam_off[w + 1] - h->w_cam_off[w] - 1; c >= 0; c--) {
+      const int f = h->free_cam_h[h->w_cam_off[w] + c];
+      next_free[c] = f >= 0 ? f : next_free[c + 1];
+    }
     for (int s2 = h->w_pt_off[w]; s2 < h->w_pt_off[w + 1]; s2++) {
-      int lo = INT_MAX, hi = -1;
-      for (int o = h->pt_obs_off_int[s2]; o < h->pt_obs_off_int[s2 + 1]; o++) {
-        const int f = h->free_cam_h[h->w_cam_off[w] + (h->h_obs_cam.p[o] & 0x3fffffff)];
-        if (f >= 0) { lo = std::min(lo, f); hi = std::max(hi, f); }
-      }
-      if (hi >= 0) bw = std::max(bw, hi - lo);
+      if (h->pt_hi[s2] < 0) continue;
+      const int fhi = h->free_cam_h[h->w_cam_off[w] + h->pt_hi[s2]];  // the highest camera of a track is observed, hence free unless fixed
+      const int flo = next_free[h->pt_lo[s2]];
+      if (fhi >= 0 && flo >= 0) bw = std::max(bw, fhi - flo);
     }
     if (h->comm) {  // every rank must take the same path: the band is the max over ranks
       double v = bw;
@@ -533,6 +568,7 @@ int upload_state(uba_handle* h) {
   return UBA_OK;
 }
 
+#define TT(label) if (getenv("UBA_TRACE")) { auto now_ = std::chrono::steady_clock::now(); fprintf(stderr, "  [trace] %-28s %.2f ms\n", label, std::chrono::duration<double, std::milli>(now_ - tt_).count()); tt_ = now_; }
 int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t* wp, const int64_t* wo, const double* cams6,
                   const double* pts3, const double* feats, const int32_t* cam_idx, const int32_t* pt_idx, const int32_t* cam_id,
                   const uba_calib* calib) {
@@ -547,55 +583,119 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   if (!(calib->feat_var > 0.0) || !(calib->fx0 > 0.0) || !(calib->fy0 > 0.0) || !(calib->cx0 > 0.0))
     return fail(h, UBA_ERR_INVALID_ARGUMENT, "calibration must have positive fx, fy, cx and feat_var");
   if (M == 4 && calib->baseline == 0.0) return fail(h, UBA_ERR_INVALID_ARGUMENT, "stereo BA needs a non-zero baseline (BundleAdjuster.h:147)");
+  auto tt_ = std::chrono::steady_clock::now();
   h->state = 0; h->prepared_fixed = -1;
   h->M = M; h->nW = nW; h->NC = NC; h->NP = NP; h->NO = NO; h->calib_in = *calib;
   h->w_cam_off.assign(wc, wc + nW + 1); h->w_pt_off.assign(wp, wp + nW + 1); h->w_obs_off.assign(wo, wo + nW + 1);
   h->obs_order.assign(NO, 0); h->pt_obs_off_caller.assign((size_t)NP + 1, 0); h->pt_order.assign(NP, 0);
   h->obs_internal.assign(NO, 0); h->pt_obs_off_int.assign((size_t)NP + 1, 0);
   h->cam_seen.assign(NC, 0); h->cam_win_h.assign(NC, 0); h->pt_win_h.assign(NP, 0);
-  // validate + count
+  TT("alloc tables")
+  // validate + count (parallel inside a window when there are few windows)
   int bad = 0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : bad)
+  const bool few = nW < 8;
+  std::vector<int32_t> cnt((size_t)NP, 0);
   for (int w = 0; w < nW; w++) {
     const int nc = wc[w + 1] - wc[w], np = wp[w + 1] - wp[w];
-    if (nc < 0 || np < 0 || wo[w + 1] < wo[w]) { bad++; continue; }
-    for (int64_t o = wo[w]; o < wo[w + 1]; o++) {
-      if (cam_idx[o] < 0 || cam_idx[o] >= nc || pt_idx[o] < 0 || pt_idx[o] >= np) { bad++; continue; }
-      h->pt_obs_off_caller[(size_t)wp[w] + pt_idx[o] + 1]++;
-      h->cam_seen[wc[w] + cam_idx[o]] = 1;
-    }
+    if (nc < 0 || np < 0 || wo[w + 1] < wo[w]) bad++;
     for (int c = wc[w]; c < wc[w + 1]; c++) h->cam_win_h[c] = w;
   }
-  if (bad) return fail(h, UBA_ERR_INVALID_ARGUMENT, "camIdx / ptIdx out of range or malformed window offsets (%d offences)", bad);
-  for (int j = 0; j < NP; j++) h->pt_obs_off_caller[j + 1] += h->pt_obs_off_caller[j];
-  // canonical order: point-major (stable), camera-ascending inside a point; and the internal point order
-#pragma omp parallel for schedule(dynamic, 16)
-  for (int w = 0; w < nW; w++) {
+  if (bad) return fail(h, UBA_ERR_INVALID_ARGUMENT, "malformed window offsets");
+  auto count_window = [&](int w, bool parallel) {
+    const int nc = wc[w + 1] - wc[w], np = wp[w + 1] - wp[w];
+    int32_t* c = cnt.data() + wp[w];
+    char* seen = h->cam_seen.data() + wc[w];
+    int badw = 0;
+#pragma omp parallel for schedule(static) reduction(+ : badw) if (parallel)
+    for (int64_t o = wo[w]; o < wo[w + 1]; o++) {
+      const int ci = cam_idx[o], pi = pt_idx[o];
+      if (ci < 0 || ci >= nc || pi < 0 || pi >= np) { badw++; continue; }
+#pragma omp atomic
+      c[pi]++;
+      seen[ci] = 1;
+    }
+    return badw;
+  };
+  if (few) { for (int w = 0; w < nW; w++) bad += count_window(w, true); }
+  else {
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : bad)
+    for (int w = 0; w < nW; w++) bad += count_window(w, false);
+  }
+  if (bad) return fail(h, UBA_ERR_INVALID_ARGUMENT, "camIdx / ptIdx out of range (%d offences)", bad);
+  for (int j = 0; j < NP; j++) h->pt_obs_off_caller[j + 1] = h->pt_obs_off_caller[j] + cnt[j];
+  TT("validate+count")
+  // Canonical order: point-major (stable), camera-ascending inside a point.  The reference's own
+  // initialiseObservations already produces it (BundleAdjuster.h:364-374): detect that and skip the sort.
+  std::vector<int32_t> lo_c((size_t)NP, INT_MAX), hi_c((size_t)NP, -1);   // caller point order
+  std::vector<char> contig_c((size_t)NP, 1);
+  auto order_window = [&](int w, bool parallel) {
     const int p0 = wp[w], np = wp[w + 1] - wp[w];
-    std::vector<int64_t> fill(np);
-    for (int j = 0; j < np; j++) fill[j] = h->pt_obs_off_caller[p0 + j];
-    for (int64_t o = wo[w]; o < wo[w + 1]; o++) h->obs_order[fill[pt_idx[o]]++] = (int32_t)o;
-    std::vector<int> lo(np, INT_MAX), hi(np, -1);
+    const int64_t o0 = wo[w], o1 = wo[w + 1];
+    int unsorted = 0;
+#pragma omp parallel for schedule(static) reduction(+ : unsorted) if (parallel)
+    for (int64_t o = o0 + 1; o < o1; o++) {
+      if (pt_idx[o] < pt_idx[o - 1] || (pt_idx[o] == pt_idx[o - 1] && cam_idx[o] < cam_idx[o - 1])) unsorted++;
+    }
+    if (!unsorted) {
+#pragma omp parallel for schedule(static) if (parallel)
+      for (int64_t o = o0; o < o1; o++) h->obs_order[o] = (int32_t)o;
+    } else {
+      std::vector<int64_t> fill(np);
+      for (int j = 0; j < np; j++) fill[j] = h->pt_obs_off_caller[p0 + j];
+      for (int64_t o = o0; o < o1; o++) h->obs_order[fill[pt_idx[o]]++] = (int32_t)o;
+    }
+#pragma omp parallel for schedule(static) if (parallel)
     for (int j = 0; j < np; j++) {
       int32_t* b = &h->obs_order[h->pt_obs_off_caller[p0 + j]];
       int32_t* e = &h->obs_order[h->pt_obs_off_caller[p0 + j + 1]];
-      // insertion sort by camera (stable; tracks are short and already ascending for reference input)
-      for (int32_t* i = b + 1; i < e; i++) {
-        const int32_t v = *i; int32_t* k = i;
-        while (k > b && cam_idx[*(k - 1)] > cam_idx[v]) { *k = *(k - 1); k--; }
-        *k = v;
+      if (unsorted) {
+        // insertion sort by camera (stable; tracks are short)
+        for (int32_t* i = b + 1; i < e; i++) {
+          const int32_t v = *i; int32_t* k = i;
+          while (k > b && cam_idx[*(k - 1)] > cam_idx[v]) { *k = *(k - 1); k--; }
+          *k = v;
+        }
       }
-      if (b < e) { lo[j] = cam_idx[*b]; hi[j] = cam_idx[*(e - 1)]; }
+      if (b < e) {
+        lo_c[p0 + j] = cam_idx[*b]; hi_c[p0 + j] = cam_idx[*(e - 1)];
+        char cg = 1;
+        for (int32_t* i = b + 1; i < e; i++) if (cam_idx[*i] != cam_idx[*(i - 1)] + 1) cg = 0;
+        contig_c[p0 + j] = cg;
+      }
     }
-    std::vector<int32_t> ids(np);
-    std::iota(ids.begin(), ids.end(), 0);
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b2) { if (lo[a] != lo[b2]) return lo[a] < lo[b2]; return hi[a] < hi[b2]; });
-    for (int j = 0; j < np; j++) { h->pt_order[p0 + j] = p0 + ids[j]; h->pt_win_h[p0 + j] = w; }
+    // internal point order: stable by (lowest camera, highest camera), unobserved points last
+    const int nc = wc[w + 1] - wc[w];
+    const int64_t nkeys = (int64_t)nc * nc + 1;
+    if (nkeys <= 8 * (int64_t)np + 1024) {
+      std::vector<int32_t> start((size_t)nkeys + 1, 0);
+      auto key = [&](int j) -> int64_t { return hi_c[p0 + j] < 0 ? nkeys - 1 : (int64_t)lo_c[p0 + j] * nc + hi_c[p0 + j]; };
+      for (int j = 0; j < np; j++) start[key(j) + 1]++;
+      for (int64_t k2 = 0; k2 < nkeys; k2++) start[k2 + 1] += start[k2];
+      for (int j = 0; j < np; j++) h->pt_order[p0 + start[key(j)]++] = p0 + j;
+    } else {
+      std::vector<int32_t> ids(np);
+      std::iota(ids.begin(), ids.end(), 0);
+      std::stable_sort(ids.begin(), ids.end(), [&](int a2, int b2) {
+        const int la = hi_c[p0 + a2] < 0 ? INT_MAX : lo_c[p0 + a2], lb = hi_c[p0 + b2] < 0 ? INT_MAX : lo_c[p0 + b2];
+        if (la != lb) return la < lb;
+        return hi_c[p0 + a2] < hi_c[p0 + b2];
+      });
+      for (int j = 0; j < np; j++) h->pt_order[p0 + j] = p0 + ids[j];
+    }
+    for (int j = 0; j < np; j++) h->pt_win_h[p0 + j] = w;
+  };
+  if (few) { for (int w = 0; w < nW; w++) order_window(w, true); }
+  else {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int w = 0; w < nW; w++) order_window(w, false);
   }
+  TT("order+sort")
   // internal CSR + observation slots (window ranges coincide with the caller's)
+  h->pt_lo.assign(NP, -1); h->pt_hi.assign(NP, -1); h->pt_contig.assign(NP, 1);
   for (int s = 0; s < NP; s++) {
     const int j = h->pt_order[s];
     h->pt_obs_off_int[s + 1] = h->pt_obs_off_int[s] + (int32_t)(h->pt_obs_off_caller[j + 1] - h->pt_obs_off_caller[j]);
+    h->pt_lo[s] = hi_c[j] < 0 ? -1 : lo_c[j]; h->pt_hi[s] = hi_c[j]; h->pt_contig[s] = contig_c[j];
   }
   // staging in internal order (pinned)
   CU(h, h->h_cams.reserve((size_t)NC * 6));
@@ -617,6 +717,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       h->h_obs_cam.p[dst + q] = cam_idx[o] | ((cam_id && cam_id[o] != 0) ? (1 << 30) : 0);
     }
   }
+  TT("staging permute")
   // device buffers
   CU(h, h->d_cams.reserve((size_t)NC * 12)); CU(h, h->d_camR.reserve((size_t)NC * kCamStride * 2));
   CU(h, h->d_cam_s2.reserve((size_t)NC * 6)); CU(h, h->d_cam_lam.reserve((size_t)NC * 6)); CU(h, h->d_cam_y.reserve((size_t)NC * 6));
@@ -627,6 +728,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   CU(h, h->d_ws.reserve(nW)); CU(h, h->d_n_active.reserve(1));
   const int rec_stride = std::max(h->cfg.max_iterations, h->cfg.fixed_iterations) + 2;
   CU(h, h->d_recs.reserve((size_t)nW * rec_stride));
+  TT("device reserve")
   cudaStream_t st = h->stream;
   CU(h, cudaMemcpyAsync(h->d_w_cam_off.p, h->w_cam_off.data(), sizeof(int32_t) * (nW + 1), cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(h->d_w_pt_off.p, h->w_pt_off.data(), sizeof(int32_t) * (nW + 1), cudaMemcpyHostToDevice, st));
@@ -644,6 +746,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   if (rc) return rc;
   CU(h, cudaMemsetAsync(h->d_recs.p, 0, sizeof(IterRec) * (size_t)nW * rec_stride, st));
   CU(h, cudaStreamSynchronize(st));
+  TT("h2d")
   fill_view_static(h);
   h->V.rec_stride = rec_stride;
   h->ws_h.assign(nW, WinState{});
