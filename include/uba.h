@@ -90,7 +90,8 @@ typedef struct uba_config {
   int32_t jacobi_scaling;          /* default 1 */
   int32_t use_bounds;              /* default 1: point box of BundleAdjuster.h:442-443,:455-460 */
   int32_t device;                  /* CUDA device ordinal; default 0 (or LOCAL_RANK under torchrun) */
-  int32_t linearizer;              /* 0 auto, 1 generic (global fp64 atomics), 2 segment-local tiles */
+  int32_t linearizer;              /* 0 auto (tiled, Schur products on the FP64 MMA path), 1 generic (global fp64
+                                      atomics), 2 tiled with DFMA Schur products (first generation) */
   int32_t compute_covariance;      /* CalibrationParameters::compute_cov (:40); default 0 */
   int32_t solver;                  /* 0 auto (banded LDL^T for large block-banded systems), 1 dense Cholesky only */
 } uba_config;

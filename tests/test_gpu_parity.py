@@ -31,7 +31,7 @@ def make(lib, name, scale, M=4, linearizer=0, **cfgkw):
 CASES = [("c1", 1.0, 4), ("c2", 0.1, 4), ("c4", 0.01, 4), ("c5", 0.02, 4), ("c1", 0.25, 2), ("c2", 0.05, 2)]
 
 
-@pytest.mark.parametrize("linearizer", [1, 2])
+@pytest.mark.parametrize("linearizer", [0, 1, 2])
 @pytest.mark.parametrize("name,scale,M", CASES)
 def test_linearization_blocks(gpu_lib, oracle, name, scale, M, linearizer):
     win, cfg, h = make(gpu_lib, name, scale, M, linearizer)
@@ -44,7 +44,7 @@ def test_linearization_blocks(gpu_lib, oracle, name, scale, M, linearizer):
     assert h.timing()["kernel_launches"] > 0
 
 
-@pytest.mark.parametrize("linearizer", [1, 2])
+@pytest.mark.parametrize("linearizer", [0, 1, 2])
 @pytest.mark.parametrize("name,scale,M,iters", [("c1", 1.0, 4, 10), ("c2", 0.1, 4, 10), ("c4", 0.01, 4, 10), ("c5", 0.02, 4, 20), ("c1", 0.25, 2, 8)])
 def test_fixed_iteration_trajectory(gpu_lib, oracle, name, scale, M, iters, linearizer):
     win, cfg, h = make(gpu_lib, name, scale, M, linearizer, fixed_iterations=iters)

@@ -104,6 +104,7 @@ struct DevView {
   // tiled lineariser plan
   const TilePart* parts;      // [n_parts]
   int32_t n_parts;
+  int32_t tile_threads;       // 128 or 256 threads per CTA of k_lin_tile
   const int32_t* tile_cams;   // local camera lists
   const uint32_t* pt_mask;    // [NP] bit s: the point observes slot s of its part's list (0: not a tile point)
   const int32_t* gen_pts;     // [n_gen] internal point slots handled by the generic lineariser
@@ -132,6 +133,8 @@ int launch_cam_prep(const DevView& V, int parity, cudaStream_t st);
 // only_listed: process V.gen_pts instead of every point
 int launch_lin_generic(const DevView& V, const DebugOut& dbg, bool only_listed, cudaStream_t st);
 int launch_lin_tile(const DevView& V, cudaStream_t st);
+int launch_lin_tile2(const DevView& V, const int* variant_off, cudaStream_t st);
+int lin_tile2_variant(int n_free_local);
 int launch_assemble(const DevView& V, int max_n, cudaStream_t st);
 // h_win_n: host array [nW] of reduced-system sizes (6 * free cameras); h_win_beta: [nW] banded half-bandwidth or 0
 int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st);

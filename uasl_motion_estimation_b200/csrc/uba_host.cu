@@ -118,6 +118,9 @@ struct uba_handle {
   std::vector<int64_t> w_red_off_h;
   int max_n = 0;
   bool use_tile = false;
+  bool use_tile2 = true;
+  int tile_threads = 256;
+  int variant_off[6] = {0, 0, 0, 0, 0, 0};
   std::vector<TilePart> parts_h;
   std::vector<int32_t> tile_cams_h, gen_pts_h;
   std::vector<uint32_t> pt_mask_h;
@@ -302,10 +305,18 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     }
     close_item(s1);
   }
-  // parts: aim at a few CTAs per SM, never less than 4 chunks of points per CTA
-  const size_t target_parts = 2 * 148;
+  // CTA size: 128 threads (two CTAs per SM) when every item's camera-pair blocks fit, else 256
+  int nt = 128;
+  if (const char* e = std::getenv("UBA_TILE_THREADS")) nt = std::atoi(e) == 256 ? 256 : 128;
   for (const Item& it : items) {
-    const int Pc = kTileThreads / it.nl;
+    const int nlf = it.nl - it.nfx;
+    if (nlf * (nlf + 1) / 2 > 128 || nlf > 10) nt = 256;
+  }
+  h->tile_threads = nt;
+  // parts: aim at a few CTAs per SM, never less than 2 chunks of points per CTA
+  const size_t target_parts = 2 * 148 * (256 / nt);
+  for (const Item& it : items) {
+    const int Pc = nt / it.nl;
     int part_pts = std::max<size_t>(2 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
     part_pts = ((part_pts + Pc - 1) / Pc) * Pc;
     for (int b = it.begin; b < it.end; b += part_pts) {
@@ -313,6 +324,18 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       p.window = it.w; p.pt_begin = b; p.pt_end = std::min(it.end, b + part_pts); p.cam_list_off = it.cam_off; p.n_local = it.nl; p.n_fixed = it.nfx;
       h->parts_h.push_back(p);
     }
+  }
+  // second-generation kernel (tensor-core Schur products) when every item is narrow enough for 128-thread
+  // CTAs; wide items (> 10 free cameras) keep the first-generation kernel, whose chunks are larger there
+  h->use_tile2 = h->cfg.linearizer != 2 && nt == 128;
+  if (const char* e = std::getenv("UBA_TILE2")) h->use_tile2 = std::atoi(e) != 0 && h->cfg.linearizer != 2;
+  for (int v = 0; v < 6; v++) h->variant_off[v] = 0;
+  if (h->use_tile2) {
+    std::stable_sort(h->parts_h.begin(), h->parts_h.end(), [](const TilePart& a, const TilePart& b) {
+      return lin_tile2_variant(a.n_local - a.n_fixed) < lin_tile2_variant(b.n_local - b.n_fixed);
+    });
+    for (const TilePart& p : h->parts_h) h->variant_off[lin_tile2_variant(p.n_local - p.n_fixed) + 1]++;
+    for (int v = 0; v < 5; v++) h->variant_off[v + 1] += h->variant_off[v];
   }
 }
 
@@ -428,6 +451,7 @@ int prepare(uba_handle* h, int fixed_frames) {
   }
   CU(h, cudaStreamSynchronize(h->stream));
   DevView& V = h->V;
+  V.tile_threads = h->tile_threads;
   V.parts = h->d_parts.p; V.n_parts = h->use_tile ? (int)h->parts_h.size() : 0; V.tile_cams = h->d_tile_cams.p; V.pt_mask = h->d_pt_mask.p;
   V.gen_pts = h->d_gen_pts.p; V.n_gen = h->use_tile ? (int)h->gen_pts_h.size() : 0;
   V.w_beta = h->d_w_beta.p;
@@ -472,7 +496,7 @@ int launch_linearizers(uba_handle* h, const DebugOut& dbg) {
     n += launch_lin_generic(h->V, dbg, false, h->stream);
     cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream);
   }
-  n += launch_lin_tile(h->V, h->stream);
+  n += h->use_tile2 ? launch_lin_tile2(h->V, h->variant_off, h->stream) : launch_lin_tile(h->V, h->stream);
   DebugOut none{};
   n += launch_lin_generic(h->V, none, true, h->stream);
   return n;
@@ -605,16 +629,32 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     const int nc = wc[w + 1] - wc[w], np = wp[w + 1] - wp[w];
     int32_t* c = cnt.data() + wp[w];
     char* seen = h->cam_seen.data() + wc[w];
-    int badw = 0;
-#pragma omp parallel for schedule(static) reduction(+ : badw) if (parallel)
-    for (int64_t o = wo[w]; o < wo[w + 1]; o++) {
+    const int64_t o0 = wo[w], o1 = wo[w + 1];
+    int badw = 0, unsorted = 0;
+#pragma omp parallel for schedule(static) reduction(+ : badw, unsorted) if (parallel)
+    for (int64_t o = o0; o < o1; o++) {
       const int ci = cam_idx[o], pi = pt_idx[o];
       if (ci < 0 || ci >= nc || pi < 0 || pi >= np) { badw++; continue; }
-#pragma omp atomic
-      c[pi]++;
       seen[ci] = 1;
+      if (o > o0 && pi < pt_idx[o - 1]) unsorted++;
     }
-    return badw;
+    if (badw) return badw;
+    if (!unsorted) {
+      // point-major input (the reference's order): counts are run lengths, no atomics needed
+      std::vector<int64_t> first((size_t)np + 1, -1);
+#pragma omp parallel for schedule(static) if (parallel)
+      for (int64_t o = o0; o < o1; o++) if (o == o0 || pt_idx[o] != pt_idx[o - 1]) first[pt_idx[o]] = o;
+      first[np] = o1;
+      for (int j = np - 1; j >= 0; j--) if (first[j] < 0) first[j] = first[j + 1];
+      for (int j = 0; j < np; j++) c[j] = (int32_t)(first[j + 1] - first[j]);
+    } else {
+#pragma omp parallel for schedule(static) if (parallel)
+      for (int64_t o = o0; o < o1; o++) {
+#pragma omp atomic
+        c[pt_idx[o]]++;
+      }
+    }
+    return 0;
   };
   if (few) { for (int w = 0; w < nW; w++) bad += count_window(w, true); }
   else {

@@ -286,10 +286,12 @@ __global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D, int 
 constexpr int kZStride = 19;   // doubles per staged Z (18 + 1 pad: conflict-free 64-bit stores)
 constexpr int kFlushStride = 43;
 
-template <int M>
-__global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
+#ifndef UBA_TILE_PHASES
+#define UBA_TILE_PHASES 0xff
+#endif
+template <int M, int NT>
+__global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
   constexpr int NR = (M == 4) ? 3 : 2;
-  constexpr int NT = kTileThreads;
   extern __shared__ double sm[];
   const TilePart part = V.parts[blockIdx.x];
   const int w = part.window;
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
       seen = (mask >> sl) & 1u;
       if (mask) { X[0] = V.pts[cur][(size_t)p * 3]; X[1] = V.pts[cur][(size_t)p * 3 + 1]; X[2] = V.pts[cur][(size_t)p * 3 + 2]; }
     }
-    if (seen) {
+    if (seen && (UBA_TILE_PHASES & 1)) {
       const int o = V.pt_obs_off[p] + __popc(mask & ((1u << sl) - 1u));
       double f[M];
 #pragma unroll
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 1b: per-point sums of E^T E and E^T r over the point's observations ---------------
+    if (UBA_TILE_PHASES & 2)
     for (int idx = t; idx < np * 9; idx += NT) {
       const int q = idx / 9, e = idx - q * 9;
       unsigned m = maskS[q];
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 1c: one thread per point: damping, 3x3 factor, h = L^-1 g, point record -----------
-    if (t < np) {
+    if (t < np && (UBA_TILE_PHASES & 4)) {
       const unsigned pm = maskS[t];
       if (pm) {
         const int pp = c0 + t;
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 1d: Z = W L^-T for my observation (zero if the point block was not positive definite)
-    if (seen && my_free) {
+    if (seen && my_free && (UBA_TILE_PHASES & 8)) {
       const double* Li = LiS + pl * 6;
       const double l0 = Li[0], l1 = Li[1], l2 = Li[2], l3 = Li[3], l4 = Li[4], l5 = Li[5];
       double* z = big + (size_t)(pl * nlf + (sl - nfx)) * kZStride;
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 2: camera-pair blocks, acc += Z_a Z_b^T over my K-group's points ------------------
-    if (p2_thread) {
+    if (p2_thread && (UBA_TILE_PHASES & 16)) {
       for (int q = kg; q < np; q += G) {
         const unsigned m = maskS[q] >> nfx;
         if (!((m >> ba) & 1u) || !((m >> bb) & 1u)) continue;
@@ -559,6 +562,367 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_lin_tile(DevView V) {
     if (fail != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_FAIL], fail);
     if (gmax > 0.0) atomic_max_nonneg(&V.w_max[w], gmax);
   }
+}
+#endif  // !UBA_EMU
+
+
+// ---------------------------------------------------------------------------------------------
+// tiled lineariser, second generation (k_lin_tile2).  Same plan and thread roles for phase 1 as
+// k_lin_tile, but
+//   * the per-point reduction + 3x3 factor is done by ONE thread per point in a single sub-phase
+//     (inputs prefetched), one barrier less;
+//   * the Schur products  sum_j Z_j Z_j^T  run on the FP64 tensor-core path
+//     (mma.sync.aligned.m8n8k4.f64, SASS DMMA.8x8x4): the chunk's Schur factors are staged as ONE
+//     matrix Zm[6 nlf (padded to 8 T)][3 Pc] in shared memory and every warp accumulates its
+//     8x8 output tiles (2 doubles per lane per tile) over its share of the K = 3 Pc columns.
+//     One DMMA replaces 8 warp-level DFMAs and ~3 LDS, so phase 2 needs 1/7 of the issue slots and
+//     a fraction of the registers and shared-memory traffic of the DFMA version.
+//   * Z h (the rhs term) is accumulated by the phase-1 threads next to B and v.
+// Peak fp64 throughput of DMMA equals DFMA's on B200 (37 TFLOP/s, tests/cuda/dmma_bench.cu); the
+// win is latency hiding, not a higher ceiling.
+// ---------------------------------------------------------------------------------------------
+#ifndef UBA_EMU
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int kT2MaxPc = 64;          // points per chunk are capped so that K = 3 Pc <= 192
+// Zm capacity in doubles: the worst case over (T, nl) of 8 T * t2_ldz(Pc) is 96 x 84 (T = 12, Pc = 23) for
+// 256-thread CTAs and 32 x 196 (T = 4, Pc = 64) for 128-thread CTAs
+__host__ __device__ constexpr int t2_zm_doubles(int nt) { return nt == 256 ? 8192 : 6400; }
+
+__host__ __device__ inline int t2_ldz(int pc) {
+  int k = ((3 * pc + 3) / 4) * 4;     // K padded to the DMMA k = 4
+  while ((k & 15) != 4) k += 4;       // row stride == 4 (mod 16) doubles: conflict-free fragment loads
+  return k;
+}
+
+template <int M, int NT, int T, int TG>
+__device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& part, double* sm) {
+  constexpr int NR = (M == 4) ? 3 : 2;
+  constexpr int W = NT / 32;
+  constexpr int KG = W / TG;                       // K-groups
+  constexpr int NTILES = T * (T + 1) / 2;
+  constexpr int TPW = (NTILES + TG - 1) / TG;      // tiles per warp
+  const int w = part.window;
+  const WinState* st = &V.ws[w];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int nl = part.n_local, nfx = part.n_fixed, nlf = nl - nfx;
+  const int cur = st->cur;
+  const double radius = st->radius;
+  const bool scale_ready = st->scale_ready != 0;
+  const int cbase = V.w_cam_off[w];
+  const int Pc = min(NT / nl, kT2MaxPc);
+  const int ldz = t2_ldz(Pc);
+  const int ksteps = (3 * Pc + 3) / 4;
+  // shared memory carve-up (doubles)
+  double* camS = sm;                                 // [kTileMaxLocal][kCamStride]
+  double* Es = camS + kTileMaxLocal * kCamStride;    // [NT][9]
+  double* LiS = Es + NT * 9;                         // [NT][6]
+  double* hS = LiS + NT * 6;                         // [NT][3]
+  unsigned* maskS = reinterpret_cast<unsigned*>(hS + NT * 3);  // [NT]
+  double* Zm = reinterpret_cast<double*>(maskS + NT);          // [8 T][ldz]
+  double* scratch = Es;                              // flush scratch aliases Es .. Zm
+  __shared__ int s_free[kTileMaxLocal];
+  __shared__ int s_gc[kTileMaxLocal];
+
+  for (int i = t; i < nl * kCamStride; i += NT) {
+    const int sl2 = i / kCamStride, k = i % kCamStride;
+    const int gc = cbase + V.tile_cams[part.cam_list_off + sl2];
+    camS[i] = V.camR[cur][(size_t)gc * kCamStride + k];
+    if (k == 0) { s_gc[sl2] = gc; s_free[sl2] = V.free_cam[gc]; }
+  }
+  for (int i = t; i < 8 * T * ldz; i += NT) Zm[i] = 0.0;   // padding rows / columns stay zero for the whole part
+  // phase-1 role
+  const int pl = t / nl, sl = t - pl * nl;
+  const bool p1_thread = pl < Pc;
+  const bool my_free = sl >= nfx;
+  // phase-2 role: warp -> (tile group g, K-group kq); my tiles t = g + i*TG, enumerated (I <= J) row by row
+  const int g = warp % TG, kq = warp / TG;
+  int tI[TPW], tJ[TPW];
+#pragma unroll
+  for (int i = 0; i < TPW; i++) {
+    int idx = g + i * TG, I = 0;
+    if (idx >= NTILES) { tI[i] = -1; tJ[i] = 0; continue; }
+    while (idx >= T - I) { idx -= T - I; I++; }
+    tI[i] = I; tJ[i] = I + idx;
+  }
+  double acc[TPW][2];
+#pragma unroll
+  for (int i = 0; i < TPW; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  double Bq[21], vq[6], zq[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { vq[i] = 0.0; zq[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 21; i++) Bq[i] = 0.0;
+  double cost = 0.0, gmax = 0.0, fail = 0.0;
+  __syncthreads();
+
+  for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += Pc) {
+    const int np = min(Pc, part.pt_end - c0);
+    // prefetch for the per-point thread of phase 1c
+    double Xp[3] = {0, 0, 0}, s2p[3] = {1, 1, 1};
+    unsigned pmask = 0;
+    if (t < np) {
+      const int pp = c0 + t;
+      pmask = V.pt_mask[pp];
+      if (pmask) {
+        Xp[0] = V.pts[cur][(size_t)pp * 3]; Xp[1] = V.pts[cur][(size_t)pp * 3 + 1]; Xp[2] = V.pts[cur][(size_t)pp * 3 + 2];
+        if (scale_ready) { s2p[0] = V.pt_s2[(size_t)pp * 3]; s2p[1] = V.pt_s2[(size_t)pp * 3 + 1]; s2p[2] = V.pt_s2[(size_t)pp * 3 + 2]; }
+      }
+      maskS[t] = pmask;
+    }
+    // ---- phase 1a: linearise my observation -------------------------------------------------
+    const bool have_pt = p1_thread && pl < np;
+    const int p = c0 + pl;
+    unsigned mask = 0;
+    double Wm[18];
+    bool seen = false;
+    if (have_pt) {
+      mask = V.pt_mask[p];
+      seen = (mask >> sl) & 1u;
+    }
+    if (seen) {
+      const double X[3] = {V.pts[cur][(size_t)p * 3], V.pts[cur][(size_t)p * 3 + 1], V.pts[cur][(size_t)p * 3 + 2]};
+      const int o = V.pt_obs_off[p] + __popc(mask & ((1u << sl) - 1u));
+      double f[M];
+#pragma unroll
+      for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
+      const int cid = (M == 2) ? ((V.obs_cam[o] >> 30) & 1) : 0;
+      double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
+      const double rho0 = obs_linearize<M>(camS + sl * kCamStride, X, f, cid, V.calib, V.loss, rraw, wgt, F, E, rh);
+      cost += 0.5 * rho0;
+      double* es = Es + t * 9;
+      double c6[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < NR; a++) {
+        c6[0] = fma(E[a][0], E[a][0], c6[0]); c6[1] = fma(E[a][0], E[a][1], c6[1]); c6[2] = fma(E[a][0], E[a][2], c6[2]);
+        c6[3] = fma(E[a][1], E[a][1], c6[3]); c6[4] = fma(E[a][1], E[a][2], c6[4]); c6[5] = fma(E[a][2], E[a][2], c6[5]);
+        g3[0] = fma(E[a][0], rh[a], g3[0]); g3[1] = fma(E[a][1], rh[a], g3[1]); g3[2] = fma(E[a][2], rh[a], g3[2]);
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) es[i] = c6[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) es[6 + i] = g3[i];
+      if (my_free) {
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+#pragma unroll
+          for (int a = 0; a < NR; a++) vq[r] = fma(F[a][r], rh[a], vq[r]);
+#pragma unroll
+          for (int c = r; c < 6; c++) {
+#pragma unroll
+            for (int a = 0; a < NR; a++) Bq[q] = fma(F[a][r], F[a][c], Bq[q]);
+            q++;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int a = 0; a < NR; a++) sacc = fma(F[a][r], E[a][c], sacc);
+            Wm[r * 3 + c] = sacc;
+          }
+      }
+    }
+    __syncthreads();
+    // ---- phase 1c: one thread per point: sum its observations' E^T E / E^T r, damping, 3x3 factor ----
+    if (t < np && pmask) {
+      const int pp = c0 + t;
+      double cg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      unsigned m = pmask;
+      while (m) {
+        const int s2i = __ffs(m) - 1;
+        m &= m - 1;
+        const double* es = Es + (t * nl + s2i) * 9;
+#pragma unroll
+        for (int e = 0; e < 9; e++) cg[e] += es[e];
+      }
+      const double Cd[3] = {cg[0], cg[3], cg[5]};
+      double s2[3], lam[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        s2[c] = scale_ready ? s2p[c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
+        lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+      }
+      const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
+      const double gg[3] = {cg[6], cg[7], cg[8]};
+      double Li[6] = {0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
+      const bool ok = point_factor(Cdamp, Li);
+      double* rec = V.pt_rec + (size_t)pp * kPtRec;
+      if (!ok) {
+        fail += 1.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) Li[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPtRec; i++) rec[i] = 0.0;
+      } else {
+        linv_mul(Li, gg, h);
+#pragma unroll
+        for (int i = 0; i < 6; i++) rec[i] = Li[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { rec[6 + i] = h[i]; rec[9 + i] = gg[i]; rec[12 + i] = lam[i]; }
+        rec[15] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const double proj = V.cfg.use_bounds ? clampd(Xp[c] - gg[c], V.calib.lo[c], V.calib.hi[c]) : Xp[c] - gg[c];
+          gmax = fmax(gmax, fabs(Xp[c] - proj));
+        }
+      }
+      if (!scale_ready) { V.pt_s2[(size_t)pp * 3] = s2[0]; V.pt_s2[(size_t)pp * 3 + 1] = s2[1]; V.pt_s2[(size_t)pp * 3 + 2] = s2[2]; }
+#pragma unroll
+      for (int i = 0; i < 6; i++) LiS[t * 6 + i] = Li[i];
+      hS[t * 3] = h[0]; hS[t * 3 + 1] = h[1]; hS[t * 3 + 2] = h[2];
+    }
+    __syncthreads();
+    // ---- phase 1d: Z = W L^-T into the chunk matrix Zm (zeros where the point does not see my slot) ----
+    if (p1_thread && my_free) {
+      double* zc = Zm + (size_t)(6 * (sl - nfx)) * ldz + 3 * pl;
+      if (seen) {
+        const double* Li = LiS + pl * 6;
+        const double l0 = Li[0], l1 = Li[1], l2 = Li[2], l3 = Li[3], l4 = Li[4], l5 = Li[5];
+        const double h0 = hS[pl * 3], h1 = hS[pl * 3 + 1], h2 = hS[pl * 3 + 2];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double z0 = Wm[r * 3] * l0;
+          const double z1 = fma(Wm[r * 3], l1, Wm[r * 3 + 1] * l2);
+          const double z2 = fma(Wm[r * 3], l3, fma(Wm[r * 3 + 1], l4, Wm[r * 3 + 2] * l5));
+          zc[(size_t)r * ldz] = z0; zc[(size_t)r * ldz + 1] = z1; zc[(size_t)r * ldz + 2] = z2;
+          zq[r] = fma(z0, h0, fma(z1, h1, fma(z2, h2, zq[r])));
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 6; r++) { zc[(size_t)r * ldz] = 0.0; zc[(size_t)r * ldz + 1] = 0.0; zc[(size_t)r * ldz + 2] = 0.0; }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: tensor-core SYRK over the chunk: acc(I,J) += Zm[8I.., k] Zm[8J.., k]^T ------------
+    if (nlf > 0) {
+      const int frow = lane >> 2, fk = lane & 3;
+      for (int ks = kq; ks < ksteps; ks += KG) {
+        const double* col = Zm + 4 * ks + fk;
+        if (TG == 1) {
+          double fr[T];
+#pragma unroll
+          for (int I = 0; I < T; I++) fr[I] = col[(size_t)(8 * I + frow) * ldz];
+          int i = 0;
+#pragma unroll
+          for (int I = 0; I < T; I++)
+#pragma unroll
+            for (int J = I; J < T; J++) { dmma884(acc[i][0], acc[i][1], fr[I], fr[J]); i++; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < TPW; i++) {
+            if (tI[i] >= 0) {
+              const double a = col[(size_t)(8 * tI[i] + frow) * ldz];
+              const double b = col[(size_t)(8 * tJ[i] + frow) * ldz];
+              dmma884(acc[i][0], acc[i][1], a, b);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- flush: Schur tiles.  K-groups are summed in shared memory, then one red.add per entry ---------
+  const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+  double* S = V.Sacc + V.w_red_off[w];
+  const int nloc = 6 * nlf;
+  if (nlf > 0) {
+    const int frow = lane >> 2, fc = (lane & 3) * 2;
+    if (KG == 1) {
+      // every tile has exactly one owner warp: straight to global memory
+#pragma unroll
+      for (int i = 0; i < TPW; i++) {
+        if (tI[i] >= 0) {
+          const int row = 8 * tI[i] + frow;
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int colx = 8 * tJ[i] + fc + e;
+            const double v = acc[i][e];
+            if (colx >= row && colx < nloc && v != 0.0) {
+              const int a = row / 6, b = colx / 6;
+              const int fa = s_free[nfx + a], fb = s_free[nfx + b];
+              atomicAdd(&S[(size_t)(6 * fa + row - 6 * a) * n + 6 * fb + (colx - 6 * b)], v);
+            }
+          }
+        }
+      }
+    } else {
+      constexpr int LDS2 = 8 * T + 1;
+      double* Sl = scratch;                         // [8 T][LDS2]
+      for (int r = 0; r < KG; r++) {
+        if (kq == r) {
+#pragma unroll
+          for (int i = 0; i < TPW; i++) {
+            if (tI[i] >= 0) {
+              double* d = Sl + (size_t)(8 * tI[i] + frow) * LDS2 + 8 * tJ[i] + fc;
+              if (r == 0) { d[0] = acc[i][0]; d[1] = acc[i][1]; } else { d[0] += acc[i][0]; d[1] += acc[i][1]; }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      for (int idx = t; idx < nloc * nloc; idx += NT) {
+        const int row = idx / nloc, colx = idx - row * nloc;
+        if (colx < row) continue;
+        const double v = Sl[(size_t)row * LDS2 + colx];
+        if (v == 0.0) continue;
+        const int a = row / 6, b = colx / 6;
+        const int fa = s_free[nfx + a], fb = s_free[nfx + b];
+        atomicAdd(&S[(size_t)(6 * fa + row - 6 * a) * n + 6 * fb + (colx - 6 * b)], v);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- flush: camera blocks B, gradients v, rhs terms Z h ----------------------------------------
+  if (p1_thread && my_free) {
+    double* o = scratch + (size_t)t * 33;
+#pragma unroll
+    for (int i = 0; i < 21; i++) o[i] = Bq[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { o[21 + i] = vq[i]; o[27 + i] = zq[i]; }
+  }
+  __syncthreads();
+  for (int idx = t; idx < nlf * 33; idx += NT) {
+    const int s2i = nfx + idx / 33, e = idx % 33;
+    double sacc = 0.0;
+    for (int q = 0; q < Pc; q++) sacc += scratch[(size_t)(q * nl + s2i) * 33 + e];
+    if (sacc == 0.0) continue;
+    const int gc = s_gc[s2i];
+    if (e < 21) {
+      int r = 0, k2 = e;
+      while (k2 >= 6 - r) { k2 -= 6 - r; r++; }
+      atomicAdd(&V.Bacc[(size_t)gc * 36 + r * 6 + r + k2], sacc);
+    } else if (e < 27) {
+      atomicAdd(&V.vacc[(size_t)gc * 6 + (e - 21)], sacc);
+    } else {
+      atomicAdd(&V.zh[(size_t)gc * 6 + (e - 27)], sacc);
+    }
+  }
+  cost = warp_sum(cost); fail = warp_sum(fail); gmax = warp_max(gmax);
+  if (warp_leader()) {
+    if (cost != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_COST], cost);
+    if (fail != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_FAIL], fail);
+    if (gmax > 0.0) atomic_max_nonneg(&V.w_max[w], gmax);
+  }
+}
+
+#ifndef UBA_T2_MINBLOCKS
+#define UBA_T2_MINBLOCKS 2
+#endif
+// One kernel per (CTA size, tile variant) so that each variant gets its own register allocation.
+// Parts are grouped by variant on the host: this launch covers parts [first, first + gridDim.x).
+template <int M, int NT, int T, int TG>
+__global__ void __launch_bounds__(NT, NT == 128 ? UBA_T2_MINBLOCKS : 1) k_lin_tile2(DevView V, int first) {
+  extern __shared__ double sm[];
+  const TilePart part = V.parts[first + blockIdx.x];
+  if (V.ws[part.window].done) return;
+  tile2_part<M, NT, T, TG>(V, part, sm);
 }
 #endif  // !UBA_EMU
 
@@ -1406,11 +1770,12 @@ int launch_lin_generic(const DevView& V, const DebugOut& dbg, bool only_listed, 
 }
 
 
-size_t lin_tile_smem_bytes() {
+size_t lin_tile_smem_bytes(int nt) {
 #ifdef UBA_EMU
+  (void)nt;
   return 0;
 #else
-  return sizeof(double) * (kTileMaxLocal * kCamStride + kTileThreads * 9 + kTileThreads * 3 + kTileThreads * 6 + kTileThreads / 2 + kTileThreads * kFlushStride);
+  return sizeof(double) * (kTileMaxLocal * kCamStride + nt * 9 + nt * 3 + nt * 6 + nt / 2 + nt * kFlushStride);
 #endif
 }
 
@@ -1420,16 +1785,76 @@ int launch_lin_tile(const DevView& V, cudaStream_t st) {
   (void)st;
   return 0;
 #else
-  const size_t smem = lin_tile_smem_bytes();
+  // 128-thread CTAs (two per SM, in different phases) when every part fits 128 threads, else 256
+  const int nt = V.tile_threads;
+  const size_t smem = lin_tile_smem_bytes(nt);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_lin_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_lin_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_lin_tile<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(256));
+    cudaFuncSetAttribute(k_lin_tile<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(256));
+    cudaFuncSetAttribute(k_lin_tile<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(128));
+    cudaFuncSetAttribute(k_lin_tile<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(128));
     configured = true;
   }
-  if (V.M == 4) UBA_LAUNCH(k_lin_tile<4>, V.n_parts, kTileThreads, smem, st, V);
-  else UBA_LAUNCH(k_lin_tile<2>, V.n_parts, kTileThreads, smem, st, V);
+  if (nt == 128) {
+    if (V.M == 4) UBA_LAUNCH((k_lin_tile<4, 128>), V.n_parts, 128, smem, st, V);
+    else UBA_LAUNCH((k_lin_tile<2, 128>), V.n_parts, 128, smem, st, V);
+  } else {
+    if (V.M == 4) UBA_LAUNCH((k_lin_tile<4, 256>), V.n_parts, 256, smem, st, V);
+    else UBA_LAUNCH((k_lin_tile<2, 256>), V.n_parts, 256, smem, st, V);
+  }
   return 1;
+#endif
+}
+
+size_t lin_tile2_smem_bytes(int nt) {
+#ifdef UBA_EMU
+  (void)nt;
+  return 0;
+#else
+  // camS | Es [nt][9] | LiS [nt][6] | hS [nt][3] | maskS [nt] | Zm (rows 8T <= 128, row stride t2_ldz(Pc))
+  return sizeof(double) * (kTileMaxLocal * kCamStride + nt * 9 + nt * 6 + nt * 3 + nt / 2 + t2_zm_doubles(nt));
+#endif
+}
+
+template <int M, int NT, int T, int TG>
+static int launch_t2_variant(const DevView& V, int first, int count, cudaStream_t st) {
+  if (count == 0) return 0;
+  const size_t smem = lin_tile2_smem_bytes(NT);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(k_lin_tile2<M, NT, T, TG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  UBA_LAUNCH((k_lin_tile2<M, NT, T, TG>), count, NT, smem, st, V, first);
+  return 1;
+}
+
+// variant of a part: row tiles of 8 over 6 * (free local cameras) rows
+int lin_tile2_variant(int n_free_local) {
+  const int rows = 6 * n_free_local;
+  return rows <= 32 ? 0 : rows <= 48 ? 1 : rows <= 64 ? 2 : rows <= 96 ? 3 : 4;
+}
+
+// variant_off[6]: parts are sorted by variant; variant v covers [variant_off[v], variant_off[v+1])
+int launch_lin_tile2(const DevView& V, const int* variant_off, cudaStream_t st) {
+  if (V.n_parts == 0) return 0;
+#ifdef UBA_EMU
+  (void)st; (void)variant_off;
+  return 0;
+#else
+  int n = 0;
+  const int* o = variant_off;
+#define T2_ALL(MM, NN)                                                              \
+  n += launch_t2_variant<MM, NN, 4, 1>(V, o[0], o[1] - o[0], st);                     \
+  n += launch_t2_variant<MM, NN, 6, 2>(V, o[1], o[2] - o[1], st);                     \
+  n += launch_t2_variant<MM, NN, 8, 2>(V, o[2], o[3] - o[2], st);                     \
+  n += launch_t2_variant<MM, NN, 12, 4>(V, o[3], o[4] - o[3], st);
+  if (V.tile_threads == 128) {
+    if (V.M == 4) { T2_ALL(4, 128) } else { T2_ALL(2, 128) }
+  } else {
+    if (V.M == 4) { T2_ALL(4, 256) n += launch_t2_variant<4, 256, 16, 8>(V, o[4], o[5] - o[4], st); }
+    else { T2_ALL(2, 256) n += launch_t2_variant<2, 256, 16, 8>(V, o[4], o[5] - o[4], st); }
+  }
+#undef T2_ALL
+  return n;
 #endif
 }
 
