@@ -1817,6 +1817,7 @@ size_t lin_tile2_smem_bytes(int nt) {
 #endif
 }
 
+#ifndef UBA_EMU
 template <int M, int NT, int T, int TG>
 static int launch_t2_variant(const DevView& V, int first, int count, cudaStream_t st) {
   if (count == 0) return 0;
@@ -1826,6 +1827,8 @@ static int launch_t2_variant(const DevView& V, int first, int count, cudaStream_
   UBA_LAUNCH((k_lin_tile2<M, NT, T, TG>), count, NT, smem, st, V, first);
   return 1;
 }
+
+#endif
 
 // variant of a part: row tiles of 8 over 6 * (free local cameras) rows
 int lin_tile2_variant(int n_free_local) {
