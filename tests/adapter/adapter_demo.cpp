@@ -52,6 +52,7 @@ static int run(int n_cams, int n_pts, unsigned long long seed, int fixed, const 
   }
   std::vector<cv::Matx33d> K(2, cv::Matx33d{k.fx0, 0, k.cx0, 0, k.fy0, k.cy0, 0, 0, 1});
   CalibrationParameters calib(K, k.feat_var, k.baseline);
+  calib.compute_cov = (M == 4);  // extract_covariance path (BundleAdjuster.h:471-472)
   BundleAdjuster<M> ba(calib, poses, tracks);
   if (ba.getStatus() != BundleAdjuster<M>::Status::INITIALISED) return 4;
   const typename BundleAdjuster<M>::Status st = ba.optimise(fixed);
@@ -66,6 +67,10 @@ static int run(int n_cams, int n_pts, unsigned long long seed, int fixed, const 
     std::fwrite(v, sizeof(double), 8, f);
   }
   for (const auto& p : out_pts) std::fwrite(p.val, sizeof(double), 3, f);
+  std::vector<cv::Mat> covs = ba.getPosesCovariance();
+  const int ncov = (int)covs.size();
+  std::fwrite(&ncov, sizeof(int), 1, f);
+  for (const auto& c : covs) { std::vector<double> z(36, 0.0); std::fwrite(c.empty() ? z.data() : c.d.data(), sizeof(double), 36, f); }
   std::fclose(f);
   // single use: a second optimise() must refuse and keep the status (BundleAdjuster.h:381-384)
   if (ba.optimise(fixed) != st) return 6;

@@ -48,7 +48,7 @@ def test_adapter_matches_the_c_abi_path(gpu_lib, tmp_path, M):
     np.testing.assert_array_equal(poses[:, 7], np.arange(nc))  # IDs renumbered from 0 (BundleAdjuster.h:233-235)
     win = synth.generate(n_cams, n_pts, 3, n_cams, seed=seed, M=M, fixed_frames=fixed, lib=gpu_lib)
     assert no == win.n_obs
-    h = capi.Handle(capi.default_config(gpu_lib), lib=gpu_lib)
+    h = capi.Handle(capi.default_config(gpu_lib, compute_covariance=int(M == 4)), lib=gpu_lib)
     h.set_problem(M, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
     rc, sums = h.optimise(fixed)
     assert rc == 0
@@ -59,3 +59,13 @@ def test_adapter_matches_the_c_abi_path(gpu_lib, tmp_path, M):
     np.testing.assert_allclose(poses[:, :4], q, rtol=0, atol=1e-8)
     np.testing.assert_allclose(poses[:, 4:7], cams[:, :3], rtol=1e-7, atol=1e-8)
     np.testing.assert_allclose(pts, h.points(), rtol=1e-7, atol=1e-7)
+    off = 16 + nc * 64 + npt * 24
+    (ncov,) = struct.unpack("i", raw[off:off + 4])
+    if M == 4:  # CalibrationParameters::compute_cov -> getPosesCovariance()
+        assert ncov == nc
+        cov = np.frombuffer(raw, np.float64, nc * 36, off + 4).reshape(nc, 6, 6)
+        ref = h.pose_covariances()
+        np.testing.assert_allclose(cov, ref, rtol=1e-5, atol=1e-12)
+        assert not cov[:fixed].any() and cov[fixed:].any()
+    else:
+        assert ncov == 0

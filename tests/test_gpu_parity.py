@@ -159,3 +159,27 @@ def test_full_size_properties(gpu_lib, oracle, name):
     costs = [it["cost"] for it in its]
     assert all(b <= a * (1 + 1e-12) for a, b in zip(costs, costs[1:]))  # monotonic: only accepted steps move x
     assert sums[0].final_cost == pytest.approx(oracle.cost(win, cfg, h.cameras(), h.points()), rel=1e-10)
+
+
+@pytest.mark.parametrize("name,scale", [("c1", 0.25), ("c4", 0.02)])
+def test_pose_covariances(gpu_lib, oracle, name, scale):
+    """extract_covariance (BundleAdjuster.h:478-528): 6x6 blocks of (J^T J)^-1 with the points marginalised ==
+    diagonal blocks of the inverse of the undamped reduced camera matrix the oracle builds at the final iterate."""
+    win, cfg, h = make(gpu_lib, name, scale, fixed_iterations=6, compute_covariance=1)
+    rc, sums = h.optimise(2)
+    assert rc == 0
+    cov = h.pose_covariances()
+    cams, pts = h.cameras(), h.points()
+    L = oracle.linearize(win, cfg, 2, -1.0, cams=cams, pts=pts, jacobi_scale=np.ones(6 * win.n_cams + 3 * win.n_pts))
+    Sinv = np.linalg.inv(L["S"])
+    fc = h.tables(2)["free_cam"]
+    for c in range(win.n_cams):
+        if fc[c] < 0:
+            assert not cov[c].any()
+        else:
+            ref = Sinv[6 * fc[c]:6 * fc[c] + 6, 6 * fc[c]:6 * fc[c] + 6]
+            assert np.abs(cov[c] - ref).max() <= 1e-7 * np.abs(ref).max(), c
+            assert np.allclose(cov[c], cov[c].T, rtol=1e-10, atol=0) and np.all(np.linalg.eigvalsh(cov[c]) > 0)
+    # results of the optimisation itself are unaffected by the extra pass
+    o = oracle.optimise(win, cfg, 2)
+    assert rel(cams, o["cams"]) < STATE_TOL and rel(pts, o["pts"]) < STATE_TOL

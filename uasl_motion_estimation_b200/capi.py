@@ -294,6 +294,11 @@ class Handle:
         self._check(self.lib.uba_get_points(self._h, dptr(a)))
         return a
 
+    def pose_covariances(self) -> np.ndarray:
+        a = np.zeros((self.n_cams, 6, 6))
+        self._check(self.lib.uba_get_pose_covariances(self._h, dptr(a)))
+        return a
+
     def iterations(self, window: int = 0):
         n = C.c_int(0)
         self._check(self.lib.uba_get_iterations(self._h, window, None, 0, C.byref(n)))

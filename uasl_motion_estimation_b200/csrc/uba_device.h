@@ -143,6 +143,8 @@ int solve_small_limit();
 int launch_backsub(const DevView& V, cudaStream_t st);
 int launch_lm_update(const DevView& V, cudaStream_t st);
 int launch_init_state(const DevView& V, double initial_radius, cudaStream_t st);
+int launch_cov_state(const DevView& V, int enter, cudaStream_t st);
+int launch_cov_blocks(const DevView& V, int n_free_total, int max_n, double* cov36, cudaStream_t st);
 int launch_l2_flush(double* buf, size_t n, cudaStream_t st);
 int launch_dfma_probe(double* out, int iters, cudaStream_t st);
 

@@ -134,6 +134,8 @@ struct uba_handle {
   DevBuf<double> d_cams, d_camR, d_cam_s2, d_cam_lam, d_cam_y, d_pts, d_pt_s2, d_pt_rec, d_feat, d_acc, d_A, d_rhs, d_Zbuf, d_dbg, d_export, d_flush;
   DevBuf<int32_t> d_w_cam_off, d_w_pt_off, d_w_free_off, d_free_list, d_free_cam, d_cam_win, d_pt_obs_off, d_pt_win, d_obs_cam, d_n_active, d_pt_order;
   DevBuf<int64_t> d_w_red_off;
+  DevBuf<double> d_cov;
+  std::vector<double> cov_h;   // [NC][36], filled when cfg.compute_covariance
   DevBuf<WinState> d_ws;
   DevBuf<IterRec> d_recs;
   size_t acc_sum1 = 0;   // doubles reduced (sum) after linearise: Sacc|Bacc|vacc|zh|w_lin
@@ -809,6 +811,37 @@ bool window_feasible(const uba_handle* h, int w) {
   return true;
 }
 
+
+// Pose covariances at the final iterate: one undamped linearisation, dense factorisation of the
+// reduced camera matrix (the banded solver keeps no dense factor, so it is bypassed), S^-1 diagonal blocks.
+int compute_covariances(uba_handle* h) {
+  const int nW = h->nW, NC = h->NC;
+  CU(h, h->d_cov.reserve((size_t)NC * 36));
+  CU(h, cudaMemsetAsync(h->d_cov.p, 0, sizeof(double) * 36 * NC, h->stream));
+  drop_graph(h);
+  h->timing.kernel_launches += launch_cov_state(h->V, 1, h->stream);
+  std::vector<int32_t> zeros(nW, 0);
+  CU(h, cudaMemcpyAsync(h->d_w_beta.p, zeros.data(), sizeof(int32_t) * nW, cudaMemcpyHostToDevice, h->stream));
+  DebugOut none{};
+  const bool was_profiling = h->profiling;
+  h->profiling = false;
+  int rc = run_linearize(h, none);
+  if (!rc) {
+    h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
+    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), zeros.data(), solve_small_limit(), h->stream);
+    h->timing.kernel_launches += launch_cov_blocks(h->V, (int)h->free_list_h.size(), h->max_n, h->d_cov.p, h->stream);
+  }
+  h->profiling = was_profiling;
+  h->timing.kernel_launches += launch_cov_state(h->V, 0, h->stream);
+  CU(h, cudaMemcpyAsync(h->d_w_beta.p, h->win_beta.data(), sizeof(int32_t) * nW, cudaMemcpyHostToDevice, h->stream));
+  if (rc) return rc;
+  h->cov_h.assign((size_t)NC * 36, 0.0);
+  CU(h, cudaMemcpyAsync(h->cov_h.data(), h->d_cov.p, sizeof(double) * 36 * NC, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaGetLastError());
+  return UBA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1024,6 +1057,11 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
   CU(h, cudaGetLastError());
   float ms = 0; cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
   h->timing.total_ms += ms;
+  h->cov_h.clear();
+  if (h->cfg.compute_covariance && !h->comm) {
+    rc = compute_covariances(h);
+    if (rc) return rc;
+  }
   CU(h, cudaMemcpy(h->ws_h.data(), h->d_ws.p, sizeof(WinState) * h->nW, cudaMemcpyDeviceToHost));
   int worst = UBA_OK;
   for (int w = 0; w < h->nW; w++) {
@@ -1080,7 +1118,15 @@ int uba_get_points(uba_handle* h, double* pts3) {
 
 int uba_get_pose_covariances(uba_handle* h, double* cov36) {
   if (!h || !cov36) return UBA_ERR_INVALID_ARGUMENT;
-  return fail(h, UBA_ERR_UNSUPPORTED, "pose covariance extraction (BundleAdjuster.h:478-528) is not implemented yet");
+  if (h->state != 2) return fail(h, UBA_ERR_STATE, "optimise has not run");
+  if (h->cov_h.empty())
+    return fail(h, UBA_ERR_STATE, "no covariances: set uba_config.compute_covariance before uba_optimise (not available on point-sharded handles)");
+  // cameras of windows without a usable solution, fixed cameras and unobserved cameras report zeros
+  for (int c = 0; c < h->NC; c++) {
+    const bool ok = h->ws_h[h->cam_win_h[c]].done != UBA_TERM_FAILURE && h->free_cam_h[c] >= 0;
+    for (int i = 0; i < 36; i++) cov36[(size_t)c * 36 + i] = ok ? h->cov_h[(size_t)c * 36 + i] : 0.0;
+  }
+  return UBA_OK;
 }
 
 int uba_get_iterations(uba_handle* h, int window, uba_iteration* out, int max_records, int* n_records) {

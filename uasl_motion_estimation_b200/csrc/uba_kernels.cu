@@ -1726,6 +1726,86 @@ __global__ void k_lm_update(DevView V) {
   if (done) atomicSub(V.n_active, 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// pose covariance blocks (extract_covariance, BundleAdjuster.h:478-528): with the points
+// marginalised the covariance of free camera f is the (f, f) block of S^-1, S the UNDAMPED reduced
+// camera matrix at the final iterate.  S = L L^T is already factorised (dense, lower, in V.A):
+// solve L Y = E_f (6 right-hand sides) column by column and form Y^T Y.   grid: one CTA per free camera.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cov_blocks(DevView V, double* cov36 /*[NC][36]*/) {
+#ifndef UBA_EMU
+  extern __shared__ double sm[];
+  const int gf = blockIdx.x;                 // index into free_list
+  const int gc = V.free_list[gf];
+  const int w = V.cam_win[gc];
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const int c0 = 6 * (gf - f0);
+  const double* L = V.A + V.w_red_off[w];
+  double* Y = sm;                            // [n - c0][6]
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int m = n - c0;
+  for (int e = t; e < m * 6; e += nt) Y[e] = (e / 6 == e % 6) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int k = 0; k < m; k++) {
+    // row k is final once divided by the pivot; then eliminate it from the rows below
+    const double inv = 1.0 / L[(size_t)(c0 + k) * n + c0 + k];
+    if (t < 6) Y[k * 6 + t] *= inv;
+    __syncthreads();
+    for (int e = t; e < (m - k - 1) * 6; e += nt) {
+      const int r = k + 1 + e / 6, c = e % 6;
+      Y[r * 6 + c] = fma(-L[(size_t)(c0 + r) * n + c0 + k], Y[k * 6 + c], Y[r * 6 + c]);
+    }
+    __syncthreads();
+  }
+  // cov = Y^T Y
+  __shared__ double red[36];
+  if (t < 36) red[t] = 0.0;
+  __syncthreads();
+  double acc[36];
+#pragma unroll
+  for (int i = 0; i < 36; i++) acc[i] = 0.0;
+  for (int r = t; r < m; r += nt) {
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = 0; b < 6; b++) acc[a * 6 + b] = fma(Y[r * 6 + a], Y[r * 6 + b], acc[a * 6 + b]);
+  }
+#pragma unroll
+  for (int i = 0; i < 36; i++) {
+    const double v = warp_sum(acc[i]);
+    if ((t & 31) == 0) atomicAdd(&red[i], v);
+  }
+  __syncthreads();
+  if (t < 36) cov36[(size_t)gc * 36 + t] = red[t];
+#endif
+}
+
+// forces a window state for the covariance pass: running, undamped
+__global__ void k_cov_state(DevView V, int enter) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= V.nW) return;
+  WinState* st = &V.ws[w];
+  if (enter) { st->pad_[0] = st->done; st->pad_[1] = 0; if (st->done != 5) st->done = 0; st->decrease_factor = st->radius; st->radius = -1.0; }
+  else { st->done = st->pad_[0]; st->radius = st->decrease_factor; st->decrease_factor = 2.0; }
+}
+
+int launch_cov_state(const DevView& V, int enter, cudaStream_t st) {
+  UBA_LAUNCH(k_cov_state, (V.nW + 127) / 128, 128, 0, st, V, enter);
+  return 1;
+}
+
+int launch_cov_blocks(const DevView& V, int n_free_total, int max_n, double* cov36, cudaStream_t st) {
+  if (n_free_total == 0) return 0;
+  const size_t smem = (size_t)max_n * 6 * sizeof(double);
+#ifndef UBA_EMU
+  cudaFuncSetAttribute(k_cov_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  UBA_LAUNCH(k_cov_blocks, n_free_total, 256, smem, st, V, cov36);
+  return 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // utilities
 // ---------------------------------------------------------------------------------------------

@@ -17,9 +17,10 @@
  *     window, :370-371); an offending window ends in Status::FAILED;
  *   - log_map_Quat's acos argument is clamped to [-1, 1] (rotation_utils.h:203 yields NaN for w > 1);
  *   - glog is not initialised (nothing logs through it any more);
- *   - getPosesCovariance() is filled only when CalibrationParameters::compute_cov is set AND libuba
- *     implements uba_get_pose_covariances; otherwise the reference's own message
- *     "[Bundle Adjuster] error computing the covariance matrix" is printed (:525).
+ *   - getPosesCovariance() (CalibrationParameters::compute_cov) returns the 6x6 blocks of the inverse
+ *     undamped reduced camera matrix, i.e. the camera blocks of (J^T J)^-1 that ceres::Covariance
+ *     computes (:502-512); fixed cameras get a zero 6x6 block instead of Ceres' refusal; on failure the
+ *     reference's own message "[Bundle Adjuster] error computing the covariance matrix" is printed (:525).
  *  Like the reference, the object is single use (:7): UNINITIALISED -> INITIALISED -> SUCCESSFUL | FAILED.
  */
 #include <array>
