@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "uba_device.h"
 
 // UBA_EMU is defined ONLY by tests/emu (a serial host emulation of the thread-independent kernels,
@@ -604,6 +606,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   constexpr int KG = W / TG;                       // K-groups
   constexpr int NTILES = T * (T + 1) / 2;
   constexpr int TPW = (NTILES + TG - 1) / TG;      // tiles per warp
+  const unsigned FULL = 0xffffffffu;
   const int w = part.window;
   const WinState* st = &V.ws[w];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -612,17 +615,21 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   const double radius = st->radius;
   const bool scale_ready = st->scale_ready != 0;
   const int cbase = V.w_cam_off[w];
-  const int Pc = min(NT / nl, kT2MaxPc);
+  // phase-1 role, warp aligned: a point's nl slot lanes sit in ONE warp, so its 3x3 block is reduced with
+  // shuffles and factored redundantly by every lane of the point (no shared staging, no idle threads)
+  const int ppw = min(32 / nl, kT2MaxPc / W);      // points per warp
+  const int Pc = W * ppw;                          // points per chunk
+  const int plw = lane / nl, sl = lane - plw * nl;
+  const bool p1_thread = plw < ppw;
+  const int pl = warp * ppw + plw;                 // point slot in the chunk
+  const int seg_base = plw * nl;                   // first lane of my point
+  const bool my_free = sl >= nfx;
   const int ldz = t2_ldz(Pc);
   const int ksteps = (3 * Pc + 3) / 4;
   // shared memory carve-up (doubles)
   double* camS = sm;                                 // [kTileMaxLocal][kCamStride]
-  double* Es = camS + kTileMaxLocal * kCamStride;    // [NT][9]
-  double* LiS = Es + NT * 9;                         // [NT][6]
-  double* hS = LiS + NT * 6;                         // [NT][3]
-  unsigned* maskS = reinterpret_cast<unsigned*>(hS + NT * 3);  // [NT]
-  double* Zm = reinterpret_cast<double*>(maskS + NT);          // [8 T][ldz]
-  double* scratch = Es;                              // flush scratch aliases Es .. Zm
+  double* Zm = camS + kTileMaxLocal * kCamStride;    // [8 T][ldz]
+  double* scratch = Zm;                              // flush scratch aliases Zm
   __shared__ int s_free[kTileMaxLocal];
   __shared__ int s_gc[kTileMaxLocal];
 
@@ -633,10 +640,6 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
     if (k == 0) { s_gc[sl2] = gc; s_free[sl2] = V.free_cam[gc]; }
   }
   for (int i = t; i < 8 * T * ldz; i += NT) Zm[i] = 0.0;   // padding rows / columns stay zero for the whole part
-  // phase-1 role
-  const int pl = t / nl, sl = t - pl * nl;
-  const bool p1_thread = pl < Pc;
-  const bool my_free = sl >= nfx;
   // phase-2 role: warp -> (tile group g, K-group kq); my tiles t = g + i*TG, enumerated (I <= J) row by row
   const int g = warp % TG, kq = warp / TG;
   int tI[TPW], tJ[TPW];
@@ -660,30 +663,20 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
 
   for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += Pc) {
     const int np = min(Pc, part.pt_end - c0);
-    // prefetch for the per-point thread of phase 1c
-    double Xp[3] = {0, 0, 0}, s2p[3] = {1, 1, 1};
-    unsigned pmask = 0;
-    if (t < np) {
-      const int pp = c0 + t;
-      pmask = V.pt_mask[pp];
-      if (pmask) {
-        Xp[0] = V.pts[cur][(size_t)pp * 3]; Xp[1] = V.pts[cur][(size_t)pp * 3 + 1]; Xp[2] = V.pts[cur][(size_t)pp * 3 + 2];
-        if (scale_ready) { s2p[0] = V.pt_s2[(size_t)pp * 3]; s2p[1] = V.pt_s2[(size_t)pp * 3 + 1]; s2p[2] = V.pt_s2[(size_t)pp * 3 + 2]; }
-      }
-      maskS[t] = pmask;
-    }
     // ---- phase 1a: linearise my observation -------------------------------------------------
     const bool have_pt = p1_thread && pl < np;
     const int p = c0 + pl;
     unsigned mask = 0;
+    double X[3] = {0, 0, 0};
     double Wm[18];
+    double cg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     bool seen = false;
     if (have_pt) {
       mask = V.pt_mask[p];
       seen = (mask >> sl) & 1u;
+      if (mask) { X[0] = V.pts[cur][(size_t)p * 3]; X[1] = V.pts[cur][(size_t)p * 3 + 1]; X[2] = V.pts[cur][(size_t)p * 3 + 2]; }
     }
-    if (seen) {
-      const double X[3] = {V.pts[cur][(size_t)p * 3], V.pts[cur][(size_t)p * 3 + 1], V.pts[cur][(size_t)p * 3 + 2]};
+    if (seen && (UBA_TILE_PHASES & 1)) {
       const int o = V.pt_obs_off[p] + __popc(mask & ((1u << sl) - 1u));
       double f[M];
 #pragma unroll
@@ -692,18 +685,12 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
       double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
       const double rho0 = obs_linearize<M>(camS + sl * kCamStride, X, f, cid, V.calib, V.loss, rraw, wgt, F, E, rh);
       cost += 0.5 * rho0;
-      double* es = Es + t * 9;
-      double c6[6] = {0, 0, 0, 0, 0, 0}, g3[3] = {0, 0, 0};
 #pragma unroll
       for (int a = 0; a < NR; a++) {
-        c6[0] = fma(E[a][0], E[a][0], c6[0]); c6[1] = fma(E[a][0], E[a][1], c6[1]); c6[2] = fma(E[a][0], E[a][2], c6[2]);
-        c6[3] = fma(E[a][1], E[a][1], c6[3]); c6[4] = fma(E[a][1], E[a][2], c6[4]); c6[5] = fma(E[a][2], E[a][2], c6[5]);
-        g3[0] = fma(E[a][0], rh[a], g3[0]); g3[1] = fma(E[a][1], rh[a], g3[1]); g3[2] = fma(E[a][2], rh[a], g3[2]);
+        cg[0] = fma(E[a][0], E[a][0], cg[0]); cg[1] = fma(E[a][0], E[a][1], cg[1]); cg[2] = fma(E[a][0], E[a][2], cg[2]);
+        cg[3] = fma(E[a][1], E[a][1], cg[3]); cg[4] = fma(E[a][1], E[a][2], cg[4]); cg[5] = fma(E[a][2], E[a][2], cg[5]);
+        cg[6] = fma(E[a][0], rh[a], cg[6]); cg[7] = fma(E[a][1], rh[a], cg[7]); cg[8] = fma(E[a][2], rh[a], cg[8]);
       }
-#pragma unroll
-      for (int i = 0; i < 6; i++) es[i] = c6[i];
-#pragma unroll
-      for (int i = 0; i < 3; i++) es[6 + i] = g3[i];
       if (my_free) {
         int q = 0;
 #pragma unroll
@@ -728,70 +715,69 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
           }
       }
     }
-    __syncthreads();
-    // ---- phase 1c: one thread per point: sum its observations' E^T E / E^T r, damping, 3x3 factor ----
-    if (t < np && pmask) {
-      const int pp = c0 + t;
-      double cg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      unsigned m = pmask;
-      while (m) {
-        const int s2i = __ffs(m) - 1;
-        m &= m - 1;
-        const double* es = Es + (t * nl + s2i) * 9;
+    // ---- phase 1b: sum E^T E / E^T r over the point's slot lanes (segmented shuffle tree + broadcast) ----
+    if (UBA_TILE_PHASES & 4) {
+      for (int off = 1; off < nl; off <<= 1) {
+        const bool take = sl + off < nl;
 #pragma unroll
-        for (int e = 0; e < 9; e++) cg[e] += es[e];
+        for (int e = 0; e < 9; e++) {
+          const double o = __shfl_down_sync(FULL, cg[e], off);
+          if (take) cg[e] += o;
+        }
       }
+#pragma unroll
+      for (int e = 0; e < 9; e++) cg[e] = __shfl_sync(FULL, cg[e], seg_base);
+    }
+    // ---- phase 1c: damping + 3x3 factor, redundantly in every lane of the point ------------------------
+    double Li[6] = {0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
+    if (have_pt && mask && (UBA_TILE_PHASES & 4)) {
       const double Cd[3] = {cg[0], cg[3], cg[5]};
       double s2[3], lam[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        s2[c] = scale_ready ? s2p[c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
+        s2[c] = scale_ready ? V.pt_s2[(size_t)p * 3 + c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
         lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
       }
       const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
       const double gg[3] = {cg[6], cg[7], cg[8]};
-      double Li[6] = {0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0};
       const bool ok = point_factor(Cdamp, Li);
-      double* rec = V.pt_rec + (size_t)pp * kPtRec;
-      if (!ok) {
-        fail += 1.0;
+      if (ok) linv_mul(Li, gg, h);
+      else {
 #pragma unroll
         for (int i = 0; i < 6; i++) Li[i] = 0.0;
-#pragma unroll
-        for (int i = 0; i < kPtRec; i++) rec[i] = 0.0;
-      } else {
-        linv_mul(Li, gg, h);
-#pragma unroll
-        for (int i = 0; i < 6; i++) rec[i] = Li[i];
-#pragma unroll
-        for (int i = 0; i < 3; i++) { rec[6 + i] = h[i]; rec[9 + i] = gg[i]; rec[12 + i] = lam[i]; }
-        rec[15] = 0.0;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const double proj = V.cfg.use_bounds ? clampd(Xp[c] - gg[c], V.calib.lo[c], V.calib.hi[c]) : Xp[c] - gg[c];
-          gmax = fmax(gmax, fabs(Xp[c] - proj));
-        }
       }
-      if (!scale_ready) { V.pt_s2[(size_t)pp * 3] = s2[0]; V.pt_s2[(size_t)pp * 3 + 1] = s2[1]; V.pt_s2[(size_t)pp * 3 + 2] = s2[2]; }
+      if (sl == (int)__ffs(mask) - 1) {        // the point's first observing lane writes its record
+        double* rec = V.pt_rec + (size_t)p * kPtRec;
+        if (!ok) {
+          fail += 1.0;
 #pragma unroll
-      for (int i = 0; i < 6; i++) LiS[t * 6 + i] = Li[i];
-      hS[t * 3] = h[0]; hS[t * 3 + 1] = h[1]; hS[t * 3 + 2] = h[2];
+          for (int i = 0; i < kPtRec; i++) rec[i] = 0.0;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; i++) rec[i] = Li[i];
+#pragma unroll
+          for (int i = 0; i < 3; i++) { rec[6 + i] = h[i]; rec[9 + i] = gg[i]; rec[12 + i] = lam[i]; }
+          rec[15] = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const double proj = V.cfg.use_bounds ? clampd(X[c] - gg[c], V.calib.lo[c], V.calib.hi[c]) : X[c] - gg[c];
+            gmax = fmax(gmax, fabs(X[c] - proj));
+          }
+        }
+        if (!scale_ready) { V.pt_s2[(size_t)p * 3] = s2[0]; V.pt_s2[(size_t)p * 3 + 1] = s2[1]; V.pt_s2[(size_t)p * 3 + 2] = s2[2]; }
+      }
     }
-    __syncthreads();
     // ---- phase 1d: Z = W L^-T into the chunk matrix Zm (zeros where the point does not see my slot) ----
-    if (p1_thread && my_free) {
+    if (p1_thread && my_free && (UBA_TILE_PHASES & 8)) {
       double* zc = Zm + (size_t)(6 * (sl - nfx)) * ldz + 3 * pl;
       if (seen) {
-        const double* Li = LiS + pl * 6;
-        const double l0 = Li[0], l1 = Li[1], l2 = Li[2], l3 = Li[3], l4 = Li[4], l5 = Li[5];
-        const double h0 = hS[pl * 3], h1 = hS[pl * 3 + 1], h2 = hS[pl * 3 + 2];
 #pragma unroll
         for (int r = 0; r < 6; r++) {
-          const double z0 = Wm[r * 3] * l0;
-          const double z1 = fma(Wm[r * 3], l1, Wm[r * 3 + 1] * l2);
-          const double z2 = fma(Wm[r * 3], l3, fma(Wm[r * 3 + 1], l4, Wm[r * 3 + 2] * l5));
+          const double z0 = Wm[r * 3] * Li[0];
+          const double z1 = fma(Wm[r * 3], Li[1], Wm[r * 3 + 1] * Li[2]);
+          const double z2 = fma(Wm[r * 3], Li[3], fma(Wm[r * 3 + 1], Li[4], Wm[r * 3 + 2] * Li[5]));
           zc[(size_t)r * ldz] = z0; zc[(size_t)r * ldz + 1] = z1; zc[(size_t)r * ldz + 2] = z2;
-          zq[r] = fma(z0, h0, fma(z1, h1, fma(z2, h2, zq[r])));
+          zq[r] = fma(z0, h[0], fma(z1, h[1], fma(z2, h[2], zq[r])));
         }
       } else {
 #pragma unroll
@@ -800,7 +786,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
     }
     __syncthreads();
     // ---- phase 2: tensor-core SYRK over the chunk: acc(I,J) += Zm[8I.., k] Zm[8J.., k]^T ------------
-    if (nlf > 0) {
+    if (nlf > 0 && (UBA_TILE_PHASES & 16)) {
       const int frow = lane >> 2, fk = lane & 3;
       for (int ks = kq; ks < ksteps; ks += KG) {
         const double* col = Zm + 4 * ks + fk;
@@ -879,9 +865,9 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
     }
     __syncthreads();
   }
-  // ---- flush: camera blocks B, gradients v, rhs terms Z h ----------------------------------------
+  // ---- flush: camera blocks B, gradients v, rhs terms Z h: summed over a slot's lanes through shared memory
   if (p1_thread && my_free) {
-    double* o = scratch + (size_t)t * 33;
+    double* o = scratch + (size_t)(pl * nl + sl) * 33;
 #pragma unroll
     for (int i = 0; i < 21; i++) o[i] = Bq[i];
 #pragma unroll
@@ -1635,9 +1621,7 @@ __global__ void __launch_bounds__(128) k_backsub(DevView V) {
         for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
         double rraw[M];
         const double s = obs_residual<M>(camRn + (size_t)gc * kCamStride, Xn, f, (oc >> 30) & 1, V.calib, rraw);
-        double rho0, rho1;
-        loss_eval(V.loss, s, rho0, rho1);
-        cnew += 0.5 * rho0;
+        cnew += 0.5 * loss_rho(V.loss, s);
       }
     }
     V.pts[nxt][(size_t)p * 3] = Xn[0]; V.pts[nxt][(size_t)p * 3 + 1] = Xn[1]; V.pts[nxt][(size_t)p * 3 + 2] = Xn[2];
@@ -1892,8 +1876,10 @@ size_t lin_tile2_smem_bytes(int nt) {
   (void)nt;
   return 0;
 #else
-  // camS | Es [nt][9] | LiS [nt][6] | hS [nt][3] | maskS [nt] | Zm (rows 8T <= 128, row stride t2_ldz(Pc))
-  return sizeof(double) * (kTileMaxLocal * kCamStride + nt * 9 + nt * 6 + nt * 3 + nt / 2 + t2_zm_doubles(nt));
+  // camS | Zm (rows 8T <= 128, row stride t2_ldz(Pc)); the flush scratch ([points x slots][33] <= nt*33 doubles, or
+  // the (8T) x (8T+1) K-group reduction tile, T <= 12 there) aliases Zm
+  const size_t zm = t2_zm_doubles(nt), fl = (size_t)nt * 33, sl = 96 * 97;
+  return sizeof(double) * (kTileMaxLocal * kCamStride + std::max(zm, std::max(fl, nt == 256 ? sl : (size_t)(64 * 65))));
 #endif
 }
 
