@@ -102,23 +102,33 @@ def build_workload(name, rank, world, windows, scale):
 
 
 def algorithmic_work(wins, fixed):
-    """Algorithmic bytes / flops of ONE linearise+Schur pass (formulas of SURVEY.md §8(d), restated in DESIGN.md)."""
+    """Algorithmic bytes / flops of ONE linearise+Schur pass (formulas of SURVEY.md §8(d), restated in DESIGN.md §3):
+    bytes = 40 N_o + 96 N_p + 8 (36 nnzb + 6 N_c') + 48 N_c,  flops = 620 N_o + sum_j (50 + 144 k_j + 216 k_j (k_j + 1) / 2),
+    k_j = observations of point j by free cameras, nnzb = camera-pair blocks inside the co-visibility band."""
     nbytes = 0.0; flops = 0.0
     for w in wins:
         free = w.cam_idx >= fixed
         k = np.bincount(w.pt_idx[free], minlength=w.n_pts).astype(np.float64)
-        pairs = np.unique(np.stack([w.pt_idx[free].astype(np.int64)], 0), axis=1).shape[1]  # points with free observations
         ncf = len(np.unique(w.cam_idx[free]))
-        # camera-pair blocks touched: for consecutive tracks the band; computed exactly from the data on small inputs
         lo = np.full(w.n_pts, 1 << 30); hi = np.full(w.n_pts, -1)
         np.minimum.at(lo, w.pt_idx[free], w.cam_idx[free]); np.maximum.at(hi, w.pt_idx[free], w.cam_idx[free])
-        span = np.clip(hi - lo, 0, None)[hi >= 0]
+        span = (hi - lo)[hi >= 0]
         band = int(span.max()) if span.size else 0
         nnzb = sum(max(0, ncf - d) for d in range(band + 1))
         nbytes += 40.0 * w.n_obs + 96.0 * w.n_pts + 8.0 * (36.0 * nnzb + 6.0 * ncf) + 48.0 * w.n_cams
         flops += 620.0 * w.n_obs + float(np.sum(50.0 + 144.0 * k + 216.0 * k * (k + 1) / 2.0))
-        del pairs
     return nbytes, flops
+
+
+def measured_traffic(name):
+    """DRAM bytes (read + write) of one launch of the linearise kernel from the committed ncu --set full capture
+    (profiles/ncu_traffic.json); null when the workload was not captured."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        if name in d:
+            return d[name]["dram_bytes_per_launch"]
+    return None
 
 
 def h2d_d2h_bytes(wins):
@@ -266,7 +276,7 @@ def main():
     achieved_gbs = nbytes / (ms_lin * 1e-3) / 1e9
     achieved_tf = flops / (ms_lin * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "linearise+Schur pass", "kernel_ms": ms_lin,
+                "traffic": measured_traffic(name) if world == 1 and args.scale == 1.0 else None, "peak_source": peak_src, "kernel": "linearise+Schur pass", "kernel_ms": ms_lin,
                 "algorithmic_bytes": nbytes, "algorithmic_flops": flops,
                 "fp64": {"achieved_tflops": achieved_tf, "peak_tflops": fp64_peak, "frac": achieved_tf / fp64_peak,
                          "peak_source": "measured here (DFMA micro-kernel, uba_probe_fp64_tflops)"},
