@@ -10,7 +10,7 @@ h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx
 h.optimise(2)
 out = np.zeros(40)
 lib.uba_debug_read_zbuf(h._h, capi.dptr(out), 40)
-names = ["load","step2","bar1wait","step3","bar2wait","step4","bar3wait","-"]
-for lbl, off in (("t0",0),("t1",8),("t70",16),("t200",24)):
+names = ["panel_T6","panel_corner","panel_factor","w_trsm","w_namedbar","w_update","cta_barrier","-"]
+for lbl, off in (("t0 (row thread)",0),("t64 (y/Lt thread)",8),("t100 (pairs only)",16),("t224 (panel lane 0)",24)):
     print(lbl, {n:int(v) for n,v in zip(names, out[off:off+8])}, "sum", int(out[off:off+8].sum()))
 print("backward cycles", int(out[32]))

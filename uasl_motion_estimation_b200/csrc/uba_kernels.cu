@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "uba_device.h"
 
@@ -1443,6 +1444,263 @@ __global__ void __launch_bounds__(256) k_chol_banded(DevView V, int w, int beta)
   if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
 
+// Band Cholesky with LOOKAHEAD (beta >= 11): same algorithm as k_chol_banded, but the serial part of a
+// block step no longer stalls the CTA.  Warp 7 is the "panel" warp: during step k it computes, for the rows
+// of block k+1 only, their triangular solve against L_kk(k), the update of the next diagonal block, and its
+// 6x6 factor L_kk(k+1) — while warps 0..6 do step k's triangular solves for all rows (into Xbuf, not in place,
+// so the panel warp still sees the untouched entries) and the trailing update of the band window (minus the
+// corner the panel warp owns).  One CTA-wide barrier per block step instead of three.
+template <int PER>
+__global__ void __launch_bounds__(256) k_chol_banded_la(DevView V, int w, int beta) {
+  extern __shared__ double sm[];
+  const WinState* st = &V.ws[w];
+  if (st->done) return;
+  constexpr int NWORK = 224;                  // worker threads (warps 0..6); warp 7 is the panel warp
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const int bw1 = beta + 1;
+  const int ring_size = kBandRing * bw1;
+  double* ring = sm;                          // [kBandRing][bw1]: row i holds A[i][i-beta .. i]
+  double* y = ring + ring_size;               // [n + beta + 7] (tail zero-padded)
+  double* Xbuf = y + (n + beta + 8);          // [beta][6] triangular-solve results of the current step
+  __shared__ int s_fail;
+  __shared__ double s_Lkk[2][36], s_invk[2][6], s_z[6], s_xp[36], s_corner[21];
+  double* rhs = V.rhs + (size_t)6 * f0;
+  double* Lt = V.A + V.w_red_off[w];
+  const double* Ab = Lt + (size_t)n * bw1;
+  const int t = threadIdx.x, nt = blockDim.x;
+  const bool panel = t >= NWORK;
+  const int pl = t - NWORK;                   // lane of the panel warp
+  if (t == 0) s_fail = 0;
+  for (int i = t; i < n + beta + 7; i += nt) y[i] = i < n ? rhs[i] : 0.0;
+  for (int e = t; e < kBandRing * bw1; e += nt) { const int i = e / bw1; ring[e] = i < n ? Ab[e] : 0.0; }
+  // trailing-update pairs (ti >= tk) over the beta rows below the block; the corner (both rows inside the
+  // next block) belongs to the panel warp
+  const int npairs = beta * (beta + 1) / 2;
+  int pti[PER], ptk[PER];
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int e = t + q * NWORK;
+    int ti = -1, tk = 0;
+    if (!panel && e < npairs) {
+      int d0 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((d0 + 1) * (d0 + 2) / 2 <= e) d0++;
+      while (d0 * (d0 + 1) / 2 > e) d0--;
+      ti = d0; tk = e - d0 * (d0 + 1) / 2;
+      if (ti < 6) ti = -1;                    // corner pair
+    }
+    pti[q] = ti; ptk[q] = tk;
+  }
+  const int nblk = n / 6;
+#ifdef UBA_BAND_TIMING
+  long long tmx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tqx;
+#define LCLK(v) asm volatile("mov.u64 %0, %%clock64;" : "=l"(v) :: "memory")
+#define LT0() LCLK(tqx);
+#define LT(k) { long long now_; LCLK(now_); tmx[k] += now_ - tqx; tqx = now_; }
+#else
+#define LT0()
+#define LT(k)
+#endif
+  __syncthreads();
+  // prologue: factor of block 0
+  if (t == NWORK) {
+    double L[6][6], iv[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) L[r][c] = c <= r ? ring[r * bw1 + beta - r + c] : 0.0;
+    if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      s_invk[0][r] = iv[r];
+#pragma unroll
+      for (int c = 0; c < 6; c++) s_Lkk[0][r * 6 + c] = L[r][c];
+    }
+  }
+  __syncthreads();
+  int o0 = 0;                                 // ring offset of row c0 (blocks never straddle the wrap)
+  for (int kb = 0; kb < nblk; kb++) {
+    const int c0 = 6 * kb, par = kb & 1;
+    const double* Lk = s_Lkk[par];
+    const double* ivk = s_invk[par];
+    LT0()
+    if (panel) {
+      // ---- panel warp: next diagonal block (k+1) --------------------------------------------------
+      if (kb + 1 < nblk) {
+        int on = o0 + 6 * bw1; if (on >= ring_size) on -= ring_size;   // ring offset of row c0 + 6
+        if (pl < 6) {
+          // row c0+6+pl against L_kk(k): entries (i, c0+c) at column offset beta - 6 - pl + c (>= 0: beta >= 11)
+          const double* row = ring + on + pl * bw1 + (beta - 6 - pl);
+          double x[6];
+#pragma unroll
+          for (int c = 0; c < 6; c++) x[c] = row[c];
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+            x[c] *= ivk[c];
+#pragma unroll
+            for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], Lk[m * 6 + c], x[m]);
+          }
+#pragma unroll
+          for (int c = 0; c < 6; c++) s_xp[pl * 6 + c] = x[c];
+        }
+        __syncwarp();
+        LT(0)
+        if (pl < 21) {
+          int r = 0, e = pl;
+          while (e > r) { e -= r + 1; r++; }   // pl -> (r, c = e), c <= r
+          double v = ring[on + r * bw1 + beta - r + e];
+#pragma unroll
+          for (int m = 0; m < 6; m++) v = fma(-s_xp[r * 6 + m], s_xp[e * 6 + m], v);
+          s_corner[pl] = v;
+        }
+        __syncwarp();
+        LT(1)
+        if (pl == 0) {
+          double L[6][6], iv[6];
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) L[r][c] = c <= r ? s_corner[r * (r + 1) / 2 + c] : 0.0;
+          if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            s_invk[par ^ 1][r] = iv[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) s_Lkk[par ^ 1][r * 6 + c] = L[r][c];
+          }
+        }
+        LT(2)
+      }
+    } else {
+      // ---- workers: ring reload prefetch -------------------------------------------------------------
+      constexpr int kPre = (30 * (kBandMaxBeta + 1) + NWORK - 1) / NWORK;
+      double pre[kPre];
+      const bool reload = kb > 0 && (kb % 5) == 0;
+      if (reload) {
+        const int r0 = c0 + kBandRing - 30;
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+          const int e = t + q * NWORK;
+          const int i = r0 + e / bw1;
+          pre[q] = (e < 30 * bw1 && i < n) ? Ab[(size_t)r0 * bw1 + e] : 0.0;
+        }
+      }
+      // ---- (3) rows below the block inside the band, and the rhs: X L_kk^T = A --------------------------
+      if (t <= beta) {
+        const bool is_rhs = t == beta;
+        int orow = o0 + (6 + t) * bw1; if (orow >= ring_size) orow -= ring_size;
+        const double* row = ring + orow;
+        const int base = beta - 6 - t;        // column offset of (i, c0); entries with base + c < 0 lie outside the band
+        double x[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((base + c >= 0) ? row[base + c] : 0.0);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], Lk[m * 6 + c], x[m]);
+        }
+        if (is_rhs) {
+#pragma unroll
+          for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; c++) Xbuf[t * 6 + c] = x[c];
+        }
+      }
+      LT(3)
+      asm volatile("bar.sync 1, %0;" ::"n"(NWORK));
+      LT(4)
+      // ---- (4) trailing update of the band window (corner excluded), rhs update, factor rows out ------
+#pragma unroll
+      for (int q = 0; q < PER; q++) {
+        const int ti = pti[q], tk = ptk[q];
+        if (ti >= 0) {
+          int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
+          const double* xi = Xbuf + ti * 6;
+          const double* xk = Xbuf + tk * 6;
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc = fma(xi[c], xk[c], acc);
+          ring[oi + (beta - ti + tk)] -= acc;
+        }
+      }
+      if (t >= 64 && t < 64 + beta) {
+        const int tt = t - 64, i = c0 + 6 + tt;
+        const int base = beta - 6 - tt;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          const double l = Xbuf[tt * 6 + c];
+          acc = fma(l, s_z[c], acc);
+          if (base + c >= 0 && i < n) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
+        }
+        y[i] -= acc;
+      } else if (t >= 160 && t < 166) {
+        const int r = t - 160;
+        Lt[(size_t)(c0 + r) * bw1] = ivk[r];
+        for (int c = 0; c < r; c++) Lt[(size_t)(c0 + r) * bw1 + (r - c)] = Lk[r * 6 + c];
+      }
+      if (reload) {
+        const int r0 = c0 + kBandRing - 30;
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+          const int e = t + q * NWORK;
+          if (e < 30 * bw1) ring[((r0 + e / bw1) % kBandRing) * bw1 + e % bw1] = pre[q];
+        }
+      }
+      LT(5)
+    }
+    __syncthreads();
+    LT(6)
+    o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
+  }
+#ifdef UBA_BAND_TIMING
+  if (t == 0 || t == 64 || t == 100 || t == 224) { for (int k = 0; k < 8; k++) V.Zbuf[(t == 0 ? 0 : t == 64 ? 8 : t == 100 ? 16 : 24) + k] = (double)tmx[k]; }
+#endif
+  // backward substitution L^T x = z, blocked; factor rows staged through shared memory in chunks
+  constexpr int kChunk = 126;
+  for (int i1 = n; i1 > 0; i1 -= kChunk) {
+    const int i0 = max(0, i1 - kChunk);
+    for (int e = t; e < (i1 - i0) * bw1; e += nt) {
+      const int i = i0 + e / bw1, c = e % bw1;
+      ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
+    }
+    __syncthreads();
+    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6) {
+      const double* blk = ring + (c0 - i0) * bw1;   // row c0 + m at blk + m*bw1: [0] = 1/L, [d] = L[c0+m][c0+m-d]
+      if (t == 0) {
+        double xb[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
+#pragma unroll
+        for (int c = 5; c >= 0; c--) {
+          xb[c] *= blk[c * bw1];
+#pragma unroll
+          for (int m = 0; m < 6; m++) if (m < c) xb[m] = fma(-blk[c * bw1 + (c - m)], xb[c], xb[m]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_z[c] = xb[c]; }
+      }
+      __syncthreads();
+      if (t < beta) {
+        const int j = c0 - 1 - t;
+        if (j >= 0) {
+          double v = y[j];
+#pragma unroll
+          for (int c = 0; c < 6; c++) { const int d = c0 + c - j; if (d <= beta) v = fma(-blk[c * bw1 + d], s_z[c], v); }
+          y[j] = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const bool failed = s_fail != 0;
+  for (int i = t; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
+  if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
+}
+
 // blocked forward + backward substitution with the factor in global memory; one CTA
 __global__ void __launch_bounds__(1024) k_trsv_large(DevView V, int w) {
   extern __shared__ double y[];  // [n]
@@ -1966,6 +2224,16 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
       const int n = h_win_n[w];
       if (h_win_beta[w] > 0) {
         const int beta = h_win_beta[w];
+        static const bool use_la = [] { const char* e = getenv("UBA_BAND_LA"); return !(e && e[0] == '0'); }();
+        if (use_la && beta >= 11) {
+          const size_t smem = ((size_t)kBandRing * (beta + 1) + n + beta + 8 + (size_t)beta * 6 + 8) * sizeof(double);
+          const int per = (beta * (beta + 1) / 2 + 223) / 224;
+#define UBA_LA_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_la<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_la<PP>, 1, 256, smem, st, V, w, beta); }
+          if (per <= 1) UBA_LA_LAUNCH(1) else if (per <= 2) UBA_LA_LAUNCH(2) else if (per <= 4) UBA_LA_LAUNCH(4) else UBA_LA_LAUNCH(9)
+#undef UBA_LA_LAUNCH
+          launches++;
+          continue;
+        }
         const size_t smem = ((size_t)kBandRing * (beta + 1) + n + beta + 8) * sizeof(double);
         const int per = (beta * (beta + 1) / 2 + 255) / 256;
         if (per <= 1) { cudaFuncSetAttribute(k_chol_banded<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<1>, 1, 256, smem, st, V, w, beta); }
