@@ -316,7 +316,8 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   }
   h->tile_threads = nt;
   // parts: aim at a few CTAs per SM, never less than 2 chunks of points per CTA
-  const size_t target_parts = 2 * 148 * (256 / nt);
+  size_t target_parts = 2 * 148 * (256 / nt);
+  if (const char* e = std::getenv("UBA_TILE_PARTS")) target_parts = (size_t)std::max(1, std::atoi(e));
   for (const Item& it : items) {
     const int Pc = nt / it.nl;
     int part_pts = std::max<size_t>(2 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);

@@ -619,7 +619,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   // phase-1 role, warp aligned: a point's nl slot lanes sit in ONE warp, so its 3x3 block is reduced with
   // shuffles and factored redundantly by every lane of the point (no shared staging, no idle threads)
   const int ppw = min(32 / nl, kT2MaxPc / W);      // points per warp
-  const int Pc = W * ppw;                          // points per chunk
+  const int Pc = W * ppw;                          // points per chunk (one observation per lane)
   const int plw = lane / nl, sl = lane - plw * nl;
   const bool p1_thread = plw < ppw;
   const int pl = warp * ppw + plw;                 // point slot in the chunk
@@ -662,27 +662,63 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   double cost = 0.0, gmax = 0.0, fail = 0.0;
   __syncthreads();
 
+  // software pipeline over chunks (registers): stage B holds the mask / first-observation offset of the chunk
+  // after next, stage A the mask, point and features of the next chunk, so that no global round trip sits at
+  // the head of a chunk
+  unsigned maskA = 0, maskB = 0;
+  int oA = 0, offB = 0;
+  double XA[3] = {0, 0, 0}, fA[M];
+  int cidA = 0;
+#pragma unroll
+  for (int m = 0; m < M; m++) fA[m] = 0.0;
+  {
+    const int pa = part.pt_begin + pl, pb = pa + Pc;
+    if (p1_thread && pa < part.pt_end) {
+      maskA = V.pt_mask[pa];
+      if (maskA) {
+        XA[0] = V.pts[cur][(size_t)pa * 3]; XA[1] = V.pts[cur][(size_t)pa * 3 + 1]; XA[2] = V.pts[cur][(size_t)pa * 3 + 2];
+        if ((maskA >> sl) & 1u) {
+          oA = V.pt_obs_off[pa] + __popc(maskA & ((1u << sl) - 1u));
+#pragma unroll
+          for (int m = 0; m < M; m++) fA[m] = V.feat[(size_t)m * V.NO + oA];
+          if (M == 2) cidA = (V.obs_cam[oA] >> 30) & 1;
+        }
+      }
+    }
+    if (p1_thread && pb < part.pt_end) { maskB = V.pt_mask[pb]; offB = V.pt_obs_off[pb]; }
+  }
   for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += Pc) {
     const int np = min(Pc, part.pt_end - c0);
     // ---- phase 1a: linearise my observation -------------------------------------------------
     const bool have_pt = p1_thread && pl < np;
     const int p = c0 + pl;
-    unsigned mask = 0;
-    double X[3] = {0, 0, 0};
+    const unsigned mask = maskA;
+    const bool seen = have_pt && ((mask >> sl) & 1u);
+    const double X[3] = {XA[0], XA[1], XA[2]};
+    double f[M];
+#pragma unroll
+    for (int m = 0; m < M; m++) f[m] = fA[m];
+    const int cid = cidA;
     double Wm[18];
     double cg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    bool seen = false;
-    if (have_pt) {
-      mask = V.pt_mask[p];
-      seen = (mask >> sl) & 1u;
-      if (mask) { X[0] = V.pts[cur][(size_t)p * 3]; X[1] = V.pts[cur][(size_t)p * 3 + 1]; X[2] = V.pts[cur][(size_t)p * 3 + 2]; }
+    {
+      // advance the pipeline: A <- next chunk (using stage B's mask / offset), B <- the chunk after next
+      const int pa = p + Pc, pb = pa + Pc;
+      maskA = maskB;
+      const int offA = offB;
+      maskB = 0;
+      if (p1_thread && pb < part.pt_end) { maskB = V.pt_mask[pb]; offB = V.pt_obs_off[pb]; }
+      if (maskA) {
+        XA[0] = V.pts[cur][(size_t)pa * 3]; XA[1] = V.pts[cur][(size_t)pa * 3 + 1]; XA[2] = V.pts[cur][(size_t)pa * 3 + 2];
+        if ((maskA >> sl) & 1u) {
+          oA = offA + __popc(maskA & ((1u << sl) - 1u));
+#pragma unroll
+          for (int m = 0; m < M; m++) fA[m] = V.feat[(size_t)m * V.NO + oA];
+          if (M == 2) cidA = (V.obs_cam[oA] >> 30) & 1;
+        }
+      }
     }
     if (seen && (UBA_TILE_PHASES & 1)) {
-      const int o = V.pt_obs_off[p] + __popc(mask & ((1u << sl) - 1u));
-      double f[M];
-#pragma unroll
-      for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
-      const int cid = (M == 2) ? ((V.obs_cam[o] >> 30) & 1) : 0;
       double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
       const double rho0 = obs_linearize<M>(camS + sl * kCamStride, X, f, cid, V.calib, V.loss, rraw, wgt, F, E, rh);
       cost += 0.5 * rho0;
