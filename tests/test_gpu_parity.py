@@ -183,3 +183,64 @@ def test_pose_covariances(gpu_lib, oracle, name, scale):
     # results of the optimisation itself are unaffected by the extra pass
     o = oracle.optimise(win, cfg, 2)
     assert rel(cams, o["cams"]) < STATE_TOL and rel(pts, o["pts"]) < STATE_TOL
+
+
+def test_long_tracks_fall_back_to_the_generic_lineariser(gpu_lib, oracle):
+    """30 keyframes: full tracks (28 free cameras > the tile limit of 21) mixed with short ones -> the tiled kernel
+    and the generic kernel both accumulate into the same reduced system."""
+    long_w = synth.generate(30, 60, 30, 30, full_tracks=1, seed=11, lib=gpu_lib)
+    short_w = synth.generate(30, 400, 3, 9, seed=12, lib=gpu_lib)
+    cat = lambda a, b: np.ascontiguousarray(np.concatenate([a, b]))
+    win = synth.Window(4, long_w.cams_gt, long_w.cams_init, cat(long_w.pts_gt, short_w.pts_gt), cat(long_w.pts_init, short_w.pts_init),
+                       cat(long_w.feats, short_w.feats), cat(long_w.cam_idx, short_w.cam_idx),
+                       cat(long_w.pt_idx, short_w.pt_idx + long_w.n_pts).astype(np.int32), cat(long_w.cam_id, short_w.cam_id), 2, long_w.calib)
+    cfg = capi.default_config(gpu_lib, fixed_iterations=5)
+    h = capi.Handle(cfg, lib=gpu_lib)
+    h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+    g = h.linearize(2, 1e4); r = oracle.linearize(win, cfg, 2, 1e4)
+    for k in BLOCKS:
+        assert rel(g[k], r[k]) < BLOCK_TOL, (k, rel(g[k], r[k]))
+    rc, _ = h.optimise(2)
+    o = oracle.optimise(win, cfg, 2)
+    assert rc == 0 and rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
+
+
+def test_duplicate_observations_of_one_camera(gpu_lib, oracle):
+    """The reference accepts two residual blocks on the same (camera, point) pair; such points bypass the tile plan."""
+    win = synth.config_window("c1", scale=0.05, lib=gpu_lib)
+    dup = np.flatnonzero((win.pt_idx % 5 == 0) & (win.cam_idx == 4))
+    feats = np.concatenate([win.feats, win.feats[dup] + 0.25]); cam_idx = np.concatenate([win.cam_idx, win.cam_idx[dup]])
+    pt_idx = np.concatenate([win.pt_idx, win.pt_idx[dup]]); cam_id = np.concatenate([win.cam_id, win.cam_id[dup]])
+    w2 = synth.Window(4, win.cams_gt, win.cams_init, win.pts_gt, win.pts_init, np.ascontiguousarray(feats), cam_idx.astype(np.int32),
+                      pt_idx.astype(np.int32), cam_id.astype(np.int32), 2, win.calib)
+    cfg = capi.default_config(gpu_lib, fixed_iterations=4)
+    h = capi.Handle(cfg, lib=gpu_lib)
+    h.set_problem(4, w2.cams_init, w2.pts_init, w2.feats, w2.cam_idx, w2.pt_idx, w2.cam_id, w2.calib)
+    g = h.linearize(2, 1e4); r = oracle.linearize(w2, cfg, 2, 1e4)
+    for k in ("residuals", "cost", "B", "C", "S", "rhs", "grad_cams", "grad_pts"):
+        assert rel(g[k], r[k]) < BLOCK_TOL, (k, rel(g[k], r[k]))
+    rc, _ = h.optimise(2)
+    o = oracle.optimise(w2, cfg, 2)
+    assert rc == 0 and rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
+
+
+def test_mono_batch_and_window_without_free_cameras(gpu_lib, oracle):
+    """M = 2 batch; the last window keeps every camera fixed (points only)."""
+    wins = [synth.config_window("c1", window=i, scale=0.04, lib=gpu_lib, M=2) for i in range(3)]
+    cfg = capi.default_config(gpu_lib, fixed_iterations=4)
+    h = capi.Handle(cfg, lib=gpu_lib)
+    h.set_batch(**synth.concat_windows(wins))
+    rc, sums = h.optimise(2)
+    assert rc == 0
+    cams = h.cameras(); pts = h.points(); c0 = p0 = 0
+    for win in wins:
+        o = oracle.optimise(win, cfg, 2)
+        assert rel(cams[c0:c0 + win.n_cams], o["cams"]) < STATE_TOL and rel(pts[p0:p0 + win.n_pts], o["pts"]) < STATE_TOL
+        c0 += win.n_cams; p0 += win.n_pts
+    h2 = capi.Handle(cfg, lib=gpu_lib)
+    w = wins[0]
+    h2.set_problem(2, w.cams_init, w.pts_init, w.feats, w.cam_idx, w.pt_idx, w.cam_id, w.calib)
+    rc, _ = h2.optimise(w.n_cams)
+    o = oracle.optimise(w, cfg, w.n_cams)
+    np.testing.assert_array_equal(h2.cameras(), w.cams_init)
+    assert rel(h2.points(), o["pts"]) < STATE_TOL
