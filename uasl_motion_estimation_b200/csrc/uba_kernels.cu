@@ -1024,7 +1024,7 @@ __global__ void k_assemble(DevView V) {
   if (banded) {
     // compact band copy for k_chol_banded: Ab[i][c] = A[i][i - beta + c], stored after the factor rows
     const int beta = V.w_beta[w], bw1 = beta + 1;
-    double* Ab = A + (size_t)n * bw1;
+    double* Ab = A + (size_t)2 * n * bw1;   // after the factor rows of both halves of the two-sided solver
     const int64_t nb = (int64_t)n * bw1;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nb; e += (int64_t)gridDim.x * blockDim.x) {
       const int i = (int)(e / bw1), c = (int)(e - (int64_t)i * bw1);
@@ -1284,7 +1284,7 @@ __global__ void __launch_bounds__(256) k_chol_banded(DevView V, int w, int beta)
   __shared__ double s_inv[6], s_z[6];
   double* rhs = V.rhs + (size_t)6 * f0;
   double* Lt = V.A + V.w_red_off[w];
-  const double* Ab = Lt + (size_t)n * bw1;
+  const double* Ab = Lt + (size_t)2 * n * bw1;
   const int t = threadIdx.x, nt = blockDim.x;
   if (t == 0) s_fail = 0;
   for (int i = t; i < n + beta + 7; i += nt) y[i] = i < n ? rhs[i] : 0.0;
@@ -1503,7 +1503,7 @@ __global__ void __launch_bounds__(256) k_chol_banded_la(DevView V, int w, int be
   __shared__ double s_Lkk[2][36], s_invk[2][6], s_z[6], s_xp[36], s_corner[21];
   double* rhs = V.rhs + (size_t)6 * f0;
   double* Lt = V.A + V.w_red_off[w];
-  const double* Ab = Lt + (size_t)n * bw1;
+  const double* Ab = Lt + (size_t)2 * n * bw1;
   const int t = threadIdx.x, nt = blockDim.x;
   const bool panel = t >= NWORK;
   const int pl = t - NWORK;                   // lane of the panel warp
@@ -1734,6 +1734,332 @@ __global__ void __launch_bounds__(256) k_chol_banded_la(DevView V, int w, int be
   }
   const bool failed = s_fail != 0;
   for (int i = t; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
+  if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
+}
+
+// Two-sided band Cholesky with lookahead ("burn at both ends"), beta in [11, 35]: the CTA is split into two
+// halves of 128 threads.  Half 0 eliminates block columns [0, m) top-down, half 1 eliminates the rows below the
+// separator bottom-up, i.e. top-down on the REVERSED matrix (i' = n-1-i keeps the band structure), each exactly
+// like k_chol_banded_la (panel warp + 3 worker warps, named barriers, no CTA-wide barrier in the loop).  They
+// meet at a separator of sw >= beta+1 rows whose Schur complement  A_ss + (T - A_ss) + (B - A_ss)  is factored
+// densely by one warp; then both halves back-substitute concurrently.  Sequential depth: n/12 + sw/6 block
+// steps instead of n/6.
+struct BandHalf {
+  int dir;        // 0: natural order, 1: reversed
+  int nh;         // rows of the half's local system (eliminated rows + separator)
+  int ne;         // rows eliminated by this half (multiple of 6)
+};
+
+template <int PER>
+__global__ void __launch_bounds__(256) k_chol_banded_la2(DevView V, int w, int beta) {
+  extern __shared__ double sm[];
+  const WinState* st = &V.ws[w];
+  if (st->done) return;
+  constexpr int NH = 128, NWORKH = 96;        // threads per half; workers per half (warp 3 of the half is the panel warp)
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const int bw1 = beta + 1;
+  const int sw = ((beta + 1 + 5) / 6) * 6;    // separator rows
+  const int m = (((n - sw) / 2) / 6) * 6;     // rows eliminated by the top half
+  const int ring_size = kBandRing * bw1;
+  const int t = threadIdx.x;
+  const int half = t >> 7, tl = t & 127;
+  BandHalf H;
+  H.dir = half; H.ne = half == 0 ? m : n - m - sw; H.nh = H.ne + sw;
+  // shared memory: per half {ring, y, Xbuf}, then the separator system
+  const int ylen = (n - m) + beta + 8;        // >= nh of either half + tail
+  double* base = sm + (size_t)half * (ring_size + ylen + beta * 6 + 8);
+  double* ring = base;
+  double* y = ring + ring_size;
+  double* Xbuf = y + ylen;
+  double* sep = sm + 2 * (size_t)(ring_size + ylen + beta * 6 + 8);   // [sw][sw + 1] + rhs [sw]
+  __shared__ int s_fail;
+  __shared__ double s_Lkk[2][2][36], s_invk[2][2][6], s_z[2][6], s_xp[2][36], s_corner[2][21];
+  double* rhs = V.rhs + (size_t)6 * f0;
+  double* A0 = V.A + V.w_red_off[w];
+  double* Lt = A0 + (size_t)half * n * bw1;   // this half's factor rows (local row numbering)
+  const double* Ab = A0 + (size_t)2 * n * bw1;
+  const bool panel = tl >= NWORKH;
+  const int pl = tl - NWORKH;
+  if (t == 0) s_fail = 0;
+  // local lower-band entry (i, k = i - beta + c) of this half's system
+  auto band_entry = [&](int i, int c) -> double {
+    if (i >= H.nh || i - beta + c < 0) return 0.0;
+    return H.dir == 0 ? Ab[(size_t)i * bw1 + c] : Ab[(size_t)(n - 1 - i + beta - c) * bw1 + c];
+  };
+  for (int i = tl; i < ylen; i += NH) y[i] = i < H.nh ? rhs[H.dir == 0 ? i : n - 1 - i] : 0.0;
+  for (int e = tl; e < kBandRing * bw1; e += NH) ring[e] = band_entry(e / bw1, e % bw1);
+  const int npairs = beta * (beta + 1) / 2;
+  int pti[PER], ptk[PER];
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int e = tl + q * NWORKH;
+    int ti = -1, tk = 0;
+    if (!panel && e < npairs) {
+      int d0 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((d0 + 1) * (d0 + 2) / 2 <= e) d0++;
+      while (d0 * (d0 + 1) / 2 > e) d0--;
+      ti = d0; tk = e - d0 * (d0 + 1) / 2;
+      if (ti < 6) ti = -1;                    // corner pair: owned by the panel warp
+    }
+    pti[q] = ti; ptk[q] = tk;
+  }
+  // corner entry of panel lane pl: (r, e), e <= r
+  int cr = 0, ce = pl;
+  while (ce > cr) { ce -= cr + 1; cr++; }
+#ifdef UBA_LA2_ONEHALF
+  const int nblk = half == 0 ? H.ne / 6 : 0;   // timing experiment: bottom half idle (results are wrong)
+#else
+  const int nblk = H.ne / 6;
+#endif
+  __syncthreads();
+  if (tl == NWORKH) {                         // prologue: factor of block 0
+    double L[6][6], iv[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) L[r][c] = c <= r ? ring[r * bw1 + beta - r + c] : 0.0;
+    if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      s_invk[half][0][r] = iv[r];
+#pragma unroll
+      for (int c = 0; c < 6; c++) s_Lkk[half][0][r * 6 + c] = L[r][c];
+    }
+  }
+  __syncthreads();
+  int o0 = 0;
+  for (int kb = 0; kb < nblk; kb++) {
+    const int c0 = 6 * kb, par = kb & 1;
+    const double* Lk = s_Lkk[half][par];
+    const double* ivk = s_invk[half][par];
+    if (panel) {
+      {
+        // the block after the last eliminated one is the first separator block: it still needs its corner update
+        // (written back to the ring), it is just not factored here
+        const bool last = kb + 1 == nblk;
+        int on = o0 + 6 * bw1; if (on >= ring_size) on -= ring_size;
+        if (pl < 6) {
+          const double* row = ring + on + pl * bw1 + (beta - 6 - pl);
+          double x[6];
+#pragma unroll
+          for (int c = 0; c < 6; c++) x[c] = row[c];
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+            x[c] *= ivk[c];
+#pragma unroll
+            for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
+          }
+#pragma unroll
+          for (int c = 0; c < 6; c++) s_xp[half][pl * 6 + c] = x[c];
+        }
+        __syncwarp();
+        if (pl < 21) {
+          double v = ring[on + cr * bw1 + beta - cr + ce];
+#pragma unroll
+          for (int mm = 0; mm < 6; mm++) v = fma(-s_xp[half][cr * 6 + mm], s_xp[half][ce * 6 + mm], v);
+          if (last) ring[on + cr * bw1 + beta - cr + ce] = v;
+          s_corner[half][pl] = v;
+        }
+        __syncwarp();
+        if (pl == 0 && !last) {
+          double L[6][6], iv[6];
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) L[r][c] = c <= r ? s_corner[half][r * (r + 1) / 2 + c] : 0.0;
+          if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            s_invk[half][par ^ 1][r] = iv[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) s_Lkk[half][par ^ 1][r * 6 + c] = L[r][c];
+          }
+        }
+      }
+    } else {
+      constexpr int kPre = (30 * 36 + NWORKH - 1) / NWORKH;   // beta <= 35
+      double pre[kPre];
+      const bool reload = kb > 0 && (kb % 5) == 0;
+      if (reload) {
+        const int r0 = c0 + kBandRing - 30;
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+          const int e = tl + q * NWORKH;
+          pre[q] = e < 30 * bw1 ? band_entry(r0 + e / bw1, e % bw1) : 0.0;
+        }
+      }
+      if (tl <= beta) {
+        const bool is_rhs = tl == beta;
+        int orow = o0 + (6 + tl) * bw1; if (orow >= ring_size) orow -= ring_size;
+        const double* row = ring + orow;
+        const int basec = beta - 6 - tl;
+        double x[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((basec + c >= 0) ? row[basec + c] : 0.0);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
+        }
+        if (is_rhs) {
+#pragma unroll
+          for (int c = 0; c < 6; c++) { s_z[half][c] = x[c]; y[c0 + c] = x[c]; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; c++) Xbuf[tl * 6 + c] = x[c];
+        }
+      }
+      if (half == 0) asm volatile("bar.sync 1, %0;" ::"n"(NWORKH)); else asm volatile("bar.sync 2, %0;" ::"n"(NWORKH));
+#pragma unroll
+      for (int q = 0; q < PER; q++) {
+        const int ti = pti[q], tk = ptk[q];
+        if (ti >= 0) {
+          int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
+          const double* xi = Xbuf + ti * 6;
+          const double* xk = Xbuf + tk * 6;
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc = fma(xi[c], xk[c], acc);
+          ring[oi + (beta - ti + tk)] -= acc;
+        }
+      }
+      if (tl >= 32 && tl < 32 + beta) {
+        const int tt = tl - 32, i = c0 + 6 + tt;
+        const int basec = beta - 6 - tt;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          const double l = Xbuf[tt * 6 + c];
+          acc = fma(l, s_z[half][c], acc);
+          if (basec + c >= 0 && i < H.nh) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
+        }
+        y[i] -= acc;
+      } else if (tl >= 80 && tl < 86) {
+        const int r = tl - 80;
+        Lt[(size_t)(c0 + r) * bw1] = ivk[r];
+        for (int c = 0; c < r; c++) Lt[(size_t)(c0 + r) * bw1 + (r - c)] = Lk[r * 6 + c];
+      }
+      if (reload) {
+        const int r0 = c0 + kBandRing - 30;
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+          const int e = tl + q * NWORKH;
+          if (e < 30 * bw1) ring[((r0 + e / bw1) % kBandRing) * bw1 + e % bw1] = pre[q];
+        }
+      }
+    }
+    if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
+    o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
+  }
+  __syncthreads();
+  // ---- separator: S = T + B - A_ss (lower), rhs = y_top + y_bot - b_s, in ORIGINAL separator order ----
+  {
+    double* ring0 = sm; double* y0 = ring0 + ring_size;
+    double* ring1 = sm + (ring_size + ylen + beta * 6 + 8); double* y1 = ring1 + ring_size;
+    const int ne0 = m, ne1 = n - m - sw;
+    const int lds = sw + 1;
+    for (int e = t; e < sw * sw; e += 256) {
+      const int a = e / sw, b = e % sw;
+      if (b > a) continue;
+      double v = 0.0;
+      if (a - b <= beta) {
+        const int it = ne0 + a, kt = ne0 + b;                    // top: local = original
+        const double tv = ring0[(it % kBandRing) * bw1 + (kt - it + beta)];
+        const int ib = ne1 + (sw - 1 - b), kbm = ne1 + (sw - 1 - a);   // bottom (reversed): row >= col
+        const double bv = ring1[(ib % kBandRing) * bw1 + (kbm - ib + beta)];
+        v = tv + bv - Ab[(size_t)(m + a) * bw1 + (b - a + beta)];
+      }
+      sep[a * lds + b] = v;
+    }
+    for (int a = t; a < sw; a += 256) sep[sw * lds + a] = y0[ne0 + a] + y1[ne1 + (sw - 1 - a)] - rhs[m + a];
+    __syncthreads();
+    if (t < 32) {                             // dense Cholesky + solve of the sw x sw separator system by one warp
+      double* rs = sep + sw * lds;
+      for (int j = 0; j < sw; j++) {
+        const double d = sep[j * lds + j];
+        if (t == 0 && (!(d > 0.0) || !isfinite(d))) s_fail = 1;
+        const double iv = rsqrt(fmax(d, 1e-300));
+        __syncwarp();
+        for (int i = j + t; i < sw; i += 32) sep[i * lds + j] *= iv;   // includes the diagonal: d * iv = sqrt(d)
+        __syncwarp();
+        for (int e = t; e < (sw - j - 1) * (sw - j - 1); e += 32) {
+          const int i = j + 1 + e / (sw - j - 1), k = j + 1 + e % (sw - j - 1);
+          if (k <= i) sep[i * lds + k] = fma(-sep[i * lds + j], sep[k * lds + j], sep[i * lds + k]);
+        }
+        __syncwarp();
+      }
+      for (int i = 0; i < sw; i++) {          // forward
+        double sacc = 0.0;
+        for (int k = t; k < i; k += 32) sacc = fma(sep[i * lds + k], rs[k], sacc);
+        sacc = warp_sum(sacc);
+        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
+        __syncwarp();
+      }
+      for (int i = sw - 1; i >= 0; i--) {     // backward
+        double sacc = 0.0;
+        for (int k = i + 1 + t; k < sw; k += 32) sacc = fma(sep[k * lds + i], rs[k], sacc);
+        sacc = warp_sum(sacc);
+        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // the separator solution becomes known boundary values of both halves
+    for (int a = t; a < sw; a += 256) { const double x = sep[sw * lds + a]; y0[ne0 + a] = x; y1[ne1 + (sw - 1 - a)] = x; }
+    __syncthreads();
+  }
+  // ---- backward substitution of both halves, concurrently (local numbering); separator rows are known ----
+  constexpr int kChunk = 126;
+#ifdef UBA_LA2_ONEHALF
+  for (int i1 = (half == 0 ? H.nh : 0); i1 > 0; i1 -= kChunk) {
+#else
+  for (int i1 = H.nh; i1 > 0; i1 -= kChunk) {
+#endif
+    const int i0 = max(0, i1 - kChunk);
+    for (int e = tl; e < (i1 - i0) * bw1; e += NH) {
+      const int i = i0 + e / bw1, c = e % bw1;
+      ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
+    }
+    if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
+    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6) {
+      const double* blk = ring + (c0 - i0) * bw1;
+      const bool known = c0 >= H.ne;          // separator block: x already final
+      if (tl == 0) {
+        double xb[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
+        if (!known) {
+#pragma unroll
+          for (int c = 5; c >= 0; c--) {
+            xb[c] *= blk[c * bw1];
+#pragma unroll
+            for (int mm = 0; mm < 6; mm++) if (mm < c) xb[mm] = fma(-blk[c * bw1 + (c - mm)], xb[c], xb[mm]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_z[half][c] = xb[c]; }
+      }
+      if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
+      if (tl < beta) {
+        const int j = c0 - 1 - tl;
+        if (j >= 0 && j < H.ne) {             // only pending rows; separator rows are final
+          double v = y[j];
+#pragma unroll
+          for (int c = 0; c < 6; c++) { const int d = c0 + c - j; if (d <= beta) v = fma(-blk[c * bw1 + d], s_z[half][c], v); }
+          y[j] = v;
+        }
+      }
+      if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
+    }
+  }
+  __syncthreads();
+  const bool failed = s_fail != 0;
+  for (int i = tl; i < H.nh; i += NH) {
+    if (H.dir == 1 && i >= H.ne) continue;    // the separator is written once, by the top half
+    rhs[H.dir == 0 ? i : n - 1 - i] = failed ? 0.0 : y[i];
+  }
   if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
 
@@ -2261,6 +2587,20 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
       if (h_win_beta[w] > 0) {
         const int beta = h_win_beta[w];
         static const bool use_la = [] { const char* e = getenv("UBA_BAND_LA"); return !(e && e[0] == '0'); }();
+        // two-sided variant: correct (tests/test_gpu_parity.py runs it through UBA_BAND_LA2=1) but only ~7 % faster on
+        // c4 and slower on c5 on B200, so it is opt-in
+        static const bool use_la2 = [] { const char* e = getenv("UBA_BAND_LA2"); return e && e[0] == '1'; }();
+        if (use_la && use_la2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
+          const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
+          const size_t per_half = (size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)beta * 6 + 8;
+          const size_t smem = (2 * per_half + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
+          const int per = (beta * (beta + 1) / 2 + 95) / 96;
+#define UBA_LA2_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_la2<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_la2<PP>, 1, 256, smem, st, V, w, beta); }
+          if (per <= 5) UBA_LA2_LAUNCH(5) else UBA_LA2_LAUNCH(7)
+#undef UBA_LA2_LAUNCH
+          launches++;
+          continue;
+        }
         if (use_la && beta >= 11) {
           const size_t smem = ((size_t)kBandRing * (beta + 1) + n + beta + 8 + (size_t)beta * 6 + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
