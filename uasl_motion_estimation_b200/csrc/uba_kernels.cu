@@ -1695,43 +1695,76 @@ __global__ void __launch_bounds__(256) k_chol_banded_la(DevView V, int w, int be
 #ifdef UBA_BAND_TIMING
   if (t == 0 || t == 64 || t == 100 || t == 224) { for (int k = 0; k < 8; k++) V.Zbuf[(t == 0 ? 0 : t == 64 ? 8 : t == 100 ? 16 : 24) + k] = (double)tmx[k]; }
 #endif
-  // backward substitution L^T x = z, blocked; factor rows staged through shared memory in chunks
+  // backward substitution L^T x = z, blocked, with lookahead: warp 7 solves the 6x6 diagonal block and applies its
+  // update to the rows of the NEXT block itself; the other threads apply the update to the remaining band rows
+  // one block behind (one CTA barrier per block).  Factor rows are staged through shared memory in chunks.
   constexpr int kChunk = 126;
+  __shared__ double s_xb[2][6];
   for (int i1 = n; i1 > 0; i1 -= kChunk) {
     const int i0 = max(0, i1 - kChunk);
+    __syncthreads();
     for (int e = t; e < (i1 - i0) * bw1; e += nt) {
       const int i = i0 + e / bw1, c = e % bw1;
       ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
     }
     __syncthreads();
-    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6) {
+    int it = 0;
+    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6, it++) {
       const double* blk = ring + (c0 - i0) * bw1;   // row c0 + m at blk + m*bw1: [0] = 1/L, [d] = L[c0+m][c0+m-d]
-      if (t == 0) {
-        double xb[6];
+      const int par = it & 1;
+      if (panel) {
+        if (pl == 0) {
+          double xb[6];
 #pragma unroll
-        for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
+          for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
 #pragma unroll
-        for (int c = 5; c >= 0; c--) {
-          xb[c] *= blk[c * bw1];
+          for (int c = 5; c >= 0; c--) {
+            xb[c] *= blk[c * bw1];
 #pragma unroll
-          for (int m = 0; m < 6; m++) if (m < c) xb[m] = fma(-blk[c * bw1 + (c - m)], xb[c], xb[m]);
+            for (int m = 0; m < 6; m++) if (m < c) xb[m] = fma(-blk[c * bw1 + (c - m)], xb[c], xb[m]);
+          }
+#pragma unroll
+          for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_xb[par][c] = xb[c]; }
         }
+        __syncwarp();
+        if (pl < 6) {                               // rows of the next block (c0 - 6 + pl): inside the band since beta >= 11
+          const int j = c0 - 6 + pl;
+          if (j >= 0) {
+            double v = y[j];
 #pragma unroll
-        for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_z[c] = xb[c]; }
-      }
-      __syncthreads();
-      if (t < beta) {
-        const int j = c0 - 1 - t;
+            for (int c = 0; c < 6; c++) v = fma(-blk[c * bw1 + (c0 + c - j)], s_xb[par][c], v);
+            y[j] = v;
+          }
+        }
+        __syncwarp();
+      } else if (it > 0 && t < beta - 6) {
+        // workers, one block behind: rows [cp - beta, cp - 6) of the previous block cp = c0 + 6
+        const int cp = c0 + 6;
+        const double* blkp = blk + 6 * bw1;
+        const int j = cp - 7 - t;
         if (j >= 0) {
           double v = y[j];
 #pragma unroll
-          for (int c = 0; c < 6; c++) { const int d = c0 + c - j; if (d <= beta) v = fma(-blk[c * bw1 + d], s_z[c], v); }
+          for (int c = 0; c < 6; c++) { const int d = cp + c - j; if (d <= beta) v = fma(-blkp[c * bw1 + d], s_xb[par ^ 1][c], v); }
           y[j] = v;
         }
       }
       __syncthreads();
     }
+    // drain: the last block of the chunk still owes its update to the rows beyond the next block
+    if (!panel && t < beta - 6) {
+      const int cp = i0;
+      const double* blkp = ring;
+      const int j = cp - 7 - t;
+      if (j >= 0) {
+        double v = y[j];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { const int d = cp + c - j; if (d <= beta) v = fma(-blkp[c * bw1 + d], s_xb[(it - 1) & 1][c], v); }
+        y[j] = v;
+      }
+    }
   }
+  __syncthreads();
   const bool failed = s_fail != 0;
   for (int i = t; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
   if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
