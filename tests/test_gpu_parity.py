@@ -72,30 +72,41 @@ def test_reference_termination_rules(gpu_lib, oracle):
     assert rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
 
 
-@pytest.mark.parametrize("solver", [0, 1, 2])
-def test_large_window_solver_paths(gpu_lib, oracle, solver, monkeypatch):
-    """200 keyframes -> reduced system 1188 x 1188: banded Cholesky with lookahead (0), blocked dense Cholesky (1),
-    two-sided banded Cholesky (2, opt-in through UBA_BAND_LA2=1; the switch is read once per process, so this case
-    runs in a subprocess)."""
-    if solver == 2:
-        import subprocess, sys, textwrap
-        code = textwrap.dedent("""
-            import sys, numpy as np
-            sys.path.insert(0, %r); sys.path.insert(0, %r)
-            import oracle_binding as ob
-            from uasl_motion_estimation_b200 import capi, synth
-            win = synth.config_window("c4", scale=0.05)
+_SOLVER_ENVS = {
+    "cluster2": {},                                          # default: two-sided band Cholesky on a 2-CTA cluster
+    "lookahead": {"UBA_BAND_C2": "0"},                       # one CTA, panel-warp lookahead
+    "two_sided_1cta": {"UBA_BAND_C2": "0", "UBA_BAND_LA2": "1"},
+    "plain_block": {"UBA_BAND_C2": "0", "UBA_BAND_LA": "0"},
+}
+
+
+@pytest.mark.parametrize("variant", sorted(_SOLVER_ENVS))
+def test_large_window_band_solver_variants(variant):
+    """200 keyframes -> reduced system 1188 x 1188, half-bandwidth 29.  Every band-Cholesky variant must reproduce the
+    oracle trajectory.  The switches are read once per process, so each case runs in a subprocess."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import oracle_binding as ob
+        from uasl_motion_estimation_b200 import capi, synth
+        for scale, nfix in ((0.05, 2), (0.021, 1)):
+            win = synth.config_window("c4", scale=scale)
             cfg = capi.default_config(fixed_iterations=3)
             h = capi.Handle(cfg); h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
-            rc, _ = h.optimise(2); o = ob.optimise(win, cfg, 2)
+            rc, _ = h.optimise(nfix); o = ob.optimise(win, cfg, nfix)
             rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
-            assert rc == 0 and rel(h.cameras(), o["cams"]) < 1e-6 and rel(h.points(), o["pts"]) < 1e-6
-            print("OK")
-        """) % (str(ROOT), str(ROOT / "tests"))
-        import os
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, UBA_BAND_LA2="1"))
-        assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
-        return
+            assert [a["accepted"] for a in h.iterations(0)] == [b["accepted"] for b in o["iterations"]]
+            assert rc == 0 and rel(h.cameras(), o["cams"]) < 1e-6 and rel(h.points(), o["pts"]) < 1e-6, (scale, rel(h.cameras(), o["cams"]))
+        print("OK")
+    """) % (str(ROOT), str(ROOT / "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **_SOLVER_ENVS[variant]))
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+@pytest.mark.parametrize("solver", [0, 1])
+def test_large_window_solver_paths(gpu_lib, oracle, solver):
+    """Banded Cholesky (0, default) against the blocked dense Cholesky (1) on the same 1188 x 1188 system."""
     win, cfg, h = make(gpu_lib, "c4", 0.05, fixed_iterations=3, solver=solver)
     assert 6 * int((h.tables(2)["free_cam"] >= 0).sum()) > 160
     rc, sums = h.optimise(2)

@@ -14,6 +14,10 @@
 //   back substitution, candidate evaluation                -> k_backsub
 //   TrustRegionMinimizer accept / reject / radius          -> k_lm_update
 #include <cuda_runtime.h>
+#ifndef UBA_EMU
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#endif
 #include <stdint.h>
 
 #include <algorithm>
@@ -1727,21 +1731,28 @@ __global__ void __launch_bounds__(256) k_chol_banded_la(DevView V, int w, int be
           for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_xb[par][c] = xb[c]; }
         }
         __syncwarp();
-        if (pl < 6) {                               // rows of the next block (c0 - 6 + pl): inside the band since beta >= 11
+        if (pl < 6) {
+          // rows of the next block (c0 - 6 + pl): this block's update (inside the band since beta >= 11) and the
+          // previous block's (cp = c0 + 6), which the workers leave to this warp so that no row has two writers
           const int j = c0 - 6 + pl;
           if (j >= 0) {
-            double v = y[j];
+            double v = y[j], v2 = 0.0;
 #pragma unroll
             for (int c = 0; c < 6; c++) v = fma(-blk[c * bw1 + (c0 + c - j)], s_xb[par][c], v);
-            y[j] = v;
+            if (it > 0) {
+              const double* blkp = blk + 6 * bw1;
+#pragma unroll
+              for (int c = 0; c < 6; c++) { const int d = c0 + 6 + c - j; if (d <= beta) v2 = fma(blkp[c * bw1 + d], s_xb[par ^ 1][c], v2); }
+            }
+            y[j] = v - v2;
           }
         }
         __syncwarp();
-      } else if (it > 0 && t < beta - 6) {
-        // workers, one block behind: rows [cp - beta, cp - 6) of the previous block cp = c0 + 6
+      } else if (it > 0 && t < beta - 12) {
+        // workers, one block behind: rows [cp - beta, cp - 12) of the previous block cp = c0 + 6
         const int cp = c0 + 6;
         const double* blkp = blk + 6 * bw1;
-        const int j = cp - 7 - t;
+        const int j = cp - 13 - t;
         if (j >= 0) {
           double v = y[j];
 #pragma unroll
@@ -2095,6 +2106,349 @@ __global__ void __launch_bounds__(256) k_chol_banded_la2(DevView V, int w, int b
   }
   if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
+
+#ifndef UBA_EMU
+// Two-sided band Cholesky on a CLUSTER OF TWO CTAs (two SMs), beta in [11, 35]: CTA 0 eliminates block columns
+// [0, m) top-down, CTA 1 eliminates the rows below the separator bottom-up (top-down on the reversed matrix), each
+// with all 256 threads exactly like k_chol_banded_la (panel warp 7 + 224 workers).  After the forward loops CTA 0
+// reads CTA 1's separator corner and rhs through distributed shared memory, factors the sw x sw separator system with
+// one warp and writes the separator solution into both CTAs' y; both then back-substitute their half concurrently
+// (with lookahead).  Sequential depth: n/12 + sw/6 block steps on each SM instead of n/6 on one.
+template <int PER>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c2(DevView V, int w, int beta) {
+  extern __shared__ double sm[];
+  const WinState* st = &V.ws[w];
+  if (st->done) return;
+  constexpr int NH = 256, NWORKH = 224;
+  const int half = (int)(blockIdx.x & 1);
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const int bw1 = beta + 1;
+  const int sw = ((beta + 1 + 5) / 6) * 6;    // separator rows
+  const int m = (((n - sw) / 2) / 6) * 6;     // rows eliminated by the top half
+  const int ring_size = kBandRing * bw1;
+  const int t = threadIdx.x;
+  BandHalf H;
+  H.dir = half; H.ne = half == 0 ? m : n - m - sw; H.nh = H.ne + sw;
+  const int ylen = (n - m) + beta + 8;        // >= nh of either half + tail
+  double* ring = sm;
+  double* y = ring + ring_size;
+  double* Xbuf = y + ylen;
+  double* sep = Xbuf + beta * 6 + 8;          // [sw][sw + 1] + rhs [sw] (used by CTA 0)
+  __shared__ int s_fail;
+  __shared__ double s_Lkk[2][36], s_invk[2][6], s_z[6], s_xp[36], s_corner[21], s_xb[2][6];
+  double* rhs = V.rhs + (size_t)6 * f0;
+  double* A0 = V.A + V.w_red_off[w];
+  double* Lt = A0 + (size_t)half * n * bw1;   // this half's factor rows (local row numbering)
+  const double* Ab = A0 + (size_t)2 * n * bw1;
+  const bool panel = t >= NWORKH;
+  const int pl = t - NWORKH;
+  if (t == 0) s_fail = 0;
+  auto band_entry = [&](int i, int c) -> double {
+    if (i >= H.nh || i - beta + c < 0) return 0.0;
+    return H.dir == 0 ? Ab[(size_t)i * bw1 + c] : Ab[(size_t)(n - 1 - i + beta - c) * bw1 + c];
+  };
+  for (int i = t; i < ylen; i += NH) y[i] = i < H.nh ? rhs[H.dir == 0 ? i : n - 1 - i] : 0.0;
+  for (int e = t; e < kBandRing * bw1; e += NH) ring[e] = band_entry(e / bw1, e % bw1);
+  const int npairs = beta * (beta + 1) / 2;
+  int pti[PER], ptk[PER];
+#pragma unroll
+  for (int q = 0; q < PER; q++) {
+    const int e = t + q * NWORKH;
+    int ti = -1, tk = 0;
+    if (!panel && e < npairs) {
+      int d0 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while ((d0 + 1) * (d0 + 2) / 2 <= e) d0++;
+      while (d0 * (d0 + 1) / 2 > e) d0--;
+      ti = d0; tk = e - d0 * (d0 + 1) / 2;
+      if (ti < 6) ti = -1;                    // corner pair: owned by the panel warp
+    }
+    pti[q] = ti; ptk[q] = tk;
+  }
+  int cr = 0, ce = pl;                        // corner entry of panel lane pl: (cr, ce), ce <= cr
+  while (ce > cr) { ce -= cr + 1; cr++; }
+  const int nblk = H.ne / 6;
+  __syncthreads();
+  if (t == NWORKH) {                          // prologue: factor of block 0
+    double L[6][6], iv[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) L[r][c] = c <= r ? ring[r * bw1 + beta - r + c] : 0.0;
+    if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      s_invk[0][r] = iv[r];
+#pragma unroll
+      for (int c = 0; c < 6; c++) s_Lkk[0][r * 6 + c] = L[r][c];
+    }
+  }
+  __syncthreads();
+  int o0 = 0;
+  for (int kb = 0; kb < nblk; kb++) {
+    const int c0 = 6 * kb, par = kb & 1;
+    const double* Lk = s_Lkk[par];
+    const double* ivk = s_invk[par];
+    if (panel) {
+      // the block after the last eliminated one is the first separator block: it still needs its corner update
+      // (written back to the ring), it is just not factored here
+      const bool last = kb + 1 == nblk;
+      int on = o0 + 6 * bw1; if (on >= ring_size) on -= ring_size;
+      if (pl < 6) {
+        const double* row = ring + on + pl * bw1 + (beta - 6 - pl);
+        double x[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) x[c] = row[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) s_xp[pl * 6 + c] = x[c];
+      }
+      __syncwarp();
+      if (pl < 21) {
+        double v = ring[on + cr * bw1 + beta - cr + ce];
+#pragma unroll
+        for (int mm = 0; mm < 6; mm++) v = fma(-s_xp[cr * 6 + mm], s_xp[ce * 6 + mm], v);
+        if (last) ring[on + cr * bw1 + beta - cr + ce] = v;
+        s_corner[pl] = v;
+      }
+      __syncwarp();
+      if (pl == 0 && !last) {
+        double L[6][6], iv[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) L[r][c] = c <= r ? s_corner[r * (r + 1) / 2 + c] : 0.0;
+        if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          s_invk[par ^ 1][r] = iv[r];
+#pragma unroll
+          for (int c = 0; c < 6; c++) s_Lkk[par ^ 1][r * 6 + c] = L[r][c];
+        }
+      }
+    } else {
+      constexpr int kPre = (30 * 36 + NWORKH - 1) / NWORKH;   // beta <= 35
+      double pre[kPre];
+      const bool reload = kb > 0 && (kb % 5) == 0;
+      if (reload) {
+        const int r0 = c0 + kBandRing - 30;
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+          const int e = t + q * NWORKH;
+          pre[q] = e < 30 * bw1 ? band_entry(r0 + e / bw1, e % bw1) : 0.0;
+        }
+      }
+      if (t <= beta) {
+        const bool is_rhs = t == beta;
+        int orow = o0 + (6 + t) * bw1; if (orow >= ring_size) orow -= ring_size;
+        const double* row = ring + orow;
+        const int basec = beta - 6 - t;
+        double x[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((basec + c >= 0) ? row[basec + c] : 0.0);
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
+        }
+        if (is_rhs) {
+#pragma unroll
+          for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 6; c++) Xbuf[t * 6 + c] = x[c];
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NWORKH));
+#pragma unroll
+      for (int q = 0; q < PER; q++) {
+        const int ti = pti[q], tk = ptk[q];
+        if (ti >= 0) {
+          int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
+          const double* xi = Xbuf + ti * 6;
+          const double* xk = Xbuf + tk * 6;
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc = fma(xi[c], xk[c], acc);
+          ring[oi + (beta - ti + tk)] -= acc;
+        }
+      }
+      if (t >= 64 && t < 64 + beta) {
+        const int tt = t - 64, i = c0 + 6 + tt;
+        const int basec = beta - 6 - tt;
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          const double l = Xbuf[tt * 6 + c];
+          acc = fma(l, s_z[c], acc);
+          if (basec + c >= 0 && i < H.nh) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
+        }
+        y[i] -= acc;
+      } else if (t >= 160 && t < 166) {
+        const int r = t - 160;
+        Lt[(size_t)(c0 + r) * bw1] = ivk[r];
+        for (int c = 0; c < r; c++) Lt[(size_t)(c0 + r) * bw1 + (r - c)] = Lk[r * 6 + c];
+      }
+      if (reload) {
+        const int r0 = c0 + kBandRing - 30;
+#pragma unroll
+        for (int q = 0; q < kPre; q++) {
+          const int e = t + q * NWORKH;
+          if (e < 30 * bw1) ring[((r0 + e / bw1) % kBandRing) * bw1 + e % bw1] = pre[q];
+        }
+      }
+    }
+    __syncthreads();
+    o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
+  }
+  cg::cluster_group cluster = cg::this_cluster();
+  cluster.sync();
+  // ---- separator (CTA 0): S = T + B - A_ss (lower), rhs = y_top + y_bot - b_s, in ORIGINAL separator order ----
+  if (half == 0) {
+    const double* ring1 = cluster.map_shared_rank(ring, 1);
+    double* y1 = cluster.map_shared_rank(y, 1);
+    int* fail1 = cluster.map_shared_rank(&s_fail, 1);
+    const int ne0 = m, ne1 = n - m - sw;
+    const int lds = sw + 1;
+    for (int e = t; e < sw * sw; e += NH) {
+      const int a = e / sw, b = e % sw;
+      if (b > a) continue;
+      double v = 0.0;
+      if (a - b <= beta) {
+        const int it = ne0 + a, kt = ne0 + b;                    // top: local = original
+        const double tv = ring[(it % kBandRing) * bw1 + (kt - it + beta)];
+        const int ib = ne1 + (sw - 1 - b), kbm = ne1 + (sw - 1 - a);   // bottom (reversed): row >= col
+        const double bv = ring1[(ib % kBandRing) * bw1 + (kbm - ib + beta)];
+        v = tv + bv - Ab[(size_t)(m + a) * bw1 + (b - a + beta)];
+      }
+      sep[a * lds + b] = v;
+    }
+    for (int a = t; a < sw; a += NH) sep[sw * lds + a] = y[ne0 + a] + y1[ne1 + (sw - 1 - a)] - rhs[m + a];
+    __syncthreads();
+    if (t < 32) {                             // dense Cholesky + solve of the sw x sw separator system by one warp
+      double* rs = sep + sw * lds;
+      for (int j = 0; j < sw; j++) {
+        const double d = sep[j * lds + j];
+        if (t == 0 && (!(d > 0.0) || !isfinite(d))) s_fail = 1;
+        const double iv = rsqrt(fmax(d, 1e-300));
+        __syncwarp();
+        for (int i = j + t; i < sw; i += 32) sep[i * lds + j] *= iv;   // includes the diagonal: d * iv = sqrt(d)
+        __syncwarp();
+        for (int e = t; e < (sw - j - 1) * (sw - j - 1); e += 32) {
+          const int i = j + 1 + e / (sw - j - 1), k = j + 1 + e % (sw - j - 1);
+          if (k <= i) sep[i * lds + k] = fma(-sep[i * lds + j], sep[k * lds + j], sep[i * lds + k]);
+        }
+        __syncwarp();
+      }
+      for (int i = 0; i < sw; i++) {          // forward
+        double sacc = 0.0;
+        for (int k = t; k < i; k += 32) sacc = fma(sep[i * lds + k], rs[k], sacc);
+        sacc = warp_sum(sacc);
+        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
+        __syncwarp();
+      }
+      for (int i = sw - 1; i >= 0; i--) {     // backward
+        double sacc = 0.0;
+        for (int k = i + 1 + t; k < sw; k += 32) sacc = fma(sep[k * lds + i], rs[k], sacc);
+        sacc = warp_sum(sacc);
+        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // the separator solution becomes known boundary values of both halves
+    for (int a = t; a < sw; a += NH) { const double x = sep[sw * lds + a]; y[ne0 + a] = x; y1[ne1 + (sw - 1 - a)] = x; }
+    if (t == 0) { const int f = s_fail | *fail1; s_fail = f; *fail1 = f; }
+  }
+  cluster.sync();
+  // ---- backward substitution of this half (local numbering) with lookahead; separator rows are known ----
+  constexpr int kChunk = 126;
+  for (int i1 = H.nh; i1 > 0; i1 -= kChunk) {
+    const int i0 = max(0, i1 - kChunk);
+    __syncthreads();
+    for (int e = t; e < (i1 - i0) * bw1; e += NH) {
+      const int i = i0 + e / bw1, c = e % bw1;
+      ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
+    }
+    __syncthreads();
+    int it = 0;
+    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6, it++) {
+      const double* blk = ring + (c0 - i0) * bw1;
+      const int par = it & 1;
+      if (panel) {
+        if (pl == 0) {
+          double xb[6];
+#pragma unroll
+          for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
+          if (c0 < H.ne) {                          // separator blocks: x already final
+#pragma unroll
+            for (int c = 5; c >= 0; c--) {
+              xb[c] *= blk[c * bw1];
+#pragma unroll
+              for (int mm = 0; mm < 6; mm++) if (mm < c) xb[mm] = fma(-blk[c * bw1 + (c - mm)], xb[c], xb[mm]);
+            }
+#pragma unroll
+            for (int c = 0; c < 6; c++) y[c0 + c] = xb[c];
+          }
+#pragma unroll
+          for (int c = 0; c < 6; c++) s_xb[par][c] = xb[c];
+        }
+        __syncwarp();
+        if (pl < 6) {                               // next block's rows: this block's and the previous block's update
+          const int j = c0 - 6 + pl;
+          if (j >= 0 && j < H.ne) {
+            double v = y[j], v2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) v = fma(-blk[c * bw1 + (c0 + c - j)], s_xb[par][c], v);
+            if (it > 0) {
+              const double* blkp = blk + 6 * bw1;
+#pragma unroll
+              for (int c = 0; c < 6; c++) { const int d = c0 + 6 + c - j; if (d <= beta) v2 = fma(blkp[c * bw1 + d], s_xb[par ^ 1][c], v2); }
+            }
+            y[j] = v - v2;
+          }
+        }
+        __syncwarp();
+      } else if (it > 0 && t < beta - 12) {         // workers, one block behind: rows [cp - beta, cp - 12)
+        const int cp = c0 + 6;
+        const double* blkp = blk + 6 * bw1;
+        const int j = cp - 13 - t;
+        if (j >= 0 && j < H.ne) {
+          double v = y[j];
+#pragma unroll
+          for (int c = 0; c < 6; c++) { const int d = cp + c - j; if (d <= beta) v = fma(-blkp[c * bw1 + d], s_xb[par ^ 1][c], v); }
+          y[j] = v;
+        }
+      }
+      __syncthreads();
+    }
+    if (!panel && t < beta - 6) {                   // drain: the chunk's last block still owes the rows beyond the next block
+      const int cp = i0;
+      const double* blkp = ring;
+      const int j = cp - 7 - t;
+      if (j >= 0 && j < H.ne) {
+        double v = y[j];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { const int d = cp + c - j; if (d <= beta) v = fma(-blkp[c * bw1 + d], s_xb[(it - 1) & 1][c], v); }
+        y[j] = v;
+      }
+    }
+  }
+  __syncthreads();
+  const bool failed = s_fail != 0;
+  for (int i = t; i < H.nh; i += NH) {
+    if (H.dir == 1 && i >= H.ne) continue;    // the separator is written once, by the top half
+    rhs[H.dir == 0 ? i : n - 1 - i] = failed ? 0.0 : y[i];
+  }
+  if (t == 0 && half == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
+}
+#endif  // UBA_EMU
 
 // blocked forward + backward substitution with the factor in global memory; one CTA
 __global__ void __launch_bounds__(1024) k_trsv_large(DevView V, int w) {
@@ -2634,6 +2988,20 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
           launches++;
           continue;
         }
+#ifndef UBA_EMU
+        // default for long bands: the two halves of the band on a cluster of two CTAs
+        static const bool use_c2 = [] { const char* e = getenv("UBA_BAND_C2"); return !(e && e[0] == '0'); }();
+        if (use_la && use_c2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
+          const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
+          const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)beta * 6 + 8 + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
+          const int per = (beta * (beta + 1) / 2 + 223) / 224;
+#define UBA_C2_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_c2<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_c2<PP>, 2, 256, smem, st, V, w, beta); }
+          if (per <= 2) UBA_C2_LAUNCH(2) else UBA_C2_LAUNCH(3)
+#undef UBA_C2_LAUNCH
+          launches++;
+          continue;
+        }
+#endif
         if (use_la && beta >= 11) {
           const size_t smem = ((size_t)kBandRing * (beta + 1) + n + beta + 8 + (size_t)beta * 6 + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
