@@ -8,6 +8,7 @@
 // Everything numerical runs in the kernels of uba_kernels.cu; this file only builds
 // index tables, moves buffers and sequences launches.  No CPU fallback.
 #include <cuda_runtime.h>
+#include <omp.h>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -105,7 +106,7 @@ struct uba_handle {
   std::vector<int32_t> obs_order;                  // canonical table (global caller obs id per point-major slot)
   std::vector<int64_t> pt_obs_off_caller;          // [NP+1] canonical CSR (caller point order)
   std::vector<int32_t> pt_order;                   // [NP] caller point id (global) per internal slot
-  std::vector<int32_t> obs_internal;               // [NO] caller obs id per internal obs slot
+  PinBuf<int32_t> h_obs_internal;                  // [NO] caller obs id per internal obs slot (pinned: uploaded for the device-side gather)
   std::vector<int32_t> pt_obs_off_int;             // [NP+1]
   std::vector<char> cam_seen;                      // [NC]
   std::vector<int32_t> pt_lo, pt_hi;               // [NP] lowest / highest camera of each internal point slot (-1: none)
@@ -114,6 +115,7 @@ struct uba_handle {
   // prepared for a given fixed_frames
   int prepared_fixed = -1;
   std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n, win_beta;
+  std::vector<char> win_infeasible;           // a window whose start violates the point bounds
   DevBuf<int32_t> d_w_beta;
   std::vector<int64_t> w_red_off_h;
   int max_n = 0;
@@ -132,7 +134,7 @@ struct uba_handle {
   PinBuf<int32_t> h_obs_cam;
   // device
   DevBuf<double> d_cams, d_camR, d_cam_s2, d_cam_lam, d_cam_y, d_pts, d_pt_s2, d_pt_rec, d_feat, d_acc, d_A, d_rhs, d_Zbuf, d_dbg, d_export, d_flush;
-  DevBuf<int32_t> d_w_cam_off, d_w_pt_off, d_w_free_off, d_free_list, d_free_cam, d_cam_win, d_pt_obs_off, d_pt_win, d_obs_cam, d_n_active, d_pt_order;
+  DevBuf<int32_t> d_w_cam_off, d_w_pt_off, d_w_free_off, d_free_list, d_free_cam, d_cam_win, d_pt_obs_off, d_pt_win, d_obs_cam, d_obs_src, d_n_active, d_pt_order;
   DevBuf<int64_t> d_w_red_off;
   DevBuf<double> d_cov;
   std::vector<double> cov_h;   // [NC][36], filled when cfg.compute_covariance
@@ -152,6 +154,7 @@ struct uba_handle {
   cudaGraphExec_t graph_exec = nullptr;
 #endif
   int64_t graph_kernels = 0;
+  std::vector<char> graph_sig;                // what the captured graph bakes in (see prepare)
   // timing
   bool profiling = false;
   uba_timing timing{};
@@ -188,14 +191,14 @@ uba::Calib make_calib(const uba_calib& in, int M, bool use_bounds) {
 void drop_graph(uba_handle* h) {
 #ifndef UBA_EMU
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  h->graph_sig.clear();
 #else
   (void)h;
 #endif
 }
 
 void fill_view_static(uba_handle* h) {
-  drop_graph(h);
-  DevView& V = h->V;
+  DevView& V = h->V;                          // (a captured graph is re-validated against the view in prepare())
   V.M = h->M; V.nW = h->nW; V.NC = h->NC; V.NP = h->NP; V.NO = h->NO;
   V.w_cam_off = h->d_w_cam_off.p; V.w_pt_off = h->d_w_pt_off.p;
   V.cams[0] = h->d_cams.p; V.cams[1] = h->d_cams.p + (size_t)h->NC * 6;
@@ -219,6 +222,9 @@ void fill_view_static(uba_handle* h) {
 
 int allreduce(uba_handle* h, double* buf, size_t count, int op);
 
+// UBA_TRACE=1: host-side phase times on stderr
+#define TT(label) if (getenv("UBA_TRACE")) { auto now_ = std::chrono::steady_clock::now(); fprintf(stderr, "  [trace] %-28s %.2f ms\n", label, std::chrono::duration<double, std::milli>(now_ - tt_).count()); tt_ = now_; }
+
 // Plan of the tiled lineariser: walk the internal point order (sorted by lowest / highest camera)
 // and cut it into items whose points share one short ascending camera list; points that do not fit
 // (too long a track, a camera seen twice) go to the generic lineariser.
@@ -227,7 +233,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   h->parts_h.clear(); h->tile_cams_h.clear(); h->gen_pts_h.clear();
   h->pt_mask_h.assign(h->NP, 0u);
   size_t tile_points = 0;
-  struct Item { int w, begin, end, cam_off, nl, nfx; };
+  struct Item { int w, begin, end, cam_off, nl, nfx, ulo; bool range; };
   std::vector<Item> items;
   std::vector<int> uni, merged, cams_p;
   for (int w = 0; w < h->nW; w++) {
@@ -235,27 +241,13 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     int item_begin = -1, min_len = 0;
     bool uni_range = true;   // the union is the camera range [ulo, uhi] (true as long as only contiguous tracks were merged)
     int ulo = 0, uhi = -1;
+    int run_lo = -1, run_hi = -1;   // (lo, hi) of the previous point when it was a contiguous tile point, else -1
     uni.clear();
     auto close_item = [&](int end) {
       if (item_begin < 0) return;
       if (uni_range) { uni.clear(); for (int c = ulo; c <= uhi; c++) uni.push_back(c); }
-      Item it{w, item_begin, end, (int)h->tile_cams_h.size(), (int)uni.size(), 0};
+      Item it{w, item_begin, end, (int)h->tile_cams_h.size(), (int)uni.size(), 0, ulo, uni_range};
       for (int c : uni) { h->tile_cams_h.push_back(c); if (c < fixed_frames) it.nfx++; }
-      for (int s = item_begin; s < end; s++) {
-        if (h->pt_mask_h[s] != 1u) { h->pt_mask_h[s] = 0u; continue; }  // 1u marks a tile point until here
-        unsigned m = 0;
-        if (uni_range) {
-          const int k = h->pt_hi[s] - h->pt_lo[s] + 1;
-          m = (k >= 32 ? 0xffffffffu : ((1u << k) - 1u)) << (unsigned)(h->pt_lo[s] - ulo);
-        } else {
-          for (int o = h->pt_obs_off_int[s]; o < h->pt_obs_off_int[s + 1]; o++) {
-            const int c = h->h_obs_cam.p[o] & 0x3fffffff;
-            m |= 1u << (unsigned)(std::lower_bound(uni.begin(), uni.end(), c) - uni.begin());
-          }
-        }
-        h->pt_mask_h[s] = m;
-        tile_points++;
-      }
       items.push_back(it);
       item_begin = -1;
     };
@@ -264,6 +256,9 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       if (k == 0) continue;
       const int lo = h->pt_lo[s], hi = h->pt_hi[s];
       if (h->pt_contig[s]) {
+        // the same contiguous track as the previous tile point changes nothing in the item: same decision
+        if (lo == run_lo && hi == run_hi) { h->pt_mask_h[s] = 1u; tile_points++; continue; }
+        run_lo = run_hi = -1;
         const int nfree = hi - std::max(lo, fixed_frames) + 1;
         if (k > kTileMaxLocal || nfree > kTileMaxFree) { h->gen_pts_h.push_back(s); continue; }
         bool ok = item_begin >= 0 && uni_range;
@@ -277,9 +272,11 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
         }
         if (!ok) { close_item(s); uni_range = true; ulo = lo; uhi = hi; min_len = k; item_begin = s; }
         else { ulo = nlo; uhi = nhi; min_len = std::min(min_len, k); }
-        h->pt_mask_h[s] = 1u;
+        h->pt_mask_h[s] = 1u; tile_points++;   // 1u marks a tile point until the mask pass below
+        run_lo = lo; run_hi = hi;
         continue;
       }
+      run_lo = run_hi = -1;
       // general track: explicit camera list
       cams_p.clear();
       bool ascending = true;
@@ -303,9 +300,30 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       if (!ok) { close_item(s); uni = cams_p; min_len = k; item_begin = s; }
       else { uni.swap(merged); min_len = std::min(min_len, k); }
       uni_range = false;
-      h->pt_mask_h[s] = 1u;
+      h->pt_mask_h[s] = 1u; tile_points++;
     }
     close_item(s1);
+  }
+  // slot masks of the tile points (bit i = the point sees the item's i-th camera), items in parallel
+  const int n_items = (int)items.size();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int ii = 0; ii < n_items; ii++) {
+    const Item& it = items[ii];
+    const int* cl = h->tile_cams_h.data() + it.cam_off;
+    for (int s = it.begin; s < it.end; s++) {
+      if (h->pt_mask_h[s] != 1u) continue;     // generic or unobserved point inside the item's range
+      unsigned m = 0;
+      if (it.range) {
+        const int k = h->pt_hi[s] - h->pt_lo[s] + 1;
+        m = (k >= 32 ? 0xffffffffu : ((1u << k) - 1u)) << (unsigned)(h->pt_lo[s] - it.ulo);
+      } else {
+        for (int o = h->pt_obs_off_int[s]; o < h->pt_obs_off_int[s + 1]; o++) {
+          const int c = h->h_obs_cam.p[o] & 0x3fffffff;
+          m |= 1u << (unsigned)(std::lower_bound(cl, cl + it.nl, c) - cl);
+        }
+      }
+      h->pt_mask_h[s] = m;
+    }
   }
   // CTA size: 128 threads (two CTAs per SM) when every item's camera-pair blocks fit, else 256
   int nt = 128;
@@ -346,7 +364,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
 int prepare(uba_handle* h, int fixed_frames) {
   if (fixed_frames < 0) fixed_frames = 0;
   if (h->prepared_fixed == fixed_frames) return UBA_OK;
-  drop_graph(h);
+  auto tt_ = std::chrono::steady_clock::now();
   const int nW = h->nW, NC = h->NC;
   if (h->comm) {
     // point-sharded: a camera is in the problem if ANY rank observes it -> max over ranks
@@ -391,6 +409,7 @@ int prepare(uba_handle* h, int fixed_frames) {
       const int f = h->free_cam_h[h->w_cam_off[w] + c];
       next_free[c] = f >= 0 ? f : next_free[c + 1];
     }
+#pragma omp parallel for schedule(static) reduction(max : bw) if (nW < 8)
     for (int s2 = h->w_pt_off[w]; s2 < h->w_pt_off[w + 1]; s2++) {
       if (h->pt_hi[s2] < 0) continue;
       const int fhi = h->free_cam_h[h->w_cam_off[w] + h->pt_hi[s2]];  // the highest camera of a track is observed, hence free unless fixed
@@ -438,6 +457,7 @@ int prepare(uba_handle* h, int fixed_frames) {
   CU(h, h->d_acc.reserve(h->acc_total));
   CU(h, h->d_A.reserve(red));
   CU(h, h->d_rhs.reserve(6 * nfree));
+  TT("prepare: free cams, band")
   // lineariser choice: 1 = generic only; otherwise the tiled kernel plus the generic one for leftovers
   h->use_tile = h->cfg.linearizer != 1;
 #ifdef UBA_EMU
@@ -445,6 +465,7 @@ int prepare(uba_handle* h, int fixed_frames) {
 #endif
   if (h->use_tile) {
     build_tile_plan(h, fixed_frames);
+    TT("prepare: tile plan")
     CU(h, h->d_parts.reserve(h->parts_h.size())); CU(h, h->d_tile_cams.reserve(h->tile_cams_h.size()));
     CU(h, h->d_pt_mask.reserve(std::max(h->NP, 1))); CU(h, h->d_gen_pts.reserve(h->gen_pts_h.size()));
     if (!h->parts_h.empty()) CU(h, cudaMemcpyAsync(h->d_parts.p, h->parts_h.data(), sizeof(TilePart) * h->parts_h.size(), cudaMemcpyHostToDevice, h->stream));
@@ -453,6 +474,7 @@ int prepare(uba_handle* h, int fixed_frames) {
     if (!h->gen_pts_h.empty()) CU(h, cudaMemcpyAsync(h->d_gen_pts.p, h->gen_pts_h.data(), sizeof(int32_t) * h->gen_pts_h.size(), cudaMemcpyHostToDevice, h->stream));
   }
   CU(h, cudaStreamSynchronize(h->stream));
+  TT("prepare: h2d + sync")
   DevView& V = h->V;
   V.tile_threads = h->tile_threads;
   V.parts = h->d_parts.p; V.n_parts = h->use_tile ? (int)h->parts_h.size() : 0; V.tile_cams = h->d_tile_cams.p; V.pt_mask = h->d_pt_mask.p;
@@ -463,6 +485,17 @@ int prepare(uba_handle* h, int fixed_frames) {
   V.w_lin = h->d_acc.p + h->off_wlin; V.w_post = h->d_acc.p + h->off_wpost; V.w_max = h->d_acc.p + h->off_wmax;
   V.w_loc = h->d_acc.p + h->off_wloc;
   V.A = h->d_A.p; V.rhs = h->d_rhs.p;
+  // The captured iteration graph stays valid when nothing it bakes in has changed: the device view (pointers and
+  // sizes, passed to every kernel by value) and the host-side launch geometry.  A sliding window re-submitted with
+  // the same shape (the per-frame case) then skips capture + instantiation.
+  {
+    std::vector<char> sig;
+    auto put = [&](const void* ptr, size_t n) { const char* c = (const char*)ptr; sig.insert(sig.end(), c, c + n); };
+    put(&V, sizeof(DevView)); put(h->variant_off, sizeof(h->variant_off)); put(&h->max_n, sizeof(h->max_n));
+    put(&h->acc_total, sizeof(h->acc_total)); put(&h->use_tile, sizeof(h->use_tile)); put(&h->use_tile2, sizeof(h->use_tile2));
+    if (nW) { put(h->win_n.data(), sizeof(int) * nW); put(h->win_beta.data(), sizeof(int) * nW); }
+    if (sig != h->graph_sig) { drop_graph(h); h->graph_sig.swap(sig); }
+  }
   h->prepared_fixed = fixed_frames;
   return UBA_OK;
 }
@@ -560,6 +593,7 @@ int run_iteration_fast(uba_handle* h) {
     if (!h->graph_exec) {
       cudaGraph_t g = nullptr;
       const int64_t before = h->timing.kernel_launches, lin_before = h->timing.linearize_launches;
+      if (getenv("UBA_TRACE")) fprintf(stderr, "  [trace] capturing the iteration graph\n");
       CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       const int rc = run_iteration(h);
       const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
@@ -595,7 +629,6 @@ int upload_state(uba_handle* h) {
   return UBA_OK;
 }
 
-#define TT(label) if (getenv("UBA_TRACE")) { auto now_ = std::chrono::steady_clock::now(); fprintf(stderr, "  [trace] %-28s %.2f ms\n", label, std::chrono::duration<double, std::milli>(now_ - tt_).count()); tt_ = now_; }
 int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t* wp, const int64_t* wo, const double* cams6,
                   const double* pts3, const double* feats, const int32_t* cam_idx, const int32_t* pt_idx, const int32_t* cam_id,
                   const uba_calib* calib) {
@@ -614,14 +647,17 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   h->state = 0; h->prepared_fixed = -1;
   h->M = M; h->nW = nW; h->NC = NC; h->NP = NP; h->NO = NO; h->calib_in = *calib;
   h->w_cam_off.assign(wc, wc + nW + 1); h->w_pt_off.assign(wp, wp + nW + 1); h->w_obs_off.assign(wo, wo + nW + 1);
-  h->obs_order.assign(NO, 0); h->pt_obs_off_caller.assign((size_t)NP + 1, 0); h->pt_order.assign(NP, 0);
-  h->obs_internal.assign(NO, 0); h->pt_obs_off_int.assign((size_t)NP + 1, 0);
-  h->cam_seen.assign(NC, 0); h->cam_win_h.assign(NC, 0); h->pt_win_h.assign(NP, 0);
+  // fully overwritten below: resize only (no zero fill of ~10 MB per call)
+  h->obs_order.resize(NO); h->pt_obs_off_caller.resize((size_t)NP + 1); h->pt_order.resize(NP);
+  h->pt_obs_off_int.resize((size_t)NP + 1);
+  h->pt_obs_off_caller[0] = 0; h->pt_obs_off_int[0] = 0;
+  h->cam_seen.assign(NC, 0); h->cam_win_h.resize(NC); h->pt_win_h.resize(NP);
   TT("alloc tables")
   // validate + count (parallel inside a window when there are few windows)
   int bad = 0;
   const bool few = nW < 8;
   std::vector<int32_t> cnt((size_t)NP, 0);
+  std::vector<char> win_canonical(nW, 0);
   for (int w = 0; w < nW; w++) {
     const int nc = wc[w + 1] - wc[w], np = wp[w + 1] - wp[w];
     if (nc < 0 || np < 0 || wo[w + 1] < wo[w]) bad++;
@@ -633,20 +669,28 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     int32_t* c = cnt.data() + wp[w];
     char* seen = h->cam_seen.data() + wc[w];
     const int64_t o0 = wo[w], o1 = wo[w + 1];
-    int badw = 0, unsorted = 0;
-#pragma omp parallel for schedule(static) reduction(+ : badw, unsorted) if (parallel)
+    int badw = 0, unsorted = 0, unsorted_cam = 0;
+#pragma omp parallel for schedule(static) reduction(+ : badw, unsorted, unsorted_cam) if (parallel)
     for (int64_t o = o0; o < o1; o++) {
       const int ci = cam_idx[o], pi = pt_idx[o];
       if (ci < 0 || ci >= nc || pi < 0 || pi >= np) { badw++; continue; }
-      seen[ci] = 1;
-      if (o > o0 && pi < pt_idx[o - 1]) unsorted++;
+      if (!seen[ci]) seen[ci] = 1;            // test first: 16 threads storing to the same few cache lines is a 10x slowdown
+      if (o > o0) {
+        if (pi < pt_idx[o - 1]) unsorted++;
+        else if (pi == pt_idx[o - 1] && ci < cam_idx[o - 1]) unsorted_cam++;
+      }
     }
     if (badw) return badw;
+    win_canonical[w] = !unsorted && !unsorted_cam;   // already point-major and camera-ascending inside a point
     if (!unsorted) {
       // point-major input (the reference's order): counts are run lengths, no atomics needed
       std::vector<int64_t> first((size_t)np + 1, -1);
+      const bool ident = win_canonical[w] != 0;
 #pragma omp parallel for schedule(static) if (parallel)
-      for (int64_t o = o0; o < o1; o++) if (o == o0 || pt_idx[o] != pt_idx[o - 1]) first[pt_idx[o]] = o;
+      for (int64_t o = o0; o < o1; o++) {
+        if (o == o0 || pt_idx[o] != pt_idx[o - 1]) first[pt_idx[o]] = o;
+        if (ident) h->obs_order[o] = (int32_t)o;
+      }
       first[np] = o1;
       for (int j = np - 1; j >= 0; j--) if (first[j] < 0) first[j] = first[j + 1];
       for (int j = 0; j < np; j++) c[j] = (int32_t)(first[j + 1] - first[j]);
@@ -665,24 +709,22 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     for (int w = 0; w < nW; w++) bad += count_window(w, false);
   }
   if (bad) return fail(h, UBA_ERR_INVALID_ARGUMENT, "camIdx / ptIdx out of range (%d offences)", bad);
+  TT("validate+count: passes")
   for (int j = 0; j < NP; j++) h->pt_obs_off_caller[j + 1] = h->pt_obs_off_caller[j] + cnt[j];
   TT("validate+count")
   // Canonical order: point-major (stable), camera-ascending inside a point.  The reference's own
   // initialiseObservations already produces it (BundleAdjuster.h:364-374): detect that and skip the sort.
   std::vector<int32_t> lo_c((size_t)NP, INT_MAX), hi_c((size_t)NP, -1);   // caller point order
   std::vector<char> contig_c((size_t)NP, 1);
+  int pt_permuted = 0;                        // windows whose internal point order differs from the caller's
+  int obs_permuted = 0;                       // windows whose observations had to be reordered
   auto order_window = [&](int w, bool parallel) {
     const int p0 = wp[w], np = wp[w + 1] - wp[w];
     const int64_t o0 = wo[w], o1 = wo[w + 1];
-    int unsorted = 0;
-#pragma omp parallel for schedule(static) reduction(+ : unsorted) if (parallel)
-    for (int64_t o = o0 + 1; o < o1; o++) {
-      if (pt_idx[o] < pt_idx[o - 1] || (pt_idx[o] == pt_idx[o - 1] && cam_idx[o] < cam_idx[o - 1])) unsorted++;
-    }
-    if (!unsorted) {
-#pragma omp parallel for schedule(static) if (parallel)
-      for (int64_t o = o0; o < o1; o++) h->obs_order[o] = (int32_t)o;
-    } else {
+    const int unsorted = win_canonical[w] ? 0 : 1;   // canonical windows got the identity order while counting
+    if (unsorted) {
+#pragma omp atomic
+      obs_permuted++;
       std::vector<int64_t> fill(np);
       for (int j = 0; j < np; j++) fill[j] = h->pt_obs_off_caller[p0 + j];
       for (int64_t o = o0; o < o1; o++) h->obs_order[fill[pt_idx[o]]++] = (int32_t)o;
@@ -709,12 +751,41 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     // internal point order: stable by (lowest camera, highest camera), unobserved points last
     const int nc = wc[w + 1] - wc[w];
     const int64_t nkeys = (int64_t)nc * nc + 1;
-    if (nkeys <= 8 * (int64_t)np + 1024) {
-      std::vector<int32_t> start((size_t)nkeys + 1, 0);
-      auto key = [&](int j) -> int64_t { return hi_c[p0 + j] < 0 ? nkeys - 1 : (int64_t)lo_c[p0 + j] * nc + hi_c[p0 + j]; };
-      for (int j = 0; j < np; j++) start[key(j) + 1]++;
-      for (int64_t k2 = 0; k2 < nkeys; k2++) start[k2 + 1] += start[k2];
-      for (int j = 0; j < np; j++) h->pt_order[p0 + start[key(j)]++] = p0 + j;
+    auto key_of = [&](int j) -> int64_t { return hi_c[p0 + j] < 0 ? nkeys - 1 : (int64_t)lo_c[p0 + j] * nc + hi_c[p0 + j]; };
+    int key_unsorted = 0;
+#pragma omp parallel for schedule(static) reduction(+ : key_unsorted) if (parallel)
+    for (int j = 1; j < np; j++) if (key_of(j) < key_of(j - 1)) key_unsorted++;
+    if (!key_unsorted) {
+      // tracks already arrive grouped by (first, last) keyframe: the internal order is the caller's
+#pragma omp parallel for schedule(static) if (parallel)
+      for (int j = 0; j < np; j++) { h->pt_order[p0 + j] = p0 + j; h->pt_win_h[p0 + j] = w; }
+    } else if (nkeys <= 8 * (int64_t)np + 1024) {
+      // stable counting sort, parallel over contiguous chunks of points.  Keys are compressed to
+      // lo * span + (hi - lo) so that the per-thread histograms stay small when tracks are short.
+      int span = 1;
+#pragma omp parallel for schedule(static) reduction(max : span) if (parallel)
+      for (int j = 0; j < np; j++) if (hi_c[p0 + j] >= 0) span = std::max(span, hi_c[p0 + j] - lo_c[p0 + j] + 1);
+      const int64_t nk = (int64_t)nc * span + 1;   // last key: unobserved points
+      auto ckey = [&](int j) -> int64_t { return hi_c[p0 + j] < 0 ? nk - 1 : (int64_t)lo_c[p0 + j] * span + (hi_c[p0 + j] - lo_c[p0 + j]); };
+      std::vector<int32_t> hist;
+      int T = 1;
+#pragma omp parallel if (parallel)
+      {
+#pragma omp single
+        { T = omp_get_num_threads(); hist.assign((size_t)T * nk, 0); }
+        const int t = omp_get_thread_num();
+        const int b = (int)((int64_t)np * t / T), e = (int)((int64_t)np * (t + 1) / T);
+        int32_t* mine = hist.data() + (size_t)t * nk;
+        for (int j = b; j < e; j++) mine[ckey(j)]++;
+#pragma omp barrier
+#pragma omp single
+        {
+          int32_t run = 0;
+          for (int64_t k2 = 0; k2 < nk; k2++)
+            for (int q = 0; q < T; q++) { const int32_t c2 = hist[(size_t)q * nk + k2]; hist[(size_t)q * nk + k2] = run; run += c2; }
+        }
+        for (int j = b; j < e; j++) h->pt_order[p0 + mine[ckey(j)]++] = p0 + j;
+      }
     } else {
       std::vector<int32_t> ids(np);
       std::iota(ids.begin(), ids.end(), 0);
@@ -725,7 +796,11 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       });
       for (int j = 0; j < np; j++) h->pt_order[p0 + j] = p0 + ids[j];
     }
-    for (int j = 0; j < np; j++) h->pt_win_h[p0 + j] = w;
+    if (key_unsorted) {
+      for (int j = 0; j < np; j++) h->pt_win_h[p0 + j] = w;
+#pragma omp atomic
+      pt_permuted++;
+    }
   };
   if (few) { for (int w = 0; w < nW; w++) order_window(w, true); }
   else {
@@ -734,29 +809,83 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   }
   TT("order+sort")
   // internal CSR + observation slots (window ranges coincide with the caller's)
-  h->pt_lo.assign(NP, -1); h->pt_hi.assign(NP, -1); h->pt_contig.assign(NP, 1);
-  for (int s = 0; s < NP; s++) {
-    const int j = h->pt_order[s];
-    h->pt_obs_off_int[s + 1] = h->pt_obs_off_int[s] + (int32_t)(h->pt_obs_off_caller[j + 1] - h->pt_obs_off_caller[j]);
-    h->pt_lo[s] = hi_c[j] < 0 ? -1 : lo_c[j]; h->pt_hi[s] = hi_c[j]; h->pt_contig[s] = contig_c[j];
+  h->pt_lo.resize(NP); h->pt_hi.resize(NP); h->pt_contig.resize(NP);
+  {
+    // prefix sum of the permuted track lengths, in parallel (per-thread partial sums, then a second sweep)
+    const int nth = std::max(1, omp_get_max_threads());
+    std::vector<int64_t> part((size_t)nth + 1, 0);
+    const bool ident = pt_permuted == 0;
+#pragma omp parallel num_threads(nth)
+    {
+      const int t = omp_get_thread_num(), T = omp_get_num_threads();
+      const int b = (int)((int64_t)NP * t / T), e = (int)((int64_t)NP * (t + 1) / T);
+      int64_t sum = 0;
+      for (int s = b; s < e; s++) {
+        const int j = ident ? s : h->pt_order[s];
+        sum += h->pt_obs_off_caller[j + 1] - h->pt_obs_off_caller[j];
+        h->pt_lo[s] = hi_c[j] < 0 ? -1 : lo_c[j]; h->pt_hi[s] = hi_c[j]; h->pt_contig[s] = contig_c[j];
+      }
+      part[t + 1] = sum;
+#pragma omp barrier
+#pragma omp single
+      for (int q = 0; q < T; q++) part[q + 1] += part[q];
+      int64_t run = part[t];
+      for (int s = b; s < e; s++) {
+        const int j = ident ? s : h->pt_order[s];
+        run += h->pt_obs_off_caller[j + 1] - h->pt_obs_off_caller[j];
+        h->pt_obs_off_int[s + 1] = (int32_t)run;
+      }
+    }
   }
-  // staging in internal order (pinned)
+  TT("internal csr")
+  // staging in internal order (pinned); a previous call's uploads from these buffers must have drained
+  CU(h, cudaStreamSynchronize(h->stream));
   CU(h, h->h_cams.reserve((size_t)NC * 6));
   CU(h, h->h_pts.reserve((size_t)NP * 3));
   CU(h, h->h_feat.reserve((size_t)NO * M));
   CU(h, h->h_obs_cam.reserve((size_t)NO));
+  CU(h, h->h_obs_internal.reserve((size_t)NO));
   std::memcpy(h->h_cams.p, cams6, sizeof(double) * 6 * NC);
+  TT("pinned reserve")
+  // observed points outside the box make the start infeasible (Ceres refuses it): noted per window while staging
+  const uba::Calib kc = make_calib(*calib, M, h->cfg.use_bounds != 0);
+  const bool bounds = h->cfg.use_bounds != 0;
+  h->win_infeasible.assign(nW, 0);
+  // Feature rows are staged AS THEY ARE (one streaming copy into pinned memory) and permuted + transposed into the
+  // SoA planes on the device (k_ingest_feats); the host only builds the slot -> caller-observation map.
+  const bool canonical = pt_permuted == 0 && obs_permuted == 0;
+  {
+    const size_t nd = (size_t)NO * M, chunk = (size_t)1 << 16;
+    const int64_t nchunks = (int64_t)((nd + chunk - 1) / chunk);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < nchunks; c++) {
+      const size_t b = (size_t)c * chunk, e = std::min(nd, b + chunk);
+      std::memcpy(h->h_feat.p + b, feats + b, sizeof(double) * (e - b));
+    }
+  }
+  if (canonical) {
+#pragma omp parallel for schedule(static)
+    for (int64_t o = 0; o < NO; o++) {
+      h->h_obs_internal.p[o] = (int32_t)o;
+      h->h_obs_cam.p[o] = cam_idx[o] | ((cam_id && cam_id[o] != 0) ? (1 << 30) : 0);
+    }
+  }
 #pragma omp parallel for schedule(static)
   for (int s = 0; s < NP; s++) {
     const int j = h->pt_order[s];
-    h->h_pts.p[(size_t)s * 3] = pts3[(size_t)j * 3]; h->h_pts.p[(size_t)s * 3 + 1] = pts3[(size_t)j * 3 + 1]; h->h_pts.p[(size_t)s * 3 + 2] = pts3[(size_t)j * 3 + 2];
+    const double px = pts3[(size_t)j * 3], py = pts3[(size_t)j * 3 + 1], pz = pts3[(size_t)j * 3 + 2];
+    h->h_pts.p[(size_t)s * 3] = px; h->h_pts.p[(size_t)s * 3 + 1] = py; h->h_pts.p[(size_t)s * 3 + 2] = pz;
     const int64_t src = h->pt_obs_off_caller[j];
     const int32_t dst = h->pt_obs_off_int[s];
     const int k = h->pt_obs_off_int[s + 1] - dst;
+    if (bounds && k > 0 && !(px >= kc.lo[0] && px <= kc.hi[0] && py >= kc.lo[1] && py <= kc.hi[1] && pz >= kc.lo[2] && pz <= kc.hi[2])) {
+      char& f = h->win_infeasible[h->pt_win_h[j]];
+      if (!f) f = 1;
+    }
+    if (canonical) continue;
     for (int q = 0; q < k; q++) {
       const int32_t o = h->obs_order[src + q];
-      h->obs_internal[dst + q] = o;
-      for (int m = 0; m < M; m++) h->h_feat.p[(size_t)m * NO + dst + q] = feats[(size_t)o * M + m];
+      h->h_obs_internal.p[dst + q] = o;
       h->h_obs_cam.p[dst + q] = cam_idx[o] | ((cam_id && cam_id[o] != 0) ? (1 << 30) : 0);
     }
   }
@@ -765,7 +894,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   CU(h, h->d_cams.reserve((size_t)NC * 12)); CU(h, h->d_camR.reserve((size_t)NC * kCamStride * 2));
   CU(h, h->d_cam_s2.reserve((size_t)NC * 6)); CU(h, h->d_cam_lam.reserve((size_t)NC * 6)); CU(h, h->d_cam_y.reserve((size_t)NC * 6));
   CU(h, h->d_pts.reserve((size_t)NP * 6)); CU(h, h->d_pt_s2.reserve((size_t)NP * 3)); CU(h, h->d_pt_rec.reserve((size_t)NP * kPtRec));
-  CU(h, h->d_feat.reserve((size_t)NO * M)); CU(h, h->d_obs_cam.reserve((size_t)NO)); CU(h, h->d_Zbuf.reserve((size_t)NO * 18));
+  CU(h, h->d_feat.reserve((size_t)NO * M)); CU(h, h->d_obs_cam.reserve((size_t)NO)); CU(h, h->d_obs_src.reserve((size_t)NO)); CU(h, h->d_Zbuf.reserve((size_t)NO * 18));
   CU(h, h->d_w_cam_off.reserve(nW + 1)); CU(h, h->d_w_pt_off.reserve(nW + 1)); CU(h, h->d_cam_win.reserve(NC));
   CU(h, h->d_pt_obs_off.reserve((size_t)NP + 1)); CU(h, h->d_pt_win.reserve(std::max(NP, 1))); CU(h, h->d_pt_order.reserve(std::max(NP, 1)));
   CU(h, h->d_ws.reserve(nW)); CU(h, h->d_n_active.reserve(1));
@@ -782,14 +911,18 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     CU(h, cudaMemcpyAsync(h->d_pt_order.p, h->pt_order.data(), sizeof(int32_t) * NP, cudaMemcpyHostToDevice, st));
   }
   if (NO) {
-    CU(h, cudaMemcpyAsync(h->d_feat.p, h->h_feat.p, sizeof(double) * NO * M, cudaMemcpyHostToDevice, st));
+    // raw rows into scratch (Zbuf is idle until the first iteration), then gather + transpose on the device
+    CU(h, cudaMemcpyAsync(h->d_Zbuf.p, h->h_feat.p, sizeof(double) * NO * M, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->d_obs_src.p, h->h_obs_internal.p, sizeof(int32_t) * NO, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(h->d_obs_cam.p, h->h_obs_cam.p, sizeof(int32_t) * NO, cudaMemcpyHostToDevice, st));
+    h->timing.kernel_launches += launch_ingest_feats(h->d_Zbuf.p, h->d_obs_src.p, h->d_feat.p, NO, M, st);
   }
   int rc = upload_state(h);
   if (rc) return rc;
   CU(h, cudaMemsetAsync(h->d_recs.p, 0, sizeof(IterRec) * (size_t)nW * rec_stride, st));
-  CU(h, cudaStreamSynchronize(st));
-  TT("h2d")
+  // no synchronisation here: the uploads come from pinned staging owned by the handle and are stream-ordered before
+  // everything uba_optimise enqueues, so the host-side planning of prepare() overlaps them
+  TT("h2d (enqueue)")
   fill_view_static(h);
   h->V.rec_stride = rec_stride;
   h->ws_h.assign(nW, WinState{});
@@ -799,18 +932,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
 
 // Ceres rejects a problem whose bounded parameter blocks start outside their box
 // ([CERES-UPSTREAM] Program::IsFeasible) -> the reference reports Status::FAILED.
-bool window_feasible(const uba_handle* h, int w) {
-  if (!h->cfg.use_bounds) return true;
-  const uba::Calib& k = h->V.calib;
-  for (int s = h->w_pt_off[w]; s < h->w_pt_off[w + 1]; s++) {
-    if (h->pt_obs_off_int[s + 1] == h->pt_obs_off_int[s]) continue;
-    for (int a = 0; a < 3; a++) {
-      const double x = h->h_pts.p[(size_t)s * 3 + a];
-      if (!(x >= k.lo[a] && x <= k.hi[a])) return false;
-    }
-  }
-  return true;
-}
+bool window_feasible(const uba_handle* h, int w) { return !h->win_infeasible[w]; }   // decided while staging (build_problem)
 
 
 // Pose covariances at the final iterate: one undamped linearisation, dense factorisation of the
@@ -907,12 +1029,12 @@ void uba_destroy(uba_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graph(h);
   if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
-  h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release();
+  h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release(); h->h_obs_internal.release();
   h->d_cams.release(); h->d_camR.release(); h->d_cam_s2.release(); h->d_cam_lam.release(); h->d_cam_y.release(); h->d_pts.release();
   h->d_pt_s2.release(); h->d_pt_rec.release(); h->d_feat.release(); h->d_acc.release(); h->d_A.release(); h->d_rhs.release();
   h->d_Zbuf.release(); h->d_dbg.release(); h->d_export.release(); h->d_flush.release();
   h->d_w_cam_off.release(); h->d_w_pt_off.release(); h->d_w_free_off.release(); h->d_free_list.release(); h->d_free_cam.release();
-  h->d_cam_win.release(); h->d_pt_obs_off.release(); h->d_pt_win.release(); h->d_obs_cam.release(); h->d_n_active.release();
+  h->d_cam_win.release(); h->d_pt_obs_off.release(); h->d_pt_win.release(); h->d_obs_cam.release(); h->d_obs_src.release(); h->d_n_active.release();
   h->d_pt_order.release(); h->d_w_red_off.release(); h->d_ws.release(); h->d_recs.release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -994,9 +1116,9 @@ int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearizat
   CU(h, cudaGetLastError());
   std::vector<double> tmp;
   auto fetch = [&](const double* dev, size_t n) -> const double* { tmp.resize(n); cudaMemcpy(tmp.data(), dev, n * sizeof(double), cudaMemcpyDeviceToHost); return tmp.data(); };
-  if (out->residuals) { const double* r = fetch(D.residuals, n_res); for (int64_t s = 0; s < NO; s++) std::memcpy(out->residuals + (size_t)h->obs_internal[s] * M, r + (size_t)s * M, sizeof(double) * M); }
-  if (out->weights) { const double* r = fetch(D.weights, n_w); for (int64_t s = 0; s < NO; s++) out->weights[h->obs_internal[s]] = r[s]; }
-  if (out->W) { const double* r = fetch(D.W, n_W); for (int64_t s = 0; s < NO; s++) std::memcpy(out->W + (size_t)h->obs_internal[s] * 18, r + (size_t)s * 18, sizeof(double) * 18); }
+  if (out->residuals) { const double* r = fetch(D.residuals, n_res); for (int64_t s = 0; s < NO; s++) std::memcpy(out->residuals + (size_t)h->h_obs_internal.p[s] * M, r + (size_t)s * M, sizeof(double) * M); }
+  if (out->weights) { const double* r = fetch(D.weights, n_w); for (int64_t s = 0; s < NO; s++) out->weights[h->h_obs_internal.p[s]] = r[s]; }
+  if (out->W) { const double* r = fetch(D.W, n_W); for (int64_t s = 0; s < NO; s++) std::memcpy(out->W + (size_t)h->h_obs_internal.p[s] * 18, r + (size_t)s * 18, sizeof(double) * 18); }
   if (out->C) { const double* r = fetch(D.C, n_C); for (int s = 0; s < NP; s++) std::memcpy(out->C + (size_t)h->pt_order[s] * 9, r + (size_t)s * 9, sizeof(double) * 9); }
   if (out->grad_pts) { const double* r = fetch(D.grad_pts, n_g); for (int s = 0; s < NP; s++) std::memcpy(out->grad_pts + (size_t)h->pt_order[s] * 3, r + (size_t)s * 3, sizeof(double) * 3); }
   if (out->lm_diag_pts) { const double* r = fetch(D.lam_pts, n_l); for (int s = 0; s < NP; s++) std::memcpy(out->lm_diag_pts + (size_t)h->pt_order[s] * 3, r + (size_t)s * 3, sizeof(double) * 3); }
@@ -1023,8 +1145,10 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
   cudaSetDevice(h->device);
   const auto t_start = std::chrono::steady_clock::now();
   cudaEventRecord(h->ev[2], h->stream);
+  auto tt_ = std::chrono::steady_clock::now();
   int rc = start_solve(h, fixed_frames);
   if (rc) return rc;
+  TT("optimise: start_solve")
   const bool fixedK = h->cfg.fixed_iterations > 0;
   const int max_it = fixedK ? h->cfg.fixed_iterations : h->cfg.max_iterations;
   const bool timed = !fixedK && h->cfg.max_solver_time_s > 0.0;
@@ -1044,6 +1168,7 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
   for (int it = 0; it < max_it; it++) {
     rc = run_iteration_fast(h);
     if (rc) return rc;
+    if (it == 0) TT("optimise: first launch")
     if (!fixedK) {
       // convergence is decided on the device; the host only needs to know when every window is done
       int n_act = 0;
@@ -1056,6 +1181,7 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
   cudaEventRecord(h->ev[3], h->stream);
   CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaGetLastError());
+  TT("optimise: iterations")
   float ms = 0; cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
   h->timing.total_ms += ms;
   h->cov_h.clear();
@@ -1107,7 +1233,12 @@ int uba_get_points(uba_handle* h, double* pts3) {
     return UBA_OK;
   }
   CU(h, h->h_out.reserve((size_t)NP * 6));
-  CU(h, cudaMemcpy(h->h_out.p, h->d_pts.p, sizeof(double) * 6 * NP, cudaMemcpyDeviceToHost));
+  // the accepted iterate lives in one of the two point buffers per window: fetch only the halves in use
+  bool need[2] = {false, false};
+  for (int w = 0; w < h->nW; w++) if (h->ws_h[w].done != UBA_TERM_FAILURE) need[h->ws_h[w].cur & 1] = true;
+  for (int b = 0; b < 2; b++)
+    if (need[b]) CU(h, cudaMemcpyAsync(h->h_out.p + (size_t)b * NP * 3, h->d_pts.p + (size_t)b * NP * 3, sizeof(double) * 3 * NP, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
 #pragma omp parallel for schedule(static)
   for (int s = 0; s < NP; s++) {
     const WinState& st = h->ws_h[h->pt_win_h[s]];
