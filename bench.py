@@ -255,16 +255,17 @@ def main():
     # ---- end to end through the C ABI from host buffers ----
     h2d, d2h = h2d_d2h_bytes(wins)
     e2e_ms = []
-    for rep in range(3):
+    cams_out = np.zeros((h.n_cams, 6)); pts_out = np.zeros((h.n_pts, 3))   # a per-frame caller reuses its result buffers
+    for rep in range(8):
         barrier()
         t0 = time.perf_counter()
         set_problem()
         rc, sums = h.optimise(fixed)
-        cams = h.cameras(); pts = h.points()
+        cams = h.cameras(cams_out); pts = h.points(pts_out)
         torch.cuda.synchronize()
         e2e_ms.append((time.perf_counter() - t0) * 1e3)
         barrier()
-    t = torch.tensor([min(e2e_ms[1:])], dtype=torch.float64, device="cuda")
+    t = torch.tensor([float(np.median(e2e_ms[2:]))], dtype=torch.float64, device="cuda")   # the first calls allocate and capture
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_obs * k_iters / (float(t[0]) * 1e-3)

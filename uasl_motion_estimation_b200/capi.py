@@ -284,13 +284,17 @@ class Handle:
         return arrays
 
     # ---- results ----
-    def cameras(self) -> np.ndarray:
-        a = np.zeros((self.n_cams, 6))
+    def cameras(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Poses [n_cams, 6]; `out` (C-contiguous float64 of that shape) is filled in place when given."""
+        a = np.zeros((self.n_cams, 6)) if out is None else out
+        assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n_cams, 6)
         self._check(self.lib.uba_get_cameras(self._h, dptr(a)))
         return a
 
-    def points(self) -> np.ndarray:
-        a = np.zeros((self.n_pts, 3))
+    def points(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Points [n_pts, 3] in the caller's order; `out` is filled in place when given."""
+        a = np.zeros((self.n_pts, 3)) if out is None else out
+        assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n_pts, 3)
         self._check(self.lib.uba_get_points(self._h, dptr(a)))
         return a
 

@@ -1046,12 +1046,14 @@ __global__ void k_assemble(DevView V) {
 // right-looking so that only rsqrt -> mul -> fma sits on the dependent chain of each pivot.
 // inv[c] = 1 / L_cc.  Returns false on a non-positive pivot.
 __device__ __forceinline__ bool chol6(double (&L)[6][6], double (&inv)[6]) {
+  // The pivot test is kept OFF the dependent chain (measured: 1045 -> 669 cycles per block on B200,
+  // tests/cuda/panel_bench.cu): a bad pivot poisons the block with NaN and the caller's flag discards the solve.
   bool ok = true;
 #pragma unroll
   for (int c = 0; c < 6; c++) {
-    double d = L[c][c];
-    if (!(d > 0.0) || !isfinite(d)) { ok = false; d = 1.0; }
-    const double iv = rsqrt(d);
+    const double d = L[c][c];
+    ok = ok && (d >= 2.2250738585072014e-308) && (d <= 1.7976931348623157e308);
+    const double iv = uba_rsqrt(d);
     inv[c] = iv;
     L[c][c] = d * iv;
 #pragma unroll
@@ -1627,27 +1629,34 @@ __global__ void __launch_bounds__(256) k_chol_banded_la(DevView V, int w, int be
         }
       }
       // ---- (3) rows below the block inside the band, and the rhs: X L_kk^T = A --------------------------
-      if (t <= beta) {
-        const bool is_rhs = t == beta;
+      // all lanes of warp 0 on one path (clamped loads + select); the rhs rides along as one more row in another warp
+      if (t < beta) {
         int orow = o0 + (6 + t) * bw1; if (orow >= ring_size) orow -= ring_size;
         const double* row = ring + orow;
         const int base = beta - 6 - t;        // column offset of (i, c0); entries with base + c < 0 lie outside the band
         double x[6];
 #pragma unroll
-        for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((base + c >= 0) ? row[base + c] : 0.0);
+        for (int c = 0; c < 6; c++) { const int ix = base + c; const double v = row[ix < 0 ? 0 : ix]; x[c] = ix >= 0 ? v : 0.0; }
 #pragma unroll
         for (int c = 0; c < 6; c++) {
           x[c] *= ivk[c];
 #pragma unroll
           for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], Lk[m * 6 + c], x[m]);
         }
-        if (is_rhs) {
 #pragma unroll
-          for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
-        } else {
+        for (int c = 0; c < 6; c++) Xbuf[t * 6 + c] = x[c];
+      } else if (t == 192) {
+        double x[6];
 #pragma unroll
-          for (int c = 0; c < 6; c++) Xbuf[t * 6 + c] = x[c];
+        for (int c = 0; c < 6; c++) x[c] = y[c0 + c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], Lk[m * 6 + c], x[m]);
         }
+#pragma unroll
+        for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
       }
       LT(3)
       asm volatile("bar.sync 1, %0;" ::"n"(NWORK));
@@ -2134,7 +2143,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   double* ring = sm;
   double* y = ring + ring_size;
   double* Xbuf = y + ylen;
-  double* sep = Xbuf + beta * 6 + 8;          // [sw][sw + 1] + rhs [sw] (used by CTA 0)
+  constexpr int XS = 7;                       // odd row stride: conflict-free row walks
+  double* sep = Xbuf + beta * XS + 8;          // [sw][sw + 1] + rhs [sw] (used by CTA 0)
   __shared__ int s_fail;
   __shared__ double s_Lkk[2][36], s_invk[2][6], s_z[6], s_xp[36], s_corner[21], s_xb[2][6];
   double* rhs = V.rhs + (size_t)6 * f0;
@@ -2243,27 +2253,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
           pre[q] = e < 30 * bw1 ? band_entry(r0 + e / bw1, e % bw1) : 0.0;
         }
       }
-      if (t <= beta) {
-        const bool is_rhs = t == beta;
+      // Row solves X L_kk^T = A in warp 0, all lanes on one path (clamped loads + select: divergent loads cost
+      // 2x here, tests/cuda/panel_bench.cu); the rhs rides along as one more row in another warp.
+      if (t < beta) {
         int orow = o0 + (6 + t) * bw1; if (orow >= ring_size) orow -= ring_size;
         const double* row = ring + orow;
         const int basec = beta - 6 - t;
         double x[6];
 #pragma unroll
-        for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((basec + c >= 0) ? row[basec + c] : 0.0);
+        for (int c = 0; c < 6; c++) { const int ix = basec + c; const double v = row[ix < 0 ? 0 : ix]; x[c] = ix >= 0 ? v : 0.0; }
 #pragma unroll
         for (int c = 0; c < 6; c++) {
           x[c] *= ivk[c];
 #pragma unroll
           for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
         }
-        if (is_rhs) {
 #pragma unroll
-          for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
-        } else {
+        for (int c = 0; c < 6; c++) Xbuf[t * XS + c] = x[c];
+      } else if (t == 192) {
+        double x[6];
 #pragma unroll
-          for (int c = 0; c < 6; c++) Xbuf[t * 6 + c] = x[c];
+        for (int c = 0; c < 6; c++) x[c] = y[c0 + c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
         }
+#pragma unroll
+        for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NWORKH));
 #pragma unroll
@@ -2271,8 +2289,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
         const int ti = pti[q], tk = ptk[q];
         if (ti >= 0) {
           int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
-          const double* xi = Xbuf + ti * 6;
-          const double* xk = Xbuf + tk * 6;
+          const double* xi = Xbuf + ti * XS;
+          const double* xk = Xbuf + tk * XS;
           double acc = 0.0;
 #pragma unroll
           for (int c = 0; c < 6; c++) acc = fma(xi[c], xk[c], acc);
@@ -2285,7 +2303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
         double acc = 0.0;
 #pragma unroll
         for (int c = 0; c < 6; c++) {
-          const double l = Xbuf[tt * 6 + c];
+          const double l = Xbuf[tt * XS + c];
           acc = fma(l, s_z[c], acc);
           if (basec + c >= 0 && i < H.nh) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
         }
@@ -3003,7 +3021,7 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
         static const bool use_c2 = [] { const char* e = getenv("UBA_BAND_C2"); return !(e && e[0] == '0'); }();
         if (use_la && use_c2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
           const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
-          const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)beta * 6 + 8 + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
+          const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)beta * 8 + 8 + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
 #define UBA_C2_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_c2<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_c2<PP>, 2, 256, smem, st, V, w, beta); }
           if (per <= 2) UBA_C2_LAUNCH(2) else UBA_C2_LAUNCH(3)
