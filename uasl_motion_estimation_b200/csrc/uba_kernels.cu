@@ -2153,6 +2153,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   const double* Ab = A0 + (size_t)2 * n * bw1;
   const bool panel = t >= NWORKH;
   const int pl = t - NWORKH;
+#ifdef UBA_BAND_TIMING
+  long long tph[8]; int nph = 0;
+#define PH() { if (t == 0) tph[nph++] = clock64(); }
+#else
+#define PH()
+#endif
+  PH()
   if (t == 0) s_fail = 0;
   auto band_entry = [&](int i, int c) -> double {
     if (i >= H.nh || i - beta + c < 0) return 0.0;
@@ -2195,14 +2202,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   }
   __syncthreads();
   int o0 = 0;
-  for (int kb = 0; kb < nblk; kb++) {
+  PH()
+  // block steps [kb0, kb1).  At the end of a half (tail == false) the block after the last eliminated one is the
+  // first separator block: it still gets its corner update (written back to the ring) but is not factored here.
+  // At the end of the separator (tail == true) there is no next block.
+  auto forward = [&](int kb0, int kb1, bool tail) {
+  for (int kb = kb0; kb < kb1; kb++) {
     const int c0 = 6 * kb, par = kb & 1;
     const double* Lk = s_Lkk[par];
     const double* ivk = s_invk[par];
-    if (panel) {
-      // the block after the last eliminated one is the first separator block: it still needs its corner update
-      // (written back to the ring), it is just not factored here
-      const bool last = kb + 1 == nblk;
+    if (panel && !(tail && kb + 1 == kb1)) {
+      const bool last = kb + 1 == kb1;
       int on = o0 + 6 * bw1; if (on >= ring_size) on -= ring_size;
       if (pl < 6) {
         const double* row = ring + on + pl * bw1 + (beta - 6 - pl);
@@ -2241,7 +2251,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
           for (int c = 0; c < 6; c++) s_Lkk[par ^ 1][r * 6 + c] = L[r][c];
         }
       }
-    } else {
+    } else if (!panel) {
       constexpr int kPre = (30 * 36 + NWORKH - 1) / NWORKH;   // beta <= 35
       double pre[kPre];
       const bool reload = kb > 0 && (kb % 5) == 0;
@@ -2325,66 +2335,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
     __syncthreads();
     o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
   }
+  };
+  forward(0, nblk, false);
+  PH()
   cg::cluster_group cluster = cg::this_cluster();
   cluster.sync();
-  // ---- separator (CTA 0): S = T + B - A_ss (lower), rhs = y_top + y_bot - b_s, in ORIGINAL separator order ----
+  PH()
+  // ---- separator (CTA 0): S = T + B - A_ss, rhs = y_top + y_bot - b_s.  The merged rows simply continue CTA 0's
+  // block elimination (sw / 6 more steps), followed by a short backward substitution inside the separator ----
   if (half == 0) {
     const double* ring1 = cluster.map_shared_rank(ring, 1);
     double* y1 = cluster.map_shared_rank(y, 1);
     int* fail1 = cluster.map_shared_rank(&s_fail, 1);
     const int ne0 = m, ne1 = n - m - sw;
-    const int lds = sw + 1;
     for (int e = t; e < sw * sw; e += NH) {
       const int a = e / sw, b = e % sw;
-      if (b > a) continue;
-      double v = 0.0;
-      if (a - b <= beta) {
-        const int it = ne0 + a, kt = ne0 + b;                    // top: local = original
-        const double tv = ring[(it % kBandRing) * bw1 + (kt - it + beta)];
-        const int ib = ne1 + (sw - 1 - b), kbm = ne1 + (sw - 1 - a);   // bottom (reversed): row >= col
-        const double bv = ring1[(ib % kBandRing) * bw1 + (kbm - ib + beta)];
-        v = tv + bv - Ab[(size_t)(m + a) * bw1 + (b - a + beta)];
-      }
-      sep[a * lds + b] = v;
+      if (b > a || a - b > beta) continue;
+      const int it = ne0 + a, kt = ne0 + b;                          // top: local = original numbering
+      const int ib = ne1 + (sw - 1 - b), kbm = ne1 + (sw - 1 - a);   // bottom (reversed): row >= col
+      ring[(it % kBandRing) * bw1 + (kt - it + beta)] += ring1[(ib % kBandRing) * bw1 + (kbm - ib + beta)] - Ab[(size_t)(m + a) * bw1 + (b - a + beta)];
     }
-    for (int a = t; a < sw; a += NH) sep[sw * lds + a] = y[ne0 + a] + y1[ne1 + (sw - 1 - a)] - rhs[m + a];
+    for (int a = t; a < sw; a += NH) y[ne0 + a] += y1[ne1 + (sw - 1 - a)] - rhs[m + a];
     __syncthreads();
-    if (t < 32) {                             // dense Cholesky + solve of the sw x sw separator system by one warp
-      double* rs = sep + sw * lds;
-      for (int j = 0; j < sw; j++) {
-        const double d = sep[j * lds + j];
-        if (t == 0 && (!(d > 0.0) || !isfinite(d))) s_fail = 1;
-        const double iv = rsqrt(fmax(d, 1e-300));
-        __syncwarp();
-        for (int i = j + t; i < sw; i += 32) sep[i * lds + j] *= iv;   // includes the diagonal: d * iv = sqrt(d)
-        __syncwarp();
-        for (int e = t; e < (sw - j - 1) * (sw - j - 1); e += 32) {
-          const int i = j + 1 + e / (sw - j - 1), k = j + 1 + e % (sw - j - 1);
-          if (k <= i) sep[i * lds + k] = fma(-sep[i * lds + j], sep[k * lds + j], sep[i * lds + k]);
+    if (t == NWORKH) {                        // factor of the first separator block
+      const int ob = (ne0 % kBandRing) * bw1;
+      double L[6][6], iv[6];
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) L[r][c] = c <= r ? ring[ob + r * bw1 + beta - r + c] : 0.0;
+      if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        s_invk[nblk & 1][r] = iv[r];
+#pragma unroll
+        for (int c = 0; c < 6; c++) s_Lkk[nblk & 1][r * 6 + c] = L[r][c];
+      }
+    }
+    __syncthreads();
+    forward(nblk, nblk + sw / 6, true);
+    // backward substitution inside the separator (factor rows staged from global memory)
+    for (int e = t; e < sw * bw1; e += NH) ring[e] = Lt[(size_t)ne0 * bw1 + e];
+    __syncthreads();
+    for (int c0 = sw - 6; c0 >= 0; c0 -= 6) {
+      const double* blk = ring + c0 * bw1;
+      if (t == 0) {
+        double xb[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) xb[c] = y[ne0 + c0 + c];
+#pragma unroll
+        for (int c = 5; c >= 0; c--) {
+          xb[c] *= blk[c * bw1];
+#pragma unroll
+          for (int mm = 0; mm < 6; mm++) if (mm < c) xb[mm] = fma(-blk[c * bw1 + (c - mm)], xb[c], xb[mm]);
         }
-        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 6; c++) { y[ne0 + c0 + c] = xb[c]; s_z[c] = xb[c]; }
       }
-      for (int i = 0; i < sw; i++) {          // forward
-        double sacc = 0.0;
-        for (int k = t; k < i; k += 32) sacc = fma(sep[i * lds + k], rs[k], sacc);
-        sacc = warp_sum(sacc);
-        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
-        __syncwarp();
+      __syncthreads();
+      if (t < c0) {                           // separator rows above the block
+        const int j = c0 - 1 - t;
+        double v = y[ne0 + j];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { const int d = c0 + c - j; if (d <= beta) v = fma(-blk[c * bw1 + d], s_z[c], v); }
+        y[ne0 + j] = v;
       }
-      for (int i = sw - 1; i >= 0; i--) {     // backward
-        double sacc = 0.0;
-        for (int k = i + 1 + t; k < sw; k += 32) sacc = fma(sep[k * lds + i], rs[k], sacc);
-        sacc = warp_sum(sacc);
-        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
-        __syncwarp();
-      }
+      __syncthreads();
     }
-    __syncthreads();
     // the separator solution becomes known boundary values of both halves
-    for (int a = t; a < sw; a += NH) { const double x = sep[sw * lds + a]; y[ne0 + a] = x; y1[ne1 + (sw - 1 - a)] = x; }
+    for (int a = t; a < sw; a += NH) y1[ne1 + (sw - 1 - a)] = y[ne0 + a];
     if (t == 0) { const int f = s_fail | *fail1; s_fail = f; *fail1 = f; }
   }
+  PH()
   cluster.sync();
+  PH()
   // ---- backward substitution of this half (local numbering) with lookahead; separator rows are known ----
   constexpr int kChunk = 126;
   for (int i1 = H.nh; i1 > 0; i1 -= kChunk) {
@@ -2459,6 +2483,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
     }
   }
   __syncthreads();
+  PH()
+#ifdef UBA_BAND_TIMING
+  if (t == 0) for (int q = 0; q < nph; q++) V.Zbuf[half * 8 + q] = (double)(tph[q] - tph[0]);
+#endif
+#undef PH
   const bool failed = s_fail != 0;
   for (int i = t; i < H.nh; i += NH) {
     if (H.dir == 1 && i >= H.ne) continue;    // the separator is written once, by the top half
