@@ -279,3 +279,26 @@ def test_mono_batch_and_window_without_free_cameras(gpu_lib, oracle):
     o = oracle.optimise(w, cfg, w.n_cams)
     np.testing.assert_array_equal(h2.cameras(), w.cams_init)
     assert rel(h2.points(), o["pts"]) < STATE_TOL
+
+
+def test_iteration_graph_is_rebuilt_when_the_solver_settings_change(gpu_lib, oracle):
+    """The LM iteration is replayed from a CUDA graph that bakes the device view in by value.  Re-submitting a window of
+    the same shape reuses the graph; changing anything in the view (here the iteration budget, through the timing entry
+    point) must not: a stale graph would stop iterating after the old budget and report a far too short time."""
+    win, cfg, h = make(gpu_lib, "c2", 0.5, fixed_iterations=2)
+    o = oracle.optimise(win, cfg, 2)
+    for _ in range(2):   # second call replays the captured graph
+        h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+        rc, sums = h.optimise(2)
+        assert rc == 0 and sums[0].iterations == 2
+        assert rel(h.cameras(), o["cams"]) < STATE_TOL and rel(h.points(), o["pts"]) < STATE_TOL
+    h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+    ms_iter = h.time_iteration(2, iterations=8, flush_l2=False)
+    ms_lin = h.time_linearize(2, 1e4, repeats=8, flush_l2=False)
+    assert ms_iter > ms_lin, (ms_iter, ms_lin)   # eight full iterations, not two plus six early exits
+    # and a different window of the same shape through the same handle still gives that window's answer
+    win2 = synth.config_window("c2", window=3, scale=0.5, lib=gpu_lib)
+    h.set_problem(4, win2.cams_init, win2.pts_init, win2.feats, win2.cam_idx, win2.pt_idx, win2.cam_id, win2.calib)
+    rc, sums = h.optimise(2)
+    o2 = oracle.optimise(win2, cfg, 2)
+    assert rc == 0 and rel(h.cameras(), o2["cams"]) < STATE_TOL and rel(h.points(), o2["pts"]) < STATE_TOL

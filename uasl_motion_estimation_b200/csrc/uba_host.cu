@@ -154,7 +154,8 @@ struct uba_handle {
   cudaGraphExec_t graph_exec = nullptr;
 #endif
   int64_t graph_kernels = 0;
-  std::vector<char> graph_sig;                // what the captured graph bakes in (see prepare)
+  std::vector<char> graph_sig;                // host-side launch geometry the captured graph bakes in (see prepare)
+  DevView graph_V;                            // ... and the device view it was captured with (see run_iteration_fast)
   // timing
   bool profiling = false;
   uba_timing timing{};
@@ -191,7 +192,6 @@ uba::Calib make_calib(const uba_calib& in, int M, bool use_bounds) {
 void drop_graph(uba_handle* h) {
 #ifndef UBA_EMU
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
-  h->graph_sig.clear();
 #else
   (void)h;
 #endif
@@ -485,13 +485,13 @@ int prepare(uba_handle* h, int fixed_frames) {
   V.w_lin = h->d_acc.p + h->off_wlin; V.w_post = h->d_acc.p + h->off_wpost; V.w_max = h->d_acc.p + h->off_wmax;
   V.w_loc = h->d_acc.p + h->off_wloc;
   V.A = h->d_A.p; V.rhs = h->d_rhs.p;
-  // The captured iteration graph stays valid when nothing it bakes in has changed: the device view (pointers and
-  // sizes, passed to every kernel by value) and the host-side launch geometry.  A sliding window re-submitted with
-  // the same shape (the per-frame case) then skips capture + instantiation.
+  // The captured iteration graph stays valid when nothing it bakes in has changed: the host-side launch geometry
+  // (checked here) and the device view passed to every kernel by value (checked at launch, run_iteration_fast).
+  // A sliding window re-submitted with the same shape (the per-frame case) then skips capture + instantiation.
   {
     std::vector<char> sig;
     auto put = [&](const void* ptr, size_t n) { const char* c = (const char*)ptr; sig.insert(sig.end(), c, c + n); };
-    put(&V, sizeof(DevView)); put(h->variant_off, sizeof(h->variant_off)); put(&h->max_n, sizeof(h->max_n));
+    put(h->variant_off, sizeof(h->variant_off)); put(&h->max_n, sizeof(h->max_n));
     put(&h->acc_total, sizeof(h->acc_total)); put(&h->use_tile, sizeof(h->use_tile)); put(&h->use_tile2, sizeof(h->use_tile2));
     if (nW) { put(h->win_n.data(), sizeof(int) * nW); put(h->win_beta.data(), sizeof(int) * nW); }
     if (sig != h->graph_sig) { drop_graph(h); h->graph_sig.swap(sig); }
@@ -590,8 +590,11 @@ int run_iteration(uba_handle* h) {
 int run_iteration_fast(uba_handle* h) {
 #ifndef UBA_EMU
   if (!h->profiling && !h->comm) {
+    // the graph bakes the device view in by value: any change of it (sizes, pointers, solver settings) invalidates it
+    if (h->graph_exec && std::memcmp(&h->V, &h->graph_V, sizeof(DevView)) != 0) drop_graph(h);
     if (!h->graph_exec) {
       cudaGraph_t g = nullptr;
+      std::memcpy(&h->graph_V, &h->V, sizeof(DevView));
       const int64_t before = h->timing.kernel_launches, lin_before = h->timing.linearize_launches;
       if (getenv("UBA_TRACE")) fprintf(stderr, "  [trace] capturing the iteration graph\n");
       CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
