@@ -115,6 +115,8 @@ struct uba_handle {
   // prepared for a given fixed_frames
   int prepared_fixed = -1;
   std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n, win_beta;
+  bool dense_override = false;                // covariance / parity dumps: every window uses the dense accumulator layout
+  std::vector<std::pair<size_t, size_t>> sum_ranges;   // (offset, count) pieces of the accumulator block summed over ranks
   std::vector<char> win_infeasible;           // a window whose start violates the point bounds
   DevBuf<int32_t> d_w_beta;
   std::vector<int64_t> w_red_off_h;
@@ -427,7 +429,10 @@ int prepare(uba_handle* h, int fixed_frames) {
       bw = (int)v;
     }
     const int beta = 6 * bw + 5;
-    if (beta <= kBandMaxBeta && h->cfg.solver != 1) h->win_beta[w] = beta;
+    // the banded solver keeps {factor rows of both halves, assembled band} = 3 n (beta + 1) doubles in the window's
+    // n x n slot of the matrix buffer
+    const int64_t nn = h->win_n[w];
+    if (beta <= kBandMaxBeta && h->cfg.solver != 1 && 3 * nn * (beta + 1) <= nn * nn) h->win_beta[w] = beta;
   }
 #ifdef UBA_EMU
   h->win_beta.assign(nW, 0);  // the emulation only has the dense stand-in solver
@@ -455,6 +460,19 @@ int prepare(uba_handle* h, int fixed_frames) {
   h->off_wloc = h->off_wmax + (size_t)nW;
   h->acc_total = h->off_wloc + (size_t)nW * WC_COUNT;
   CU(h, h->d_acc.reserve(h->acc_total));
+  // what a point-sharded run has to sum over ranks after each linearisation: the Schur accumulators (only the band
+  // of banded windows: 285 KB instead of 11 MB on c4) and the tail {B, v, Z h, cost}; adjacent ranges are merged
+  h->sum_ranges.clear();
+  auto add_range = [&](size_t off, size_t cnt) {
+    if (!cnt) return;
+    if (!h->sum_ranges.empty() && h->sum_ranges.back().first + h->sum_ranges.back().second == off) h->sum_ranges.back().second += cnt;
+    else h->sum_ranges.emplace_back(off, cnt);
+  };
+  for (int w = 0; w < nW; w++) {
+    const size_t nn = (size_t)h->win_n[w];
+    add_range((size_t)h->w_red_off_h[w], h->win_beta[w] > 0 ? nn * (size_t)(h->win_beta[w] + 1) : nn * nn);
+  }
+  add_range(red, h->acc_sum1 - red);
   CU(h, h->d_A.reserve(red));
   CU(h, h->d_rhs.reserve(6 * nfree));
   TT("prepare: free cams, band")
@@ -540,15 +558,31 @@ int launch_linearizers(uba_handle* h, const DebugOut& dbg) {
 
 // the linearise + Schur pass (the roofline kernel of the hot path)
 int run_linearize(uba_handle* h, const DebugOut& dbg) {
-  CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
+  // zero what this pass accumulates into: for banded windows only the band of the Schur accumulator is ever touched
+  if (!h->dense_override && h->sum_ranges.size() <= 4) {
+    for (size_t i = 0; i < h->sum_ranges.size(); i++) {
+      const auto& r = h->sum_ranges[i];
+      const size_t cnt = i + 1 == h->sum_ranges.size() ? h->acc_total - r.first : r.second;   // the last range runs into the per-window tails
+      CU(h, cudaMemsetAsync(h->d_acc.p + r.first, 0, cnt * sizeof(double), h->stream));
+    }
+  } else {
+    CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
+  }
   PhaseTimer t(h, 0);
   h->timing.kernel_launches += launch_linearizers(h, dbg);
   h->timing.linearize_launches++;
   t.stop();
   if (h->comm) {
     PhaseTimer tc(h, 4);
-    int rc = allreduce(h, h->d_acc.p, h->acc_sum1, kNcclSum);
-    if (rc) return rc;
+    if (h->dense_override) {
+      int rc = allreduce(h, h->d_acc.p, h->acc_sum1, kNcclSum);
+      if (rc) return rc;
+    } else {
+      for (const auto& r : h->sum_ranges) {
+        int rc = allreduce(h, h->d_acc.p + r.first, r.second, kNcclSum);
+        if (rc) return rc;
+      }
+    }
     tc.stop();
   }
   return UBA_OK;
@@ -951,7 +985,9 @@ int compute_covariances(uba_handle* h) {
   DebugOut none{};
   const bool was_profiling = h->profiling;
   h->profiling = false;
+  h->dense_override = true;
   int rc = run_linearize(h, none);
+  h->dense_override = false;
   if (!rc) {
     h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
     h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), zeros.data(), solve_small_limit(), h->stream);
@@ -1108,11 +1144,13 @@ int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearizat
   CU(h, cudaMemsetAsync(h->d_dbg.p, 0, (n_res + n_w + n_C + n_W + n_g + n_l) * sizeof(double), h->stream));
   DebugOut D;
   D.residuals = h->d_dbg.p; D.weights = D.residuals + n_res; D.C = D.weights + n_w; D.W = D.C + n_C; D.grad_pts = D.W + n_W; D.lam_pts = D.grad_pts + n_g;
-  rc = run_linearize(h, D);
-  if (rc) return rc;
   // the parity dump wants the dense damped matrix even for windows the banded solver would handle
   std::vector<int32_t> zeros(h->nW, 0);
   CU(h, cudaMemcpyAsync(h->d_w_beta.p, zeros.data(), sizeof(int32_t) * h->nW, cudaMemcpyHostToDevice, h->stream));
+  h->dense_override = true;
+  rc = run_linearize(h, D);
+  h->dense_override = false;
+  if (rc) { cudaMemcpyAsync(h->d_w_beta.p, h->win_beta.data(), sizeof(int32_t) * h->nW, cudaMemcpyHostToDevice, h->stream); return rc; }
   h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
   CU(h, cudaMemcpyAsync(h->d_w_beta.p, h->win_beta.data(), sizeof(int32_t) * h->nW, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));

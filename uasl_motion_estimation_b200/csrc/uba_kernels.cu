@@ -38,6 +38,13 @@ namespace uba {
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
+// Entry (row, col), col >= row, of a window's Schur accumulator.  Windows that go to the banded solver keep only the
+// band (row-major, beta + 1 entries per row: col - row <= beta by construction of beta), which is also all that a
+// point-sharded run has to all-reduce; the others keep the dense n x n upper triangle.
+__device__ __forceinline__ size_t sacc_index(int n, int beta, int row, int col) {
+  return beta > 0 ? (size_t)row * (beta + 1) + (col - row) : (size_t)row * n + col;
+}
+
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
   // non-negative doubles order like their bit patterns
   atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
@@ -208,6 +215,7 @@ __global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D, int 
       // second pass: Z = W Linv^T per free-camera observation, Schur outer products
       const int64_t red = V.w_red_off[w];
       const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+      const int sbeta = V.w_beta[w];
       double* S = V.Sacc + red;
       for (int o = o0; o < o1; o++) {
         const int oc = V.obs_cam[o];
@@ -254,16 +262,16 @@ __global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D, int 
             for (int i = 0; i < 18; i++) Za[i] = za[i];
           }
           // block (fa, fb) with fa <= fb: observations of a point are camera-ascending
-          double* blk = S + (size_t)(6 * fa) * n + 6 * fb;
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
             for (int c = 0; c < 6; c++)
             {
+              if (fa == fb && c < r) continue;   // only the upper triangle is kept
               double v = Za[r * 3] * Zb[c * 3] + Za[r * 3 + 1] * Zb[c * 3 + 1] + Za[r * 3 + 2] * Zb[c * 3 + 2];
               if (fa == fb && oa != o)  // one camera seen twice by this point: add the transposed product too
                 v += Zb[r * 3] * Za[c * 3] + Zb[r * 3 + 1] * Za[c * 3 + 1] + Zb[r * 3 + 2] * Za[c * 3 + 2];
-              atomicAdd(&blk[(size_t)r * n + c], v);
+              atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + r, 6 * fb + c)], v);
             }
         }
       }
@@ -533,7 +541,8 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
     const int b = a + r;
     const int fa = s_free[nfx + a], fb = s_free[nfx + b];
     if (e < 36) {
-      if (sacc != 0.0) atomicAdd(&S[(size_t)(6 * fa + e / 6) * n + 6 * fb + e % 6], sacc);
+      const int row = 6 * fa + e / 6, colx = 6 * fb + e % 6;
+      if (sacc != 0.0 && colx >= row) atomicAdd(&S[sacc_index(n, V.w_beta[w], row, colx)], sacc);
     } else if (a == b) {
       if (sacc != 0.0) atomicAdd(&V.zh[(size_t)s_gc[nfx + a] * 6 + (e - 36)], sacc);
     }
@@ -858,6 +867,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   // ---- flush: Schur tiles.  K-groups are summed in shared memory, then one red.add per entry ---------
   const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
   double* S = V.Sacc + V.w_red_off[w];
+  const int sbeta = V.w_beta[w];
   const int nloc = 6 * nlf;
   if (nlf > 0) {
     const int frow = lane >> 2, fc = (lane & 3) * 2;
@@ -874,7 +884,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
             if (colx >= row && colx < nloc && v != 0.0) {
               const int a = row / 6, b = colx / 6;
               const int fa = s_free[nfx + a], fb = s_free[nfx + b];
-              atomicAdd(&S[(size_t)(6 * fa + row - 6 * a) * n + 6 * fb + (colx - 6 * b)], v);
+              atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + row - 6 * a, 6 * fb + (colx - 6 * b))], v);
             }
           }
         }
@@ -901,7 +911,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
         if (v == 0.0) continue;
         const int a = row / 6, b = colx / 6;
         const int fa = s_free[nfx + a], fb = s_free[nfx + b];
-        atomicAdd(&S[(size_t)(6 * fa + row - 6 * a) * n + 6 * fb + (colx - 6 * b)], v);
+        atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + row - 6 * a, 6 * fb + (colx - 6 * b))], v);
       }
     }
     __syncthreads();
@@ -965,16 +975,16 @@ __device__ __forceinline__ double cam_damping(const DevView& V, const WinState* 
 
 // symmetric entry (i, j), i >= j, of the damped reduced camera matrix, read from the upper block
 // triangle of the Schur accumulator, the camera blocks B and the LM damping
-__device__ __forceinline__ double reduced_entry(const DevView& V, const WinState* st, int f0, int n, const double* S, int i, int j) {
+__device__ __forceinline__ double reduced_entry(const DevView& V, const WinState* st, int f0, int n, int sbeta, const double* S, int i, int j) {
   const int fr = j / 6, r = j - fr * 6, fc = i / 6, c = i - fc * 6;
   if (fr == fc) {
     const int gc = V.free_list[f0 + fr];
     const double b = V.Bacc[(size_t)gc * 36 + r * 6 + c];
-    double val = b - S[(size_t)(6 * fr + r) * n + 6 * fr + c];
+    double val = b - S[sacc_index(n, sbeta, 6 * fr + r, 6 * fr + c)];
     if (r == c) val += cam_damping(V, st, gc, r, b, false);
     return val;
   }
-  return -S[(size_t)j * n + i];
+  return -S[sacc_index(n, sbeta, j, i)];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -994,7 +1004,8 @@ __global__ void k_assemble(DevView V) {
   double* A = V.A + red;
   double* rhs = V.rhs + (size_t)6 * f0;
   // banded windows: pass 1 (this loop) builds lambda on the diagonal + rhs; pass 2 (below) writes the band
-  const bool banded = V.w_beta[w] > 0;
+  const int sbeta = V.w_beta[w];
+  const bool banded = sbeta > 0;
   const int64_t nmat = banded ? (int64_t)n : (int64_t)n * n;
   const int64_t total = nmat + n;
   double gmax = 0.0;
@@ -1007,12 +1018,12 @@ __global__ void k_assemble(DevView V) {
         const int gc = V.free_list[f0 + fa];
         const double* B = V.Bacc + (size_t)gc * 36;
         const int rr = r < c ? r : c, cc = r < c ? c : r;
-        val = B[rr * 6 + cc] - S[(size_t)(6 * fa + rr) * n + 6 * fa + cc];
+        val = B[rr * 6 + cc] - S[sacc_index(n, sbeta, 6 * fa + rr, 6 * fa + cc)];
         if (r == c) val += cam_damping(V, st, gc, r, B[r * 6 + r], true);
       } else if (fa < fb) {
-        val = -S[(size_t)i * n + j];
+        val = -S[sacc_index(n, sbeta, i, j)];
       } else {
-        val = -S[(size_t)j * n + i];
+        val = -S[sacc_index(n, sbeta, j, i)];
       }
       if (!banded) A[(size_t)i * n + j] = val;
     } else {
@@ -1033,7 +1044,7 @@ __global__ void k_assemble(DevView V) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nb; e += (int64_t)gridDim.x * blockDim.x) {
       const int i = (int)(e / bw1), c = (int)(e - (int64_t)i * bw1);
       const int k = i - beta + c;
-      Ab[e] = k >= 0 ? reduced_entry(V, st, f0, n, S, i, k) : 0.0;
+      Ab[e] = k >= 0 ? reduced_entry(V, st, f0, n, V.w_beta[w], S, i, k) : 0.0;
     }
   }
 }
@@ -2154,7 +2165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   const bool panel = t >= NWORKH;
   const int pl = t - NWORKH;
 #ifdef UBA_BAND_TIMING
-  long long tph[8]; int nph = 0;
+  long long tph[8]; int nph = 0; long long busy = 0;
 #define PH() { if (t == 0) tph[nph++] = clock64(); }
 #else
 #define PH()
@@ -2184,6 +2195,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   }
   int cr = 0, ce = pl;                        // corner entry of panel lane pl: (cr, ce), ce <= cr
   while (ce > cr) { ce -= cr + 1; cr++; }
+  int dg_r = 0, dg_c = t - (NWORKH - 21);     // the last 21 workers: entry (dg_r, dg_c) of the diagonal block's factor
+  if (dg_c >= 0 && dg_c < 21) { while (dg_c > dg_r) { dg_c -= dg_r + 1; dg_r++; } } else dg_c = 0;
   const int nblk = H.ne / 6;
   __syncthreads();
   if (t == NWORKH) {                          // prologue: factor of block 0
@@ -2208,6 +2221,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   // At the end of the separator (tail == true) there is no next block.
   auto forward = [&](int kb0, int kb1, bool tail) {
   for (int kb = kb0; kb < kb1; kb++) {
+#ifdef UBA_BAND_TIMING
+    const long long tb0 = clock64();
+#endif
     const int c0 = 6 * kb, par = kb & 1;
     const double* Lk = s_Lkk[par];
     const double* ivk = s_invk[par];
@@ -2307,21 +2323,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
           ring[oi + (beta - ti + tk)] -= acc;
         }
       }
-      if (t >= 64 && t < 64 + beta) {
-        const int tt = t - 64, i = c0 + 6 + tt;
-        const int basec = beta - 6 - tt;
+      // side duties.  Factor rows go out to global memory one value per thread, six consecutive lanes per row (the six
+      // values of a row are contiguous there): a thread-per-row store walks 29 sectors per instruction and made its
+      // warp the step's straggler.  The diagonal block's factor goes out the same way, the rhs update sits in warp 3.
+      if (t < 6 * beta) {
+        const int tt = t / 6, c = t - 6 * tt, i = c0 + 6 + tt;
+        if (i < H.nh && beta - 6 - tt + c >= 0) Lt[(size_t)i * bw1 + (6 + tt - c)] = Xbuf[tt * XS + c];
+      }
+      if (t >= NWORKH - 21) Lt[(size_t)(c0 + dg_r) * bw1 + (dg_r - dg_c)] = (dg_r == dg_c) ? ivk[dg_r] : Lk[dg_r * 6 + dg_c];
+      if (t >= 96 && t < 96 + beta) {
+        const int tt = t - 96, i = c0 + 6 + tt;
         double acc = 0.0;
 #pragma unroll
-        for (int c = 0; c < 6; c++) {
-          const double l = Xbuf[tt * XS + c];
-          acc = fma(l, s_z[c], acc);
-          if (basec + c >= 0 && i < H.nh) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
-        }
+        for (int c = 0; c < 6; c++) acc = fma(Xbuf[tt * XS + c], s_z[c], acc);
         y[i] -= acc;
-      } else if (t >= 160 && t < 166) {
-        const int r = t - 160;
-        Lt[(size_t)(c0 + r) * bw1] = ivk[r];
-        for (int c = 0; c < r; c++) Lt[(size_t)(c0 + r) * bw1 + (r - c)] = Lk[r * 6 + c];
       }
       if (reload) {
         const int r0 = c0 + kBandRing - 30;
@@ -2332,6 +2347,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
         }
       }
     }
+#ifdef UBA_BAND_TIMING
+    busy += clock64() - tb0;
+#endif
     __syncthreads();
     o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
   }
@@ -2486,6 +2504,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   PH()
 #ifdef UBA_BAND_TIMING
   if (t == 0) for (int q = 0; q < nph; q++) V.Zbuf[half * 8 + q] = (double)(tph[q] - tph[0]);
+  if (half == 0 && (t & 31) == 0) V.Zbuf[16 + (t >> 5)] = (double)busy;
+  if (half == 0 && t == 64) V.Zbuf[24] = (double)busy;
 #endif
 #undef PH
   const bool failed = s_fail != 0;
