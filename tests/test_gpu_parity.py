@@ -302,3 +302,28 @@ def test_iteration_graph_is_rebuilt_when_the_solver_settings_change(gpu_lib, ora
     rc, sums = h.optimise(2)
     o2 = oracle.optimise(win2, cfg, 2)
     assert rc == 0 and rel(h.cameras(), o2["cams"]) < STATE_TOL and rel(h.points(), o2["pts"]) < STATE_TOL
+
+
+@pytest.mark.parametrize("variant", ["track_order", "camera_descending", "random_points"])
+def test_ingest_paths(gpu_lib, oracle, variant):
+    """Canonical input (fast path: one streaming copy, identity maps) and permuted input (general path) through the device-side
+    feature gather; results against the oracle, and the canonical and permuted runs against each other."""
+    base = synth.config_window("c4", scale=0.05, lib=gpu_lib)
+    if variant == "track_order":
+        win = synth.reorder(base)
+    elif variant == "camera_descending":
+        win = synth.reorder(base, camera_descending=True)
+    else:
+        win = synth.reorder(base, point_order=np.random.default_rng(3).permutation(base.n_pts))
+    cfg = capi.default_config(gpu_lib, fixed_iterations=4)
+    h = capi.Handle(cfg, lib=gpu_lib)
+    h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+    t = h.tables(2); r = oracle.tables(win.n_cams, win.n_pts, win.cam_idx, win.pt_idx, 2)
+    for k in t:
+        assert np.array_equal(t[k], r[k]), k
+    g = h.linearize(2, 1e4); o = oracle.linearize(win, cfg, 2, 1e4)
+    for k in BLOCKS:
+        assert rel(g[k], o[k]) < BLOCK_TOL, k
+    rc, _ = h.optimise(2)
+    oo = oracle.optimise(win, cfg, 2)
+    assert rc == 0 and rel(h.cameras(), oo["cams"]) < STATE_TOL and rel(h.points(), oo["pts"]) < STATE_TOL

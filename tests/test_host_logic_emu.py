@@ -8,6 +8,11 @@ import pytest
 from uasl_motion_estimation_b200 import capi, synth
 
 
+BLOCK_TOL = 1e-9   # north_star: residual vectors and normal-equation blocks within 1e-9 relative
+STATE_TOL = 1e-6   # final poses and points within 1e-6 relative after a fixed number of LM iterations
+BLOCKS = ("residuals", "weights", "cost", "grad_cams", "grad_pts", "B", "C", "W", "S", "rhs", "lm_diag_cams", "lm_diag_pts")
+
+
 def rel(a, b):
     a = np.asarray(a, float).reshape(-1); b = np.asarray(b, float).reshape(-1)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
@@ -44,6 +49,34 @@ def test_tables_with_shuffled_observations_and_empty_points(emu_lib, oracle):
     for k in t:
         assert np.array_equal(t[k], r[k]), k
     assert (np.diff(t["pt_obs_off"])[3::7] == 0).all()
+
+
+@pytest.mark.parametrize("variant", ["track_order", "camera_descending", "random_points"])
+def test_ingest_paths_give_the_same_tables_and_blocks(emu_lib, oracle, variant):
+    """The ingest has a fast path for input that is already canonical (tracks grouped by first/last keyframe, observations
+    point-major and frame-ascending: nothing moves) next to the general one (parallel counting sort of the points, per-point
+    observation sort).  Each must give the oracle's tables bit for bit and its blocks to 1e-9."""
+    base = synth.config_window("c2", scale=0.006, lib=emu_lib)
+    if variant == "track_order":
+        win = synth.reorder(base)
+    elif variant == "camera_descending":
+        win = synth.reorder(base, camera_descending=True)
+    else:
+        win = synth.reorder(base, point_order=np.random.default_rng(3).permutation(base.n_pts))
+    cfg = capi.default_config(emu_lib, fixed_iterations=3)
+    h = capi.Handle(cfg, lib=emu_lib)
+    h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+    t = h.tables(2); r = oracle.tables(win.n_cams, win.n_pts, win.cam_idx, win.pt_idx, 2)
+    for k in t:
+        assert np.array_equal(t[k], r[k]), k
+    if variant == "track_order":
+        assert np.array_equal(t["obs_order"], np.arange(win.n_obs)) and np.array_equal(t["pt_order"], np.arange(win.n_pts))
+    g = h.linearize(2, 1e4); o = oracle.linearize(win, cfg, 2, 1e4)
+    for k in BLOCKS:
+        assert rel(g[k], o[k]) < BLOCK_TOL, k
+    rc, _ = h.optimise(2)
+    oo = oracle.optimise(win, cfg, 2)
+    assert rc == 0 and rel(h.cameras(), oo["cams"]) < STATE_TOL and rel(h.points(), oo["pts"]) < STATE_TOL
 
 
 @pytest.mark.parametrize("name,scale,M", [("c1", 0.02, 4), ("c2", 0.004, 4), ("c4", 0.001, 4), ("c5", 0.002, 4), ("c1", 0.02, 2), ("c2", 0.004, 2)])

@@ -602,10 +602,29 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// asynchronous global -> shared copies (LDGSTS): the prefetch of the next chunk holds no registers
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gsrc)) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(__cvta_generic_to_global(gsrc)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 constexpr int kT2MaxPc = 64;          // points per chunk are capped so that K = 3 Pc <= 192
+constexpr int kT2StageD = 8;          // per lane and buffer: point (3) + features (<= 4) doubles, 1 spare
+constexpr int kT2StageI = 4;          // ... and ints: next chunk's mask, its first-observation offset, obs_cam word, spare
 // Zm capacity in doubles: the worst case over (T, nl) of 8 T * t2_ldz(Pc) is 96 x 84 (T = 12, Pc = 23) for
 // 256-thread CTAs and 32 x 196 (T = 4, Pc = 64) for 128-thread CTAs
 __host__ __device__ constexpr int t2_zm_doubles(int nt) { return nt == 256 ? 8192 : 6400; }
+// doubles of the region {Zm | flush scratch} (the scratch aliases Zm): [points x slots][33] <= nt*33, or the
+// (8T) x (8T+1) K-group reduction tile (T <= 12 for 256-thread CTAs, <= 8 for 128-thread ones)
+__host__ __device__ constexpr int t2_main_doubles(int nt) {
+  return nt == 256 ? (96 * 97 > 8192 ? 96 * 97 : 8192) : (6400 > 128 * 33 ? (6400 > 64 * 65 ? 6400 : 64 * 65) : 128 * 33);
+}
+// ... followed by the two prefetch staging buffers
+__host__ __device__ constexpr int t2_stage_doubles(int nt) { return 2 * nt * (kT2StageD + kT2StageI / 2); }
 
 __host__ __device__ inline int t2_ldz(int pc) {
   int k = ((3 * pc + 3) / 4) * 4;     // K padded to the DMMA k = 4
@@ -675,62 +694,67 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   double cost = 0.0, gmax = 0.0, fail = 0.0;
   __syncthreads();
 
-  // software pipeline over chunks (registers): stage B holds the mask / first-observation offset of the chunk
-  // after next, stage A the mask, point and features of the next chunk, so that no global round trip sits at
-  // the head of a chunk
-  unsigned maskA = 0, maskB = 0;
-  int oA = 0, offB = 0;
-  double XA[3] = {0, 0, 0}, fA[M];
-  int cidA = 0;
+  // Prefetch pipeline over chunks through shared memory (cp.async, no registers held across a chunk): while chunk k
+  // is processed, the point and features of this lane's observation in chunk k+1 and the mask / first-observation
+  // offset of its point in chunk k+2 are in flight into the lane's staging slot (two buffers, alternating).
+  double* stageD = Zm + t2_main_doubles(NT);                       // [2][NT][kT2StageD]
+  int* stageI = reinterpret_cast<int*>(stageD + 2 * NT * kT2StageD);   // [2][NT][kT2StageI]
+  unsigned mask_cur = 0;
+  // issue the copies for the chunk whose first point slot is c (mask m, offset off known) into buffer b, plus the
+  // mask / offset of the chunk after it
+  auto prefetch = [&](int b, int pa, unsigned m, int off) {
+    double* sd = stageD + ((size_t)b * NT + t) * kT2StageD;
+    int* si = stageI + ((size_t)b * NT + t) * kT2StageI;
+    if (m) {
+      const double* px = V.pts[cur] + (size_t)pa * 3;
+      cp_async8(sd, px); cp_async8(sd + 1, px + 1); cp_async8(sd + 2, px + 2);
+      if ((m >> sl) & 1u) {
+        const int o = off + __popc(m & ((1u << sl) - 1u));
 #pragma unroll
-  for (int m = 0; m < M; m++) fA[m] = 0.0;
-  {
-    const int pa = part.pt_begin + pl, pb = pa + Pc;
-    if (p1_thread && pa < part.pt_end) {
-      maskA = V.pt_mask[pa];
-      if (maskA) {
-        XA[0] = V.pts[cur][(size_t)pa * 3]; XA[1] = V.pts[cur][(size_t)pa * 3 + 1]; XA[2] = V.pts[cur][(size_t)pa * 3 + 2];
-        if ((maskA >> sl) & 1u) {
-          oA = V.pt_obs_off[pa] + __popc(maskA & ((1u << sl) - 1u));
-#pragma unroll
-          for (int m = 0; m < M; m++) fA[m] = V.feat[(size_t)m * V.NO + oA];
-          if (M == 2) cidA = (V.obs_cam[oA] >> 30) & 1;
-        }
+        for (int q = 0; q < M; q++) cp_async8(sd + 3 + q, V.feat + (size_t)q * V.NO + o);
+        if (M == 2) cp_async4(si + 2, V.obs_cam + o);
       }
     }
-    if (p1_thread && pb < part.pt_end) { maskB = V.pt_mask[pb]; offB = V.pt_obs_off[pb]; }
+    const int pb = pa + Pc;
+    if (pb < part.pt_end) { cp_async4(si, V.pt_mask + pb); cp_async4(si + 1, V.pt_obs_off + pb); }
+    else si[0] = 0;
+    cp_async_commit();
+  };
+  if (p1_thread) {
+    const int pa = part.pt_begin + pl;
+    int off0 = 0;
+    if (pa < part.pt_end) { mask_cur = V.pt_mask[pa]; off0 = V.pt_obs_off[pa]; }
+    prefetch(0, pa, mask_cur, off0);
   }
-  for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += Pc) {
+  int buf = 0;
+  for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += Pc, buf ^= 1) {
     const int np = min(Pc, part.pt_end - c0);
     // ---- phase 1a: linearise my observation -------------------------------------------------
     const bool have_pt = p1_thread && pl < np;
     const int p = c0 + pl;
-    const unsigned mask = maskA;
+    const unsigned mask = mask_cur;
     const bool seen = have_pt && ((mask >> sl) & 1u);
-    const double X[3] = {XA[0], XA[1], XA[2]};
-    double f[M];
+    double X[3] = {0, 0, 0}, f[M];
 #pragma unroll
-    for (int m = 0; m < M; m++) f[m] = fA[m];
-    const int cid = cidA;
+    for (int q = 0; q < M; q++) f[q] = 0.0;
+    int cid = 0;
+    if (p1_thread) {
+      cp_async_wait_all();
+      const double* sd = stageD + ((size_t)buf * NT + t) * kT2StageD;
+      const int* si = stageI + ((size_t)buf * NT + t) * kT2StageI;
+      if (mask) { X[0] = sd[0]; X[1] = sd[1]; X[2] = sd[2]; }
+      if (seen) {
+#pragma unroll
+        for (int q = 0; q < M; q++) f[q] = sd[3 + q];
+        if (M == 2) cid = (si[2] >> 30) & 1;
+      }
+      const unsigned mask_next = (unsigned)si[0];
+      const int off_next = si[1];
+      prefetch(buf ^ 1, p + Pc, mask_next, off_next);
+      mask_cur = mask_next;
+    }
     double Wm[18];
     double cg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    {
-      // advance the pipeline: A <- next chunk (using stage B's mask / offset), B <- the chunk after next
-      const int pa = p + Pc, pb = pa + Pc;
-      maskA = maskB;
-      const int offA = offB;
-      maskB = 0;
-      if (p1_thread && pb < part.pt_end) { maskB = V.pt_mask[pb]; offB = V.pt_obs_off[pb]; }
-      if (maskA) {
-        XA[0] = V.pts[cur][(size_t)pa * 3]; XA[1] = V.pts[cur][(size_t)pa * 3 + 1]; XA[2] = V.pts[cur][(size_t)pa * 3 + 2];
-        if ((maskA >> sl) & 1u) {
-          oA = offA + __popc(maskA & ((1u << sl) - 1u));
-#pragma unroll
-          for (int m = 0; m < M; m++) fA[m] = V.feat[(size_t)m * V.NO + oA];
-          if (M == 2) cidA = (V.obs_cam[oA] >> 30) & 1;
-        }
-      }
-    }
     if (seen && (UBA_TILE_PHASES & 1)) {
       double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
       const double rho0 = obs_linearize<M>(camS + sl * kCamStride, X, f, cid, V.calib, V.loss, rraw, wgt, F, E, rh);
@@ -2962,8 +2986,7 @@ size_t lin_tile2_smem_bytes(int nt) {
 #else
   // camS | Zm (rows 8T <= 128, row stride t2_ldz(Pc)); the flush scratch ([points x slots][33] <= nt*33 doubles, or
   // the (8T) x (8T+1) K-group reduction tile, T <= 12 there) aliases Zm
-  const size_t zm = t2_zm_doubles(nt), fl = (size_t)nt * 33, sl = 96 * 97;
-  return sizeof(double) * (kTileMaxLocal * kCamStride + std::max(zm, std::max(fl, nt == 256 ? sl : (size_t)(64 * 65))));
+  return sizeof(double) * ((size_t)kTileMaxLocal * kCamStride + t2_main_doubles(nt) + t2_stage_doubles(nt));
 #endif
 }
 

@@ -75,6 +75,24 @@ def generate(n_cams, n_pts, track_min, track_max, full_tracks=0, outliers=0.0, s
                   np.ascontiguousarray(pt_idx[:n]), np.ascontiguousarray(cam_id[:n]), fixed_frames, calib)
 
 
+def reorder(win: Window, point_order: np.ndarray | None = None, camera_descending: bool = False) -> Window:
+    """The same window with its points renumbered (`point_order[new] = old`) and its observations re-emitted point-major —
+    camera-ascending inside a point as the reference's initialiseObservations does (BundleAdjuster.h:364-374), or descending.
+    `point_order=None` sorts the tracks by (first, last) keyframe: the order a sliding window's track container has."""
+    counts = np.bincount(win.pt_idx, minlength=win.n_pts)
+    lo = np.full(win.n_pts, np.iinfo(np.int32).max, np.int64); hi = np.full(win.n_pts, -1, np.int64)
+    np.minimum.at(lo, win.pt_idx, win.cam_idx); np.maximum.at(hi, win.pt_idx, win.cam_idx)
+    if point_order is None:
+        point_order = np.lexsort((hi, np.where(counts > 0, lo, np.iinfo(np.int32).max)))
+    new_of_old = np.empty(win.n_pts, np.int64); new_of_old[point_order] = np.arange(win.n_pts)
+    new_pt = new_of_old[win.pt_idx]
+    key_cam = -win.cam_idx.astype(np.int64) if camera_descending else win.cam_idx.astype(np.int64)
+    o = np.lexsort((key_cam, new_pt))
+    return Window(win.M, win.cams_gt, win.cams_init, np.ascontiguousarray(win.pts_gt[point_order]), np.ascontiguousarray(win.pts_init[point_order]),
+                  np.ascontiguousarray(win.feats[o]), np.ascontiguousarray(win.cam_idx[o]), np.ascontiguousarray(new_pt[o].astype(np.int32)),
+                  np.ascontiguousarray(win.cam_id[o]), win.fixed_frames, win.calib)
+
+
 def config_window(name: str, window: int = 0, scale: float = 1.0, lib=None, M=4) -> Window:
     """One window of configuration c1..c5; ``scale`` shrinks the point count (parity tests)."""
     c = CONFIGS[name]
