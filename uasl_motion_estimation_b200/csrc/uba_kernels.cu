@@ -2178,8 +2178,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   double* ring = sm;
   double* y = ring + ring_size;
   double* Xbuf = y + ylen;
-  constexpr int XS = 7;                       // odd row stride: conflict-free row walks
-  double* sep = Xbuf + beta * XS + 8;          // [sw][sw + 1] + rhs [sw] (used by CTA 0)
+  constexpr int XS = 9;                       // row stride of Xbuf [40][XS]: columns 6..8 and rows >= beta stay zero (DMMA padding)
   __shared__ int s_fail;
   __shared__ double s_Lkk[2][36], s_invk[2][6], s_z[6], s_xp[36], s_corner[21], s_xb[2][6];
   double* rhs = V.rhs + (size_t)6 * f0;
@@ -2189,7 +2188,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   const bool panel = t >= NWORKH;
   const int pl = t - NWORKH;
 #ifdef UBA_BAND_TIMING
-  long long tph[8]; int nph = 0; long long busy = 0;
+  long long tph[8]; int nph = 0; long long busy = 0; long long seg[6] = {0, 0, 0, 0, 0, 0}; long long tq = 0;
+#define SG(i) { const long long now_ = clock64(); seg[i] += now_ - tq; tq = now_; }
 #define PH() { if (t == 0) tph[nph++] = clock64(); }
 #else
 #define PH()
@@ -2202,23 +2202,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   };
   for (int i = t; i < ylen; i += NH) y[i] = i < H.nh ? rhs[H.dir == 0 ? i : n - 1 - i] : 0.0;
   for (int e = t; e < kBandRing * bw1; e += NH) ring[e] = band_entry(e / bw1, e % bw1);
-  const int npairs = beta * (beta + 1) / 2;
-  int pti[PER], ptk[PER];
+  for (int i = t; i < 40 * XS; i += NH) Xbuf[i] = 0.0;
+  // trailing update W -= X X^T on the FP64 tensor-core path: 8x8 tiles (I >= J) of the beta x beta window, dealt to
+  // the 7 worker warps; the X fragments of a tile are 4 shared-memory loads per lane instead of 12 per scalar pair
+  constexpr int kTW = 3;                      // tiles per worker warp (15 tiles for beta = 35, 10 for beta = 29)
+  const int NBt = (beta + 7) / 8, ntile = NBt * (NBt + 1) / 2;
+  int tI[kTW], tJ[kTW];
 #pragma unroll
-  for (int q = 0; q < PER; q++) {
-    const int e = t + q * NWORKH;
-    int ti = -1, tk = 0;
-    if (!panel && e < npairs) {
-      int d0 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((d0 + 1) * (d0 + 2) / 2 <= e) d0++;
-      while (d0 * (d0 + 1) / 2 > e) d0--;
-      ti = d0; tk = e - d0 * (d0 + 1) / 2;
-      if (ti < 6) ti = -1;                    // corner pair: owned by the panel warp
-    }
-    pti[q] = ti; ptk[q] = tk;
+  for (int q = 0; q < kTW; q++) {
+    int idx = (t >> 5) + 7 * q, I = 0;
+    if (panel || idx >= ntile) { tI[q] = -1; tJ[q] = 0; continue; }
+    while (idx > I) { idx -= I + 1; I++; }    // row-major over the lower triangle: (I, J = idx), J <= I
+    tI[q] = I; tJ[q] = idx;
   }
   int cr = 0, ce = pl;                        // corner entry of panel lane pl: (cr, ce), ce <= cr
   while (ce > cr) { ce -= cr + 1; cr++; }
+  const bool rf_on = !panel && t < 6 * bw1;   // ring refill role: entry (rf_row, rf_col) of the 6 incoming rows
+  const int rf_row = t / bw1, rf_col = t - rf_row * bw1;
   int dg_r = 0, dg_c = t - (NWORKH - 21);     // the last 21 workers: entry (dg_r, dg_c) of the diagonal block's factor
   if (dg_c >= 0 && dg_c < 21) { while (dg_c > dg_r) { dg_c -= dg_r + 1; dg_r++; } } else dg_c = 0;
   const int nblk = H.ne / 6;
@@ -2246,7 +2246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   auto forward = [&](int kb0, int kb1, bool tail) {
   for (int kb = kb0; kb < kb1; kb++) {
 #ifdef UBA_BAND_TIMING
-    const long long tb0 = clock64();
+    const long long tb0 = clock64(); tq = tb0;
 #endif
     const int c0 = 6 * kb, par = kb & 1;
     const double* Lk = s_Lkk[par];
@@ -2292,17 +2292,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
         }
       }
     } else if (!panel) {
-      constexpr int kPre = (30 * 36 + NWORKH - 1) / NWORKH;   // beta <= 35
-      double pre[kPre];
-      const bool reload = kb > 0 && (kb % 5) == 0;
-      if (reload) {
-        const int r0 = c0 + kBandRing - 30;
-#pragma unroll
-        for (int q = 0; q < kPre; q++) {
-          const int e = t + q * NWORKH;
-          pre[q] = e < 30 * bw1 ? band_entry(r0 + e / bw1, e % bw1) : 0.0;
-        }
+      // Ring refill, every step: the 6 rows of the block that was eliminated in the previous step are dead; the rows 126
+      // further down take their slots.  One entry per thread (6 (beta+1) <= 216), row / column of the entry fixed per
+      // thread (no index arithmetic in the loop), loaded here and stored at the end of the step.
+      double pre = 0.0;
+      if (rf_on) {
+        const int i = c0 + kBandRing + rf_row;
+        if (i < H.nh) pre = H.dir == 0 ? Ab[(size_t)i * bw1 + rf_col] : Ab[(size_t)(n - 1 - i + beta - rf_col) * bw1 + rf_col];
       }
+#ifdef UBA_BAND_TIMING
+      SG(0)
+#endif
       // Row solves X L_kk^T = A in warp 0, all lanes on one path (clamped loads + select: divergent loads cost
       // 2x here, tests/cuda/panel_bench.cu); the rhs rides along as one more row in another warp.
       if (t < beta) {
@@ -2333,20 +2333,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
 #pragma unroll
         for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
       }
+#ifdef UBA_BAND_TIMING
+      SG(1)
+#endif
       asm volatile("bar.sync 1, %0;" ::"n"(NWORKH));
+#ifdef UBA_BAND_TIMING
+      SG(2)
+#endif
+      {
+        const int fr = (t & 31) >> 2, fk = t & 3;
 #pragma unroll
-      for (int q = 0; q < PER; q++) {
-        const int ti = pti[q], tk = ptk[q];
-        if (ti >= 0) {
-          int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
-          const double* xi = Xbuf + ti * XS;
-          const double* xk = Xbuf + tk * XS;
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < 6; c++) acc = fma(xi[c], xk[c], acc);
-          ring[oi + (beta - ti + tk)] -= acc;
+        for (int q = 0; q < kTW; q++) {
+          if (tI[q] < 0) continue;
+          const double* xa = Xbuf + (8 * tI[q] + fr) * XS + fk;
+          const double* xb = Xbuf + (8 * tJ[q] + fr) * XS + fk;
+          double d0 = 0.0, d1 = 0.0;
+          dmma884(d0, d1, xa[0], xb[0]);
+          dmma884(d0, d1, xa[4], xb[4]);
+          const int ti = 8 * tI[q] + fr, tk = 8 * tJ[q] + 2 * fk;
+          if (ti >= 6 && ti < beta) {           // rows inside the window; the corner (ti < 6) belongs to the panel warp
+            int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
+            double* dst = ring + oi + (beta - ti + tk);
+            if (tk <= ti) dst[0] -= d0;
+            if (tk + 1 <= ti) dst[1] -= d1;
+          }
         }
       }
+#ifdef UBA_BAND_TIMING
+      SG(3)
+#endif
       // side duties.  Factor rows go out to global memory one value per thread, six consecutive lanes per row (the six
       // values of a row are contiguous there): a thread-per-row store walks 29 sectors per instruction and made its
       // warp the step's straggler.  The diagonal block's factor goes out the same way, the rhs update sits in warp 3.
@@ -2362,16 +2377,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
         for (int c = 0; c < 6; c++) acc = fma(Xbuf[tt * XS + c], s_z[c], acc);
         y[i] -= acc;
       }
-      if (reload) {
-        const int r0 = c0 + kBandRing - 30;
-#pragma unroll
-        for (int q = 0; q < kPre; q++) {
-          const int e = t + q * NWORKH;
-          if (e < 30 * bw1) ring[((r0 + e / bw1) % kBandRing) * bw1 + e % bw1] = pre[q];
-        }
-      }
+#ifdef UBA_BAND_TIMING
+      SG(4)
+#endif
+      if (rf_on) ring[o0 + rf_row * bw1 + rf_col] = pre;   // slot of row c0 + rf_row, dead since the previous step
     }
 #ifdef UBA_BAND_TIMING
+    if (!panel) SG(5)
     busy += clock64() - tb0;
 #endif
     __syncthreads();
@@ -2529,7 +2541,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
 #ifdef UBA_BAND_TIMING
   if (t == 0) for (int q = 0; q < nph; q++) V.Zbuf[half * 8 + q] = (double)(tph[q] - tph[0]);
   if (half == 0 && (t & 31) == 0) V.Zbuf[16 + (t >> 5)] = (double)busy;
-  if (half == 0 && t == 64) V.Zbuf[24] = (double)busy;
+  if (half == 0 && (t == 0 || t == 100 || t == 192)) for (int q = 0; q < 6; q++) V.Zbuf[32 + (t == 0 ? 0 : t == 100 ? 8 : 16) + q] = (double)seg[q];
 #endif
 #undef PH
   const bool failed = s_fail != 0;
@@ -3093,7 +3105,7 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
         static const bool use_c2 = [] { const char* e = getenv("UBA_BAND_C2"); return !(e && e[0] == '0'); }();
         if (use_la && use_c2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
           const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
-          const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)beta * 8 + 8 + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
+          const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)40 * 9 + 8 + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
 #define UBA_C2_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_c2<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_c2<PP>, 2, 256, smem, st, V, w, beta); }
           if (per <= 2) UBA_C2_LAUNCH(2) else UBA_C2_LAUNCH(3)
