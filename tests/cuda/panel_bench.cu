@@ -279,6 +279,66 @@ __global__ void workers(double* out, long long* cyc, int iters) {
   if (t == 0) { cyc[0] = c1 - c0; out[0] = ring[5] + y[3] + Xbuf[9]; }
 }
 
+// ---- one block of the backward substitution (k_chol_banded_c2), 256 threads, beta = 29 ---------------------------------
+// PARTS bit 0: diagonal solve by lane 0 of warp 7, bit 1: next block's rows by 6 lanes of warp 7, bit 2: workers one block behind
+template <int PARTS>
+__global__ void backward(double* out, long long* cyc, int iters) {
+  constexpr int beta = 29, bw1 = 30, NWORK = 224;
+  __shared__ double ring[126 * bw1], y[256], s_xb[2][6];
+  const int t = threadIdx.x;
+  const bool panel = t >= NWORK; const int pl = t - NWORK;
+  for (int i = t; i < 126 * bw1; i += 256) ring[i] = (i % bw1 == 0) ? 0.5 : 1e-3 * ((i * 7) % 13);
+  for (int i = t; i < 256; i += 256) y[i] = 0.5 + 1e-3 * i;
+  if (t < 12) s_xb[t / 6][t % 6] = 0.1;
+  __syncthreads();
+  const long long c00 = clock64();
+  for (int rep = 0; rep < iters; rep++) {
+    int it = 1;
+    for (int c0 = 120; c0 >= 36; c0 -= 6, it++) {
+      const double* blk = ring + c0 * bw1;
+      const int par = it & 1;
+      if (panel) {
+        if ((PARTS & 1) && pl == 0) {
+          double xb[6];
+#pragma unroll
+          for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
+#pragma unroll
+          for (int c = 5; c >= 0; c--) {
+            xb[c] *= blk[c * bw1];
+#pragma unroll
+            for (int mm = 0; mm < 6; mm++) if (mm < c) xb[mm] = fma(-blk[c * bw1 + (c - mm)], xb[c], xb[mm]);
+          }
+#pragma unroll
+          for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c] * 1e-3 + 0.5; s_xb[par][c] = xb[c] * 1e-3; }
+        }
+        __syncwarp();
+        if ((PARTS & 2) && pl < 6) {
+          const int j = c0 - 6 + pl;
+          double v = y[j], v2 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 6; c++) v = fma(-blk[c * bw1 + (c0 + c - j)], s_xb[par][c], v);
+          const double* blkp = blk + 6 * bw1;
+#pragma unroll
+          for (int c = 0; c < 6; c++) { const int d = c0 + 6 + c - j; if (d <= beta) v2 = fma(blkp[c * bw1 + d], s_xb[par ^ 1][c], v2); }
+          y[j] = (v - v2) * 1e-3 + 0.5;
+        }
+        __syncwarp();
+      } else if ((PARTS & 4) && t < beta - 12) {
+        const int cp = c0 + 6;
+        const double* blkp = blk + 6 * bw1;
+        const int j = cp - 13 - t;
+        double v = y[j];
+#pragma unroll
+        for (int c = 0; c < 6; c++) { const int d = cp + c - j; if (d <= beta) v = fma(-blkp[c * bw1 + d], s_xb[par ^ 1][c], v); }
+        y[j] = v * 1e-3 + 0.5;
+      }
+      __syncthreads();
+    }
+  }
+  const long long c1 = clock64();
+  if (t == 0) { cyc[0] = c1 - c00; out[0] = y[40] + y[100]; }
+}
+
 int main() {
   double* out; long long* cyc; cudaMalloc(&out, 64); cudaMalloc(&cyc, 64);
   const int iters = 2000;
@@ -302,6 +362,14 @@ int main() {
     for (int rep = 0; rep < 2; rep++) { w.k<<<1, 224>>>(out, cyc, iters); cudaDeviceSynchronize(); }
     long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
     printf("%-44s %7.1f cycles/step %s\n", w.name, (double)h / iters, cudaGetErrorString(cudaGetLastError()));
+  }
+  struct { const char* name; void (*k)(double*, long long*, int); } bk[] = {
+      {"backward block: all parts", backward<7>}, {"backward block: diagonal solve only", backward<1>}, {"backward block: next rows only", backward<2>},
+      {"backward block: workers only", backward<4>}, {"backward block: barriers only", backward<0>}};
+  for (auto& w : bk) {
+    for (int rep = 0; rep < 2; rep++) { w.k<<<1, 256>>>(out, cyc, 200); cudaDeviceSynchronize(); }
+    long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%-44s %7.1f cycles/block %s\n", w.name, (double)h / (200.0 * 15), cudaGetErrorString(cudaGetLastError()));
   }
   return 0;
 }

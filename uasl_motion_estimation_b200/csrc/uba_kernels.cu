@@ -2629,7 +2629,8 @@ __global__ void __launch_bounds__(128) k_solve_epilogue(DevView V) {
   const int f0 = V.w_free_off[w];
   const double* y = V.rhs + (size_t)6 * f0;
   double mc = 0.0, step2 = 0.0, x2 = 0.0;
-  for (int gc = c0 + threadIdx.x; gc < c1; gc += blockDim.x) {
+  // grid (window, camera slices): a 200-keyframe window is spread over several SMs instead of looping in one CTA
+  for (int gc = c0 + blockIdx.y * blockDim.x + threadIdx.x; gc < c1; gc += gridDim.y * blockDim.x) {
     const int f = V.free_cam[gc];
     double cand[6];
 #pragma unroll
@@ -3152,7 +3153,12 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
     }
   }
 #endif
-  UBA_LAUNCH(k_solve_epilogue, V.nW, 128, 0, st, V);
+  {
+    const int avg = (V.NC + V.nW - 1) / V.nW;          // any split is correct (grid-stride loop); this one suits uniform windows
+    const int bs = avg <= 32 ? 32 : 64;
+    int slices = (avg + bs - 1) / bs; if (slices > 16) slices = 16;
+    UBA_LAUNCH(k_solve_epilogue, dim3(V.nW, slices), bs, 0, st, V);
+  }
   return launches + 1;
 }
 
