@@ -2692,16 +2692,10 @@ __global__ void __launch_bounds__(128) k_backsub(DevView V) {
         double f[M];
 #pragma unroll
         for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
-        double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
-        obs_linearize<M>(camR + (size_t)gc * kCamStride, X, f, (oc >> 30) & 1, V.calib, V.loss, rraw, wgt, F, E, rh);
-        const double* yc = V.cam_y + (size_t)gc * 6;
-#pragma unroll
-        for (int a = 0; a < NR; a++) {
-          double fy = 0.0;
-#pragma unroll
-          for (int r = 0; r < 6; r++) fy += F[a][r] * yc[r];
-          t3[0] += E[a][0] * fy; t3[1] += E[a][1] * fy; t3[2] += E[a][2] * fy;
-        }
+        // t3 += E^T (F y_c), matrix-free (uba_math.h: obs_apply)
+        const double* ycp = V.cam_y + (size_t)gc * 6;
+        const double yc[6] = {ycp[0], ycp[1], ycp[2], ycp[3], ycp[4], ycp[5]};
+        obs_apply<M>(camR + (size_t)gc * kCamStride, X, f, (oc >> 30) & 1, V.calib, V.loss, yc, t3);
       }
       const double* rec = V.pt_rec + (size_t)p * kPtRec;
       double Li[6], h[3], g[3], lam[3];
