@@ -2685,7 +2685,33 @@ __global__ void __launch_bounds__(128) k_backsub(DevView V) {
       const int cbase = V.w_cam_off[w];
       const double* camR = V.camR[cur];
       double t3[3] = {0, 0, 0};
-      for (int o = o0; o < o1; o++) {
+      // The kernel is bound by the latency of its global loads (ncu: long scoreboard), so the camera words and features of
+      // the first KC observations are fetched up front (KC x (M + 1) independent loads in flight) and kept in registers
+      // for the candidate-cost pass below; longer tracks take the one-at-a-time path for the rest.
+      constexpr int KC = 6;
+      int occ[KC];
+      double fcc[KC][M];
+      const int kk = min(o1 - o0, KC);
+#pragma unroll
+      for (int q = 0; q < KC; q++) {
+        if (q < kk) {
+          occ[q] = V.obs_cam[o0 + q];
+#pragma unroll
+          for (int m = 0; m < M; m++) fcc[q][m] = V.feat[(size_t)m * V.NO + o0 + q];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < KC; q++) {
+        if (q < kk) {
+          const int gc = cbase + (occ[q] & 0x3fffffff);
+          if (V.free_cam[gc] >= 0) {
+            const double* ycp = V.cam_y + (size_t)gc * 6;
+            const double yc[6] = {ycp[0], ycp[1], ycp[2], ycp[3], ycp[4], ycp[5]};
+            obs_apply<M>(camR + (size_t)gc * kCamStride, X, fcc[q], (occ[q] >> 30) & 1, V.calib, V.loss, yc, t3);
+          }
+        }
+      }
+      for (int o = o0 + KC; o < o1; o++) {
         const int oc = V.obs_cam[o];
         const int gc = cbase + (oc & 0x3fffffff);
         if (V.free_cam[gc] < 0) continue;
@@ -2718,7 +2744,16 @@ __global__ void __launch_bounds__(128) k_backsub(DevView V) {
       }
       // candidate cost at (candidate cameras, candidate point)
       const double* camRn = V.camR[nxt];
-      for (int o = o0; o < o1; o++) {
+#pragma unroll
+      for (int q = 0; q < KC; q++) {
+        if (q < kk) {
+          const int gc = cbase + (occ[q] & 0x3fffffff);
+          double rraw[M];
+          const double s = obs_residual<M>(camRn + (size_t)gc * kCamStride, Xn, fcc[q], (occ[q] >> 30) & 1, V.calib, rraw);
+          cnew += 0.5 * loss_rho(V.loss, s);
+        }
+      }
+      for (int o = o0 + KC; o < o1; o++) {
         const int oc = V.obs_cam[o];
         const int gc = cbase + (oc & 0x3fffffff);
         double f[M];
