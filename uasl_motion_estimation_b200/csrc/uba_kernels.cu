@@ -694,14 +694,19 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   double cost = 0.0, gmax = 0.0, fail = 0.0;
   __syncthreads();
 
-  // Prefetch pipeline over chunks through shared memory (cp.async, no registers held across a chunk): while chunk k
-  // is processed, the point and features of this lane's observation in chunk k+1 and the mask / first-observation
-  // offset of its point in chunk k+2 are in flight into the lane's staging slot (two buffers, alternating).
+  // Prefetch pipeline over chunks, two implementations (chosen per tile variant by measurement on B200):
+  //  * kAsyncPipe (the T = 4 variant: c4, c5): through shared memory with cp.async, no registers held across a chunk.  While
+  //    chunk k is processed, the point and features of this lane's observation in chunk k+1 and the mask / first-observation
+  //    offset of its point in chunk k+2 are in flight into the lane's staging slot (two buffers, alternating).  The register
+  //    version made ptxas spill the prefetched values right after their loads, which stalls on cold data (-5 % on c4).
+  //  * otherwise (wider variants: c1, c2, c3) in registers: stage B holds the mask / offset of the chunk after next, stage A
+  //    the mask, point and features of the next chunk (the shared-memory version costs 8 % there).
+  constexpr bool kAsyncPipe = (T == 4);
   double* stageD = Zm + t2_main_doubles(NT);                       // [2][NT][kT2StageD]
   int* stageI = reinterpret_cast<int*>(stageD + 2 * NT * kT2StageD);   // [2][NT][kT2StageI]
   unsigned mask_cur = 0;
-  // issue the copies for the chunk whose first point slot is c (mask m, offset off known) into buffer b, plus the
-  // mask / offset of the chunk after it
+  // issue the copies for the chunk whose point is pa (mask m, offset off known) into buffer b, plus the mask / offset
+  // of the chunk after it
   auto prefetch = [&](int b, int pa, unsigned m, int off) {
     double* sd = stageD + ((size_t)b * NT + t) * kT2StageD;
     int* si = stageI + ((size_t)b * NT + t) * kT2StageI;
@@ -720,11 +725,34 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
     else si[0] = 0;
     cp_async_commit();
   };
-  if (p1_thread) {
-    const int pa = part.pt_begin + pl;
-    int off0 = 0;
-    if (pa < part.pt_end) { mask_cur = V.pt_mask[pa]; off0 = V.pt_obs_off[pa]; }
-    prefetch(0, pa, mask_cur, off0);
+  unsigned maskA = 0, maskB = 0;
+  int oA = 0, offB = 0;
+  double XA[3] = {0, 0, 0}, fA[M];
+  int cidA = 0;
+#pragma unroll
+  for (int m = 0; m < M; m++) fA[m] = 0.0;
+  if constexpr (kAsyncPipe) {
+    if (p1_thread) {
+      const int pa = part.pt_begin + pl;
+      int off0 = 0;
+      if (pa < part.pt_end) { mask_cur = V.pt_mask[pa]; off0 = V.pt_obs_off[pa]; }
+      prefetch(0, pa, mask_cur, off0);
+    }
+  } else {
+    const int pa = part.pt_begin + pl, pb = pa + Pc;
+    if (p1_thread && pa < part.pt_end) {
+      maskA = V.pt_mask[pa];
+      if (maskA) {
+        XA[0] = V.pts[cur][(size_t)pa * 3]; XA[1] = V.pts[cur][(size_t)pa * 3 + 1]; XA[2] = V.pts[cur][(size_t)pa * 3 + 2];
+        if ((maskA >> sl) & 1u) {
+          oA = V.pt_obs_off[pa] + __popc(maskA & ((1u << sl) - 1u));
+#pragma unroll
+          for (int m = 0; m < M; m++) fA[m] = V.feat[(size_t)m * V.NO + oA];
+          if (M == 2) cidA = (V.obs_cam[oA] >> 30) & 1;
+        }
+      }
+    }
+    if (p1_thread && pb < part.pt_end) { maskB = V.pt_mask[pb]; offB = V.pt_obs_off[pb]; }
   }
   int buf = 0;
   for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += Pc, buf ^= 1) {
@@ -732,26 +760,48 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
     // ---- phase 1a: linearise my observation -------------------------------------------------
     const bool have_pt = p1_thread && pl < np;
     const int p = c0 + pl;
-    const unsigned mask = mask_cur;
+    const unsigned mask = kAsyncPipe ? mask_cur : maskA;
     const bool seen = have_pt && ((mask >> sl) & 1u);
     double X[3] = {0, 0, 0}, f[M];
 #pragma unroll
     for (int q = 0; q < M; q++) f[q] = 0.0;
     int cid = 0;
-    if (p1_thread) {
-      cp_async_wait_all();
-      const double* sd = stageD + ((size_t)buf * NT + t) * kT2StageD;
-      const int* si = stageI + ((size_t)buf * NT + t) * kT2StageI;
-      if (mask) { X[0] = sd[0]; X[1] = sd[1]; X[2] = sd[2]; }
-      if (seen) {
+    if constexpr (kAsyncPipe) {
+      if (p1_thread) {
+        cp_async_wait_all();
+        const double* sd = stageD + ((size_t)buf * NT + t) * kT2StageD;
+        const int* si = stageI + ((size_t)buf * NT + t) * kT2StageI;
+        if (mask) { X[0] = sd[0]; X[1] = sd[1]; X[2] = sd[2]; }
+        if (seen) {
 #pragma unroll
-        for (int q = 0; q < M; q++) f[q] = sd[3 + q];
-        if (M == 2) cid = (si[2] >> 30) & 1;
+          for (int q = 0; q < M; q++) f[q] = sd[3 + q];
+          if (M == 2) cid = (si[2] >> 30) & 1;
+        }
+        const unsigned mask_next = (unsigned)si[0];
+        const int off_next = si[1];
+        prefetch(buf ^ 1, p + Pc, mask_next, off_next);
+        mask_cur = mask_next;
       }
-      const unsigned mask_next = (unsigned)si[0];
-      const int off_next = si[1];
-      prefetch(buf ^ 1, p + Pc, mask_next, off_next);
-      mask_cur = mask_next;
+    } else {
+      X[0] = XA[0]; X[1] = XA[1]; X[2] = XA[2];
+#pragma unroll
+      for (int m = 0; m < M; m++) f[m] = fA[m];
+      cid = cidA;
+      // advance the pipeline: A <- next chunk (using stage B's mask / offset), B <- the chunk after next
+      const int pa = p + Pc, pb = pa + Pc;
+      maskA = maskB;
+      const int offA = offB;
+      maskB = 0;
+      if (p1_thread && pb < part.pt_end) { maskB = V.pt_mask[pb]; offB = V.pt_obs_off[pb]; }
+      if (maskA) {
+        XA[0] = V.pts[cur][(size_t)pa * 3]; XA[1] = V.pts[cur][(size_t)pa * 3 + 1]; XA[2] = V.pts[cur][(size_t)pa * 3 + 2];
+        if ((maskA >> sl) & 1u) {
+          oA = offA + __popc(maskA & ((1u << sl) - 1u));
+#pragma unroll
+          for (int m = 0; m < M; m++) fA[m] = V.feat[(size_t)m * V.NO + oA];
+          if (M == 2) cidA = (V.obs_cam[oA] >> 30) & 1;
+        }
+      }
     }
     double Wm[18];
     double cg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
