@@ -137,7 +137,7 @@ int launch_lin_tile2(const DevView& V, const int* variant_off, cudaStream_t st);
 int lin_tile2_variant(int n_free_local);
 int launch_assemble(const DevView& V, int max_n, cudaStream_t st);
 // h_win_n: host array [nW] of reduced-system sizes (6 * free cameras); h_win_beta: [nW] banded half-bandwidth or 0
-int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st);
+int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st, bool keep_factor = false);
 constexpr int kBandMaxBeta = 63;
 int solve_small_limit();
 int launch_backsub(const DevView& V, cudaStream_t st);

@@ -990,7 +990,7 @@ int compute_covariances(uba_handle* h) {
   h->dense_override = false;
   if (!rc) {
     h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
-    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), zeros.data(), solve_small_limit(), h->stream);
+    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), zeros.data(), solve_small_limit(), h->stream, true);
     h->timing.kernel_launches += launch_cov_blocks(h->V, (int)h->free_list_h.size(), h->max_n, h->d_cov.p, h->stream);
   }
   h->profiling = was_profiling;

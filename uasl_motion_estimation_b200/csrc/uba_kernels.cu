@@ -1156,7 +1156,7 @@ __device__ __forceinline__ bool chol6(double (&L)[6][6], double (&inv)[6]) {
 // the column (all threads), one serial 6x6 factor (one thread), one triangular solve of the rows
 // below (thread per row).  The right-hand side rides along as row n, so the forward substitution is
 // free; the backward substitution is blocked the same way.  Barriers: 3 + 2 per BLOCK column.
-__global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n) {
+__global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n, int keep_factor) {
   extern __shared__ double sm[];
   const int w = blockIdx.x;
   WinState* st = &V.ws[w];
@@ -1173,7 +1173,9 @@ __global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n) {
   double* rhs = V.rhs + (size_t)6 * f0;
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid == 0) s_fail = 0;
-  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; if (j <= i) a[i * ld + j] = A[(size_t)i * n + j]; }
+  // lower triangle in, one row per warp pass (no index divisions)
+  for (int i = tid >> 5; i < n; i += nt >> 5)
+    for (int j = tid & 31; j <= i; j += 32) a[i * ld + j] = A[(size_t)i * n + j];
   for (int i = tid; i < n; i += nt) a[n * ld + i] = rhs[i];
   __syncthreads();
   for (int kb = 0; kb < nf; kb++) {
@@ -1253,13 +1255,218 @@ __global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n) {
   }
   const bool failed = s_fail != 0;
   for (int i = tid; i < n; i += nt) rhs[i] = failed ? 0.0 : z[i];
-  // keep the factor (lower triangle) for the covariance extraction
-  for (int e = tid; e < n * n; e += nt) { const int i = e / n, j = e - i * n; if (j <= i) A[(size_t)i * n + j] = a[i * ld + j]; }
+  // the factor (lower triangle) goes back only when the covariance extraction asks for it
+  if (keep_factor) {
+    for (int i = tid >> 5; i < n; i += nt >> 5)
+      for (int j = tid & 31; j <= i; j += 32) A[(size_t)i * n + j] = a[i * ld + j];
+  }
   if (tid == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
 
 // ---- large windows: blocked right-looking Cholesky in global memory (lower triangle of A) -----
 constexpr int NB = 32;
+
+#ifndef UBA_EMU
+// Dense Cholesky solve for small windows (n <= max_n <= 160), RIGHT-looking with lookahead — the dense sibling of
+// k_chol_banded_la.  Per 6-wide block step: warp 7 (the panel warp) solves the next block's six rows against L_kk,
+// updates that block's 6x6 corner and factors it in registers (pivot tests off the dependent chain), while the 224
+// workers solve all rows below (thread per row, the rhs rides along as one more row), then apply the rank-6 trailing
+// update on the FP64 tensor-core path (DMMA.8x8x4 tiles over the remaining lower triangle, dealt to the 7 worker warps).
+// One named barrier (the panel warp only ARRIVES: it has finished reading the entries the workers then overwrite in
+// place) and one CTA barrier per step, against five in k_chol_small, whose serial 6x6 factor also stalls the whole CTA.
+__global__ void __launch_bounds__(256) k_chol_small_la(DevView V, int max_n, int keep_factor) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.x;
+  WinState* st = &V.ws[w];
+  if (st->done) return;
+  constexpr int NWORK = 224, XS = 9;
+  const int f0 = V.w_free_off[w];
+  const int nf = V.w_free_off[w + 1] - f0;
+  const int n = 6 * nf;
+  if (n == 0 || n > max_n || V.w_beta[w] > 0) return;
+  const int ld = n + 1;                 // odd: conflict-free column walks
+  double* a = sm;                       // [n + 1][ld], row n = right-hand side
+  double* invd = a + (size_t)(n + 1) * ld;   // [n] 1 / L_cc
+  double* Xbuf = invd + n + (n & 1);    // [n + 8][XS] row solves of the current step; columns 6..8 stay zero (DMMA padding)
+  __shared__ int s_fail;
+  __shared__ double s_Lkk[2][36], s_invk[2][6], s_xp[36], s_corner[21];
+  double* A = V.A + V.w_red_off[w];
+  double* rhs = V.rhs + (size_t)6 * f0;
+  const int t = threadIdx.x, nt = blockDim.x;
+  const bool panel = t >= NWORK;
+  const int pl = t - NWORK, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_fail = 0;
+  for (int i = warp; i < n; i += nt >> 5)
+    for (int j = lane; j <= i; j += 32) a[i * ld + j] = A[(size_t)i * n + j];
+  for (int i = t; i < n; i += nt) a[n * ld + i] = rhs[i];
+  for (int i = t; i < (n + 8) * XS; i += nt) Xbuf[i] = 0.0;
+  int cr = 0, ce = pl;                        // corner entry of panel lane pl: (cr, ce), ce <= cr
+  while (ce > cr) { ce -= cr + 1; cr++; }
+  __syncthreads();
+  if (t == NWORK) {                           // prologue: factor of block 0
+    double L[6][6], iv[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) L[r][c] = c <= r ? a[r * ld + c] : 0.0;
+    if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      s_invk[0][r] = iv[r]; invd[r] = iv[r];
+#pragma unroll
+      for (int c = 0; c < 6; c++) { s_Lkk[0][r * 6 + c] = L[r][c]; if (c <= r) a[r * ld + c] = L[r][c]; }
+    }
+  }
+  __syncthreads();
+  for (int kb = 0; kb < nf; kb++) {
+    const int c0 = 6 * kb, par = kb & 1;
+    const int mrows = n - c0 - 6;             // matrix rows below the block; row index mrows of Xbuf is the rhs
+    const double* Lk = s_Lkk[par];
+    const double* ivk = s_invk[par];
+    if (panel) {
+      const bool more = kb + 1 < nf;
+      if (more && pl < 6) {
+        const double* row = a + (c0 + 6 + pl) * ld + c0;
+        double x[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) x[c] = row[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], Lk[m * 6 + c], x[m]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) s_xp[pl * 6 + c] = x[c];
+      }
+      __syncwarp();
+      asm volatile("bar.arrive 1, 256;" ::: "memory");   // the workers may now overwrite these rows' entries in place
+      if (more) {
+        if (pl < 21) {
+          double v = a[(c0 + 6 + cr) * ld + c0 + 6 + ce];
+#pragma unroll
+          for (int m = 0; m < 6; m++) v = fma(-s_xp[cr * 6 + m], s_xp[ce * 6 + m], v);
+          s_corner[pl] = v;
+        }
+        __syncwarp();
+        if (pl == 0) {
+          double L[6][6], iv[6];
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) L[r][c] = c <= r ? s_corner[r * (r + 1) / 2 + c] : 0.0;
+          if (!chol6(L, iv)) s_fail = 1;
+#pragma unroll
+          for (int r = 0; r < 6; r++) {
+            s_invk[par ^ 1][r] = iv[r]; invd[c0 + 6 + r] = iv[r];
+#pragma unroll
+            for (int c = 0; c < 6; c++) { s_Lkk[par ^ 1][r * 6 + c] = L[r][c]; if (c <= r) a[(c0 + 6 + r) * ld + c0 + 6 + c] = L[r][c]; }
+          }
+        }
+      }
+    } else {
+      // rows below the block and the rhs: X L_kk^T = A (at most one row per thread: n + 1 - c0 - 6 <= 155 < 224)
+      const int r = t;
+      const bool have = r <= mrows;
+      const int i = r < mrows ? c0 + 6 + r : n;
+      double x[6];
+      if (have) {
+        const double* row = a + i * ld + c0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) x[c] = row[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          x[c] *= ivk[c];
+#pragma unroll
+          for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], Lk[m * 6 + c], x[m]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) Xbuf[r * XS + c] = x[c];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (have) {
+        double* row = a + i * ld + c0;
+#pragma unroll
+        for (int c = 0; c < 6; c++) row[c] = x[c];
+      }
+      // trailing update of rows c0+6 .. n-1 and the rhs row: 8x8 tiles (I >= J) over mrows + 1 rows x mrows columns
+      if (mrows > 0) {
+        const int NBt = (mrows + 1 + 7) >> 3, ntile = NBt * (NBt + 1) / 2;
+        const int fr = lane >> 2, fk = lane & 3;
+        // four tiles in flight per warp: a tile is a latency chain (fragment loads -> two dependent DMMAs -> read-modify-
+        // write of the matrix), so independent tiles are interleaved by hand
+        constexpr int UN = 4;
+        int I = 0, J = warp;
+        while (J > I) { J -= I + 1; I++; }
+        for (int idx = warp; idx < ntile; idx += 7 * UN) {
+          int tI[UN], tJ[UN];
+          double d0[UN], d1[UN];
+#pragma unroll
+          for (int u = 0; u < UN; u++) {
+            tI[u] = idx + 7 * u < ntile ? I : -1; tJ[u] = J;
+            J += 7;
+            while (J > I) { J -= I + 1; I++; }
+          }
+#pragma unroll
+          for (int u = 0; u < UN; u++) {
+            d0[u] = 0.0; d1[u] = 0.0;
+            if (tI[u] >= 0) {                     // warp-uniform
+              const double* xa = Xbuf + (8 * tI[u] + fr) * XS + fk;
+              const double* xb = Xbuf + (8 * tJ[u] + fr) * XS + fk;
+              dmma884(d0[u], d1[u], xa[0], xb[0]);
+              dmma884(d0[u], d1[u], xa[4], xb[4]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UN; u++) {
+            if (tI[u] < 0) continue;
+            const int ti = 8 * tI[u] + fr, tk = 8 * tJ[u] + 2 * fk;
+            if (ti >= 6 && ti <= mrows) {       // ti < 6: the next block's rows, whose corner belongs to the panel warp
+              double* dst = a + (ti < mrows ? c0 + 6 + ti : n) * ld + c0 + 6 + tk;
+              const int kmax = ti < mrows ? ti : mrows - 1;
+              if (tk <= kmax) dst[0] -= d0[u];
+              if (tk + 1 <= kmax) dst[1] -= d1[u];
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // backward substitution L^T x = z (z sits in row n), blocked
+  double* z = a + n * ld;
+  for (int kb = nf - 1; kb >= 0; kb--) {
+    const int c0 = 6 * kb;
+    if (t == 0) {
+      double xb[6];
+#pragma unroll
+      for (int c = 5; c >= 0; c--) {
+        double v = z[c0 + c];
+#pragma unroll
+        for (int m = 0; m < 6; m++) if (m > c) v = fma(-a[(c0 + m) * ld + c0 + c], xb[m], v);
+        xb[c] = v * invd[c0 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) z[c0 + c] = xb[c];
+    }
+    __syncthreads();
+    for (int i = t; i < c0; i += nt) {
+      double v = z[i];
+#pragma unroll
+      for (int c = 0; c < 6; c++) v = fma(-a[(c0 + c) * ld + i], z[c0 + c], v);
+      z[i] = v;
+    }
+    __syncthreads();
+  }
+  const bool failed = s_fail != 0;
+  for (int i = t; i < n; i += nt) rhs[i] = failed ? 0.0 : z[i];
+  if (keep_factor) {
+    for (int i = warp; i < n; i += nt >> 5)
+      for (int j = lane; j <= i; j += 32) A[(size_t)i * n + j] = a[i * ld + j];
+  }
+  if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
+}
+#endif  // UBA_EMU
 
 __global__ void __launch_bounds__(256) k_chol_diag(DevView V, int w, int j0) {
   __shared__ double a[NB][NB + 1];
@@ -3138,7 +3345,7 @@ int launch_assemble(const DevView& V, int max_n, cudaStream_t st) {
 
 int solve_small_limit() { return 160; }
 
-int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st) {
+int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st, bool keep_factor) {
   int launches = 0;
   int small_max = 0, n_large = 0;
   for (int w = 0; w < V.nW; w++) {
@@ -3157,7 +3364,18 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
       cudaFuncSetAttribute(k_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = smem;
     }
-    UBA_LAUNCH(k_chol_small, V.nW, 256, smem, st, V, max_small_n);
+    static const bool use_small_la = [] { const char* e = getenv("UBA_SMALL_LA"); return !(e && e[0] == '0'); }();
+    if (use_small_la) {
+      const size_t smem_la = smem + ((size_t)(small_max + 8) * 9 + 2) * sizeof(double);
+      static size_t configured_la = 0;
+      if (smem_la > configured_la) {
+        cudaFuncSetAttribute(k_chol_small_la, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_la);
+        configured_la = smem_la;
+      }
+      UBA_LAUNCH(k_chol_small_la, V.nW, 256, smem_la, st, V, max_small_n, keep_factor ? 1 : 0);
+    } else {
+      UBA_LAUNCH(k_chol_small, V.nW, 256, smem, st, V, max_small_n, keep_factor ? 1 : 0);
+    }
     launches++;
   }
   if (n_large) {
