@@ -327,3 +327,32 @@ def test_ingest_paths(gpu_lib, oracle, variant):
     rc, _ = h.optimise(2)
     oo = oracle.optimise(win, cfg, 2)
     assert rc == 0 and rel(h.cameras(), oo["cams"]) < STATE_TOL and rel(h.points(), oo["pts"]) < STATE_TOL
+
+
+def test_small_window_left_looking_solver_fallback():
+    """UBA_SMALL_LA=0 selects the left-looking dense solver for small windows; same trajectory as the oracle (c1 and c2 shapes,
+    and the covariance pass, which asks the solver to keep its factor)."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import oracle_binding as ob
+        from uasl_motion_estimation_b200 import capi, synth
+        rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+        for name, scale in (("c1", 0.5), ("c2", 0.1)):
+            win = synth.config_window(name, scale=scale)
+            cfg = capi.default_config(fixed_iterations=4, compute_covariance=1)
+            h = capi.Handle(cfg); h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+            rc, _ = h.optimise(2); o = ob.optimise(win, cfg, 2)
+            assert rc == 0 and rel(h.cameras(), o["cams"]) < 1e-6 and rel(h.points(), o["pts"]) < 1e-6
+            cov = h.pose_covariances(); cams, pts = h.cameras(), h.points()
+            L = ob.linearize(win, cfg, 2, -1.0, cams=cams, pts=pts, jacobi_scale=np.ones(6 * win.n_cams + 3 * win.n_pts))
+            Sinv = np.linalg.inv(L["S"]); fc = h.tables(2)["free_cam"]
+            for c in range(win.n_cams):
+                if fc[c] >= 0:
+                    ref = Sinv[6 * fc[c]:6 * fc[c] + 6, 6 * fc[c]:6 * fc[c] + 6]
+                    assert np.abs(cov[c] - ref).max() <= 1e-7 * np.abs(ref).max(), c
+        print("OK")
+    """) % (str(ROOT), str(ROOT / "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, UBA_SMALL_LA="0"))
+    assert r.returncode == 0 and "OK" in r.stdout, (r.stdout + r.stderr)[-2000:]
