@@ -116,7 +116,7 @@ struct uba_handle {
   int prepared_fixed = -1;
   std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n, win_beta;
   bool dense_override = false;                // covariance / parity dumps: every window uses the dense accumulator layout
-  std::vector<std::pair<size_t, size_t>> sum_ranges;   // (offset, count) pieces of the accumulator block summed over ranks
+  std::vector<std::pair<size_t, size_t>> sum_ranges, zero_ranges;   // (offset, count) pieces of the accumulator block summed over ranks
   std::vector<char> win_infeasible;           // a window whose start violates the point bounds
   DevBuf<int32_t> d_w_beta;
   std::vector<int64_t> w_red_off_h;
@@ -144,7 +144,7 @@ struct uba_handle {
   DevBuf<IterRec> d_recs;
   size_t acc_sum1 = 0;   // doubles reduced (sum) after linearise: Sacc|Bacc|vacc|zh|w_lin
   size_t acc_total = 0;  // all accumulator doubles (one memset)
-  size_t off_Bacc = 0, off_vacc = 0, off_zh = 0, off_wlin = 0, off_wpost = 0, off_wmax = 0, off_wloc = 0;
+  size_t off_Bacc = 0, off_vacc = 0, off_zh = 0, off_wlin = 0, off_sacc = 0, off_wpost = 0, off_wrmax = 0, off_wmax = 0, off_wloc = 0;
   DevView V{};
   std::vector<WinState> ws_h;
   // comm
@@ -450,13 +450,17 @@ int prepare(uba_handle* h, int fixed_frames) {
   CU(h, cudaMemcpyAsync(h->d_w_free_off.p, h->w_free_off_h.data(), sizeof(int32_t) * (nW + 1), cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_w_red_off.p, h->w_red_off_h.data(), sizeof(int64_t) * (nW + 1), cudaMemcpyHostToDevice, h->stream));
   // accumulator block: [Sacc | Bacc | vacc | zh | w_lin] [w_post] [w_max] [w_loc]
-  h->off_Bacc = red;
+  // layout: [B | v | zh | w_lin] [S_acc of every window] [w_post | w_rmax] [w_max] [w_loc].  The per-camera tail comes FIRST so
+  // that it is contiguous with the band of the first window: one allreduce per linearisation on a point-sharded c4.
+  h->off_Bacc = 0;
   h->off_vacc = h->off_Bacc + (size_t)NC * 36;
   h->off_zh = h->off_vacc + (size_t)NC * 6;
   h->off_wlin = h->off_zh + (size_t)NC * 6;
-  h->acc_sum1 = h->off_wlin + (size_t)nW * WL_COUNT;
+  h->off_sacc = h->off_wlin + (size_t)nW * WL_COUNT;
+  h->acc_sum1 = h->off_sacc + red;
   h->off_wpost = h->acc_sum1;
-  h->off_wmax = h->off_wpost + (size_t)nW * WP_COUNT;
+  h->off_wrmax = h->off_wpost + (size_t)nW * WP_COUNT;            // per-rank gradient max-norms (summed: every slot has one writer)
+  h->off_wmax = h->off_wrmax + (h->comm ? (size_t)nW * h->n_ranks : 0);
   h->off_wloc = h->off_wmax + (size_t)nW;
   h->acc_total = h->off_wloc + (size_t)nW * WC_COUNT;
   CU(h, h->d_acc.reserve(h->acc_total));
@@ -468,11 +472,15 @@ int prepare(uba_handle* h, int fixed_frames) {
     if (!h->sum_ranges.empty() && h->sum_ranges.back().first + h->sum_ranges.back().second == off) h->sum_ranges.back().second += cnt;
     else h->sum_ranges.emplace_back(off, cnt);
   };
+  add_range(0, h->off_sacc);
   for (int w = 0; w < nW; w++) {
     const size_t nn = (size_t)h->win_n[w];
-    add_range((size_t)h->w_red_off_h[w], h->win_beta[w] > 0 ? nn * (size_t)(h->win_beta[w] + 1) : nn * nn);
+    add_range(h->off_sacc + (size_t)h->w_red_off_h[w], h->win_beta[w] > 0 ? nn * (size_t)(h->win_beta[w] + 1) : nn * nn);
   }
-  add_range(red, h->acc_sum1 - red);
+  // ... and what is zeroed before each linearisation: the same pieces plus the per-window scalars at the end
+  h->zero_ranges = h->sum_ranges;
+  if (!h->zero_ranges.empty() && h->zero_ranges.back().first + h->zero_ranges.back().second == h->off_wpost) h->zero_ranges.back().second += h->acc_total - h->off_wpost;
+  else h->zero_ranges.emplace_back(h->off_wpost, h->acc_total - h->off_wpost);
   CU(h, h->d_A.reserve(red));
   CU(h, h->d_rhs.reserve(6 * nfree));
   TT("prepare: free cams, band")
@@ -499,7 +507,7 @@ int prepare(uba_handle* h, int fixed_frames) {
   V.gen_pts = h->d_gen_pts.p; V.n_gen = h->use_tile ? (int)h->gen_pts_h.size() : 0;
   V.w_beta = h->d_w_beta.p;
   V.free_cam = h->d_free_cam.p; V.free_list = h->d_free_list.p; V.w_free_off = h->d_w_free_off.p; V.w_red_off = h->d_w_red_off.p;
-  V.Sacc = h->d_acc.p; V.Bacc = h->d_acc.p + h->off_Bacc; V.vacc = h->d_acc.p + h->off_vacc; V.zh = h->d_acc.p + h->off_zh;
+  V.Sacc = h->d_acc.p + h->off_sacc; V.Bacc = h->d_acc.p + h->off_Bacc; V.vacc = h->d_acc.p + h->off_vacc; V.zh = h->d_acc.p + h->off_zh;
   V.w_lin = h->d_acc.p + h->off_wlin; V.w_post = h->d_acc.p + h->off_wpost; V.w_max = h->d_acc.p + h->off_wmax;
   V.w_loc = h->d_acc.p + h->off_wloc;
   V.A = h->d_A.p; V.rhs = h->d_rhs.p;
@@ -559,12 +567,8 @@ int launch_linearizers(uba_handle* h, const DebugOut& dbg) {
 // the linearise + Schur pass (the roofline kernel of the hot path)
 int run_linearize(uba_handle* h, const DebugOut& dbg) {
   // zero what this pass accumulates into: for banded windows only the band of the Schur accumulator is ever touched
-  if (!h->dense_override && h->sum_ranges.size() <= 4) {
-    for (size_t i = 0; i < h->sum_ranges.size(); i++) {
-      const auto& r = h->sum_ranges[i];
-      const size_t cnt = i + 1 == h->sum_ranges.size() ? h->acc_total - r.first : r.second;   // the last range runs into the per-window tails
-      CU(h, cudaMemsetAsync(h->d_acc.p + r.first, 0, cnt * sizeof(double), h->stream));
-    }
+  if (!h->dense_override && h->zero_ranges.size() <= 4) {
+    for (const auto& r : h->zero_ranges) CU(h, cudaMemsetAsync(h->d_acc.p + r.first, 0, r.second * sizeof(double), h->stream));
   } else {
     CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
   }
@@ -605,10 +609,12 @@ int run_iteration(uba_handle* h) {
   }
   if (h->comm) {
     PhaseTimer tc(h, 4);
-    rc = allreduce(h, h->d_acc.p + h->off_wpost, (size_t)h->nW * WP_COUNT, kNcclSum);
+    // one collective for {candidate cost, model change, norms} (sums) and the gradient max-norm: every rank writes its
+    // max into its own slot of w_rmax, the slots are summed with the rest, the max over slots is taken locally
+    h->timing.kernel_launches += launch_rank_max(h->d_acc.p + h->off_wmax, h->d_acc.p + h->off_wrmax, h->nW, h->rank, h->n_ranks, 0, h->stream);
+    rc = allreduce(h, h->d_acc.p + h->off_wpost, (size_t)h->nW * (WP_COUNT + h->n_ranks), kNcclSum);
     if (rc) return rc;
-    rc = allreduce(h, h->d_acc.p + h->off_wmax, (size_t)h->nW, kNcclMax);
-    if (rc) return rc;
+    h->timing.kernel_launches += launch_rank_max(h->d_acc.p + h->off_wmax, h->d_acc.p + h->off_wrmax, h->nW, h->rank, h->n_ranks, 1, h->stream);
     tc.stop();
   }
   {
@@ -623,7 +629,10 @@ int run_iteration(uba_handle* h) {
 // (no per-phase profiling, no NCCL on this handle).
 int run_iteration_fast(uba_handle* h) {
 #ifndef UBA_EMU
-  if (!h->profiling && !h->comm) {
+  // Point-sharded handles launch directly: capturing the NCCL collectives into the graph works (UBA_COMM_GRAPH=1,
+  // results identical) but measured SLOWER on 2 B200 (0.44 vs 0.36 ms per iteration)
+  static const bool comm_graph = [] { const char* e = getenv("UBA_COMM_GRAPH"); return e && e[0] == '1'; }();
+  if (!h->profiling && (!h->comm || comm_graph)) {
     // the graph bakes the device view in by value: any change of it (sizes, pointers, solver settings) invalidates it
     if (h->graph_exec && std::memcmp(&h->V, &h->graph_V, sizeof(DevView)) != 0) drop_graph(h);
     if (!h->graph_exec) {
@@ -1341,6 +1350,7 @@ int uba_comm_init(uba_handle* h, const char id[UBA_NCCL_UNIQUE_ID_BYTES], int ra
   const int rc = h->nccl.CommInitRank(&h->comm, n_ranks, u, rank);
   if (rc != 0) { h->comm = nullptr; return fail(h, UBA_ERR_NCCL, "ncclCommInitRank failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?"); }
   h->rank = rank; h->n_ranks = n_ranks;
+  h->prepared_fixed = -1;                     // the accumulator layout depends on the communicator
   return UBA_OK;
 }
 

@@ -3200,6 +3200,17 @@ __global__ void k_ingest_feats(const double* __restrict__ raw, const int32_t* __
   }
 }
 
+// point-sharded runs: per-window gradient max-norm through a SUM allreduce — scatter (gather = 0): this rank's max into its
+// slot; gather (gather = 1, after the allreduce): max over the ranks' slots
+__global__ void k_rank_max(double* w_max, double* w_rmax, int nW, int rank, int n_ranks, int gather) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nW) return;
+  if (!gather) { w_rmax[(size_t)w * n_ranks + rank] = w_max[w]; return; }
+  double m = 0.0;
+  for (int r = 0; r < n_ranks; r++) m = fmax(m, w_rmax[(size_t)w * n_ranks + r]);
+  w_max[w] = m;
+}
+
 __global__ void k_l2_flush(double* buf, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = (double)i;
 }
@@ -3476,6 +3487,11 @@ int launch_ingest_feats(const double* raw, const int32_t* src, double* feat, int
   if (NO == 0) return 0;
   const int64_t blocks = (NO + 255) / 256;
   UBA_LAUNCH(k_ingest_feats, (int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st, raw, src, feat, NO, M);
+  return 1;
+}
+
+int launch_rank_max(double* w_max, double* w_rmax, int nW, int rank, int n_ranks, int gather, cudaStream_t st) {
+  UBA_LAUNCH(k_rank_max, (nW + 127) / 128, 128, 0, st, w_max, w_rmax, nW, rank, n_ranks, gather);
   return 1;
 }
 
