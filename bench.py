@@ -156,6 +156,8 @@ def run_reference(args, rank, world):
         sample = f"the full {name} window, one LM iteration per step"
     win = wins[0]
     cfg = capi.default_config(lib, loss_kind=synth.CONFIGS[name]["loss"])
+    # all the host threads it can use — torchrun pins OMP_NUM_THREADS=1, and only rank 0 runs this arm
+    ob.lib().uba_ref_set_threads(os.cpu_count() or 1)
     threads = ob.lib().uba_ref_max_threads()
     for _ in range(args.warmup):
         ob.time_iteration(win, cfg, 2, 1)
@@ -194,6 +196,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # torchrun pins OMP_NUM_THREADS=1 for every rank; the ingest path of libuba is OpenMP-parallel, so give each rank its share of
+    # the host cores instead (before libgomp initialises)
+    if world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import torch
     import torch.distributed as dist
     from uasl_motion_estimation_b200 import capi, synth
