@@ -169,3 +169,23 @@ def test_all_cameras_fixed_moves_only_points(emu_lib, oracle):
     o = oracle.optimise(win, cfg, win.n_cams)
     np.testing.assert_array_equal(h.cameras(), win.cams_init)
     assert rel(h.points(), o["pts"]) < 1e-6
+
+
+def test_features_that_are_not_floats_take_the_double_upload(emu_lib, oracle):
+    """The reference's features are float detections widened to double, and such rows travel to the GPU as float32 (exactly).
+    Rows with any value that is not a float must take the double path and still match the oracle on the same doubles."""
+    base = synth.config_window("c2", scale=0.01, lib=emu_lib)
+    feats = base.feats + 1e-7 * np.sin(np.arange(base.feats.size)).reshape(base.feats.shape)   # no longer float32-representable
+    assert (feats.astype(np.float32).astype(np.float64) != feats).any()
+    win = synth.Window(4, base.cams_gt, base.cams_init, base.pts_gt, base.pts_init, np.ascontiguousarray(feats), base.cam_idx, base.pt_idx,
+                       base.cam_id, 2, base.calib)
+    cfg = capi.default_config(emu_lib, fixed_iterations=3)
+    h = capi.Handle(cfg, lib=emu_lib)
+    h.set_problem(4, win.cams_init, win.pts_init, win.feats, win.cam_idx, win.pt_idx, win.cam_id, win.calib)
+    g = h.linearize(2, 1e4); o = oracle.linearize(win, cfg, 2, 1e4)
+    for k in BLOCKS:
+        assert rel(g[k], o[k]) < BLOCK_TOL, k
+    # the residuals see the perturbation: they differ from the float-rounded window's by more than the parity tolerance
+    hb = capi.Handle(cfg, lib=emu_lib)
+    hb.set_problem(4, base.cams_init, base.pts_init, base.feats, base.cam_idx, base.pt_idx, base.cam_id, base.calib)
+    assert rel(hb.linearize(2, 1e4)["residuals"], g["residuals"]) > 1e-9

@@ -147,7 +147,7 @@ int launch_cov_state(const DevView& V, int enter, cudaStream_t st);
 int launch_cov_blocks(const DevView& V, int n_free_total, int max_n, double* cov36, cudaStream_t st);
 int launch_l2_flush(double* buf, size_t n, cudaStream_t st);
 int launch_rank_max(double* w_max, double* w_rmax, int nW, int rank, int n_ranks, int gather, cudaStream_t st);
-int launch_ingest_feats(const double* raw, const int32_t* src, double* feat, int64_t NO, int M, cudaStream_t st);
+int launch_ingest_feats(const void* raw, const int32_t* src, double* feat, int64_t NO, int M, int raw_is_f32, cudaStream_t st);
 int launch_dfma_probe(double* out, int iters, cudaStream_t st);
 
 }  // namespace uba

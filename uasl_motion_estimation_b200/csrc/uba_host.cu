@@ -243,7 +243,6 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     int item_begin = -1, min_len = 0;
     bool uni_range = true;   // the union is the camera range [ulo, uhi] (true as long as only contiguous tracks were merged)
     int ulo = 0, uhi = -1;
-    int run_lo = -1, run_hi = -1;   // (lo, hi) of the previous point when it was a contiguous tile point, else -1
     uni.clear();
     auto close_item = [&](int end) {
       if (item_begin < 0) return;
@@ -258,11 +257,15 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       if (k == 0) continue;
       const int lo = h->pt_lo[s], hi = h->pt_hi[s];
       if (h->pt_contig[s]) {
-        // the same contiguous track as the previous tile point changes nothing in the item: same decision
-        if (lo == run_lo && hi == run_hi) { h->pt_mask_h[s] = 1u; tile_points++; continue; }
-        run_lo = run_hi = -1;
+        // a run of identical contiguous tracks (the points are sorted by first / last keyframe) gets one decision
+        int e = s + 1;
+        while (e < s1 && h->pt_lo[e] == lo && h->pt_hi[e] == hi && h->pt_contig[e] && h->pt_obs_off_int[e + 1] > h->pt_obs_off_int[e]) e++;
         const int nfree = hi - std::max(lo, fixed_frames) + 1;
-        if (k > kTileMaxLocal || nfree > kTileMaxFree) { h->gen_pts_h.push_back(s); continue; }
+        if (k > kTileMaxLocal || nfree > kTileMaxFree) {
+          for (int q = s; q < e; q++) h->gen_pts_h.push_back(q);
+          s = e - 1;
+          continue;
+        }
         bool ok = item_begin >= 0 && uni_range;
         int nlo = lo, nhi = hi;
         if (ok) {
@@ -274,11 +277,11 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
         }
         if (!ok) { close_item(s); uni_range = true; ulo = lo; uhi = hi; min_len = k; item_begin = s; }
         else { ulo = nlo; uhi = nhi; min_len = std::min(min_len, k); }
-        h->pt_mask_h[s] = 1u; tile_points++;   // 1u marks a tile point until the mask pass below
-        run_lo = lo; run_hi = hi;
+        std::fill(h->pt_mask_h.begin() + s, h->pt_mask_h.begin() + e, 1u);   // 1u marks a tile point until the mask pass below
+        tile_points += (size_t)(e - s);
+        s = e - 1;
         continue;
       }
-      run_lo = run_hi = -1;
       // general track: explicit camera list
       cams_p.clear();
       bool ascending = true;
@@ -900,13 +903,29 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   // Feature rows are staged AS THEY ARE (one streaming copy into pinned memory) and permuted + transposed into the
   // SoA planes on the device (k_ingest_feats); the host only builds the slot -> caller-observation map.
   const bool canonical = pt_permuted == 0 && obs_permuted == 0;
+  // Feature coordinates come from float detections widened to double in the reference (cv::Point2f, BundleAdjuster.h:371):
+  // when every value is exactly a float — checked here, in the same pass — the rows are staged and uploaded as float32
+  // (half the bytes) and widened on the device, bit for bit the same doubles.  Anything else is staged as doubles.
+  bool feat_f32 = true;
   {
     const size_t nd = (size_t)NO * M, chunk = (size_t)1 << 16;
     const int64_t nchunks = (int64_t)((nd + chunk - 1) / chunk);
-#pragma omp parallel for schedule(static)
+    float* hf32 = reinterpret_cast<float*>(h->h_feat.p);
+    int not_float = 0;
+#pragma omp parallel for schedule(static) reduction(+ : not_float)
     for (int64_t c = 0; c < nchunks; c++) {
       const size_t b = (size_t)c * chunk, e = std::min(nd, b + chunk);
-      std::memcpy(h->h_feat.p + b, feats + b, sizeof(double) * (e - b));
+      int bad_here = 0;
+      for (size_t i = b; i < e; i++) { const float v = (float)feats[i]; hf32[i] = v; bad_here |= ((double)v != feats[i]); }
+      not_float += bad_here;
+    }
+    if (not_float) {
+      feat_f32 = false;
+#pragma omp parallel for schedule(static)
+      for (int64_t c = 0; c < nchunks; c++) {
+        const size_t b = (size_t)c * chunk, e = std::min(nd, b + chunk);
+        std::memcpy(h->h_feat.p + b, feats + b, sizeof(double) * (e - b));
+      }
     }
   }
   if (canonical) {
@@ -958,10 +977,10 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   }
   if (NO) {
     // raw rows into scratch (Zbuf is idle until the first iteration), then gather + transpose on the device
-    CU(h, cudaMemcpyAsync(h->d_Zbuf.p, h->h_feat.p, sizeof(double) * NO * M, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->d_Zbuf.p, h->h_feat.p, (feat_f32 ? sizeof(float) : sizeof(double)) * NO * M, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(h->d_obs_src.p, h->h_obs_internal.p, sizeof(int32_t) * NO, cudaMemcpyHostToDevice, st));
     CU(h, cudaMemcpyAsync(h->d_obs_cam.p, h->h_obs_cam.p, sizeof(int32_t) * NO, cudaMemcpyHostToDevice, st));
-    h->timing.kernel_launches += launch_ingest_feats(h->d_Zbuf.p, h->d_obs_src.p, h->d_feat.p, NO, M, st);
+    h->timing.kernel_launches += launch_ingest_feats(h->d_Zbuf.p, h->d_obs_src.p, h->d_feat.p, NO, M, feat_f32 ? 1 : 0, st);
   }
   int rc = upload_state(h);
   if (rc) return rc;

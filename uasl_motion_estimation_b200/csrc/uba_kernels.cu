@@ -3192,11 +3192,12 @@ int launch_cov_blocks(const DevView& V, int n_free_total, int max_n, double* cov
 // ---------------------------------------------------------------------------------------------
 // Ingest: feature rows arrive as the caller stores them (AoS [NO][M], caller observation order; the reference's
 // Observation<N>::data, BundleAdjuster.h:23-33).  Internal slot i holds caller observation src[i]; the SoA planes
-// feat[m][i] are what the linearisers read coalesced.
-__global__ void k_ingest_feats(const double* __restrict__ raw, const int32_t* __restrict__ src, double* __restrict__ feat, int64_t NO, int M) {
+// feat[m][i] are what the linearisers read coalesced.  The rows travel as float32 when every value is exactly a float.
+template <typename TRaw>
+__global__ void k_ingest_feats(const TRaw* __restrict__ raw, const int32_t* __restrict__ src, double* __restrict__ feat, int64_t NO, int M) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < NO; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t o = src[i];
-    for (int m = 0; m < M; m++) feat[(size_t)m * NO + i] = raw[(size_t)o * M + m];
+    for (int m = 0; m < M; m++) feat[(size_t)m * NO + i] = (double)raw[(size_t)o * M + m];
   }
 }
 
@@ -3483,10 +3484,12 @@ int launch_lm_update(const DevView& V, cudaStream_t st) {
   return 1;
 }
 
-int launch_ingest_feats(const double* raw, const int32_t* src, double* feat, int64_t NO, int M, cudaStream_t st) {
+int launch_ingest_feats(const void* raw, const int32_t* src, double* feat, int64_t NO, int M, int raw_is_f32, cudaStream_t st) {
   if (NO == 0) return 0;
   const int64_t blocks = (NO + 255) / 256;
-  UBA_LAUNCH(k_ingest_feats, (int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st, raw, src, feat, NO, M);
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  if (raw_is_f32) UBA_LAUNCH(k_ingest_feats<float>, grid, 256, 0, st, (const float*)raw, src, feat, NO, M);
+  else UBA_LAUNCH(k_ingest_feats<double>, grid, 256, 0, st, (const double*)raw, src, feat, NO, M);
   return 1;
 }
 
