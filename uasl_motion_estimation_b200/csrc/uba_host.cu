@@ -116,6 +116,10 @@ struct uba_handle {
   int prepared_fixed = -1;
   std::vector<int32_t> free_cam_h, free_list_h, w_free_off_h, win_n, win_beta;
   bool dense_override = false;                // covariance / parity dumps: every window uses the dense accumulator layout
+  // ingest scratch, kept across calls: fresh multi-megabyte vectors page-fault on every call (~1 ms per c4 window on a VM)
+  std::vector<int32_t> sc_cnt, sc_lo, sc_hi, sc_hist;
+  std::vector<int64_t> sc_first;
+  std::vector<char> sc_contig;
   std::vector<std::pair<size_t, size_t>> sum_ranges, zero_ranges;   // (offset, count) pieces of the accumulator block summed over ranks
   std::vector<char> win_infeasible;           // a window whose start violates the point bounds
   DevBuf<int32_t> d_w_beta;
@@ -705,7 +709,9 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   // validate + count (parallel inside a window when there are few windows)
   int bad = 0;
   const bool few = nW < 8;
-  std::vector<int32_t> cnt((size_t)NP, 0);
+  h->sc_cnt.resize((size_t)NP);
+  h->sc_first.resize((size_t)NP + nW + 1);
+  std::vector<int32_t>& cnt = h->sc_cnt;
   std::vector<char> win_canonical(nW, 0);
   for (int w = 0; w < nW; w++) {
     const int nc = wc[w + 1] - wc[w], np = wp[w + 1] - wp[w];
@@ -733,7 +739,9 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     win_canonical[w] = !unsorted && !unsorted_cam;   // already point-major and camera-ascending inside a point
     if (!unsorted) {
       // point-major input (the reference's order): counts are run lengths, no atomics needed
-      std::vector<int64_t> first((size_t)np + 1, -1);
+      int64_t* first = h->sc_first.data() + wp[w] + w;     // np + 1 slots of this window
+#pragma omp parallel for schedule(static) if (parallel)
+      for (int j = 0; j <= np; j++) first[j] = -1;
       const bool ident = win_canonical[w] != 0;
 #pragma omp parallel for schedule(static) if (parallel)
       for (int64_t o = o0; o < o1; o++) {
@@ -742,8 +750,11 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       }
       first[np] = o1;
       for (int j = np - 1; j >= 0; j--) if (first[j] < 0) first[j] = first[j + 1];
+#pragma omp parallel for schedule(static) if (parallel)
       for (int j = 0; j < np; j++) c[j] = (int32_t)(first[j + 1] - first[j]);
     } else {
+#pragma omp parallel for schedule(static) if (parallel)
+      for (int j = 0; j < np; j++) c[j] = 0;
 #pragma omp parallel for schedule(static) if (parallel)
       for (int64_t o = o0; o < o1; o++) {
 #pragma omp atomic
@@ -763,8 +774,9 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   TT("validate+count")
   // Canonical order: point-major (stable), camera-ascending inside a point.  The reference's own
   // initialiseObservations already produces it (BundleAdjuster.h:364-374): detect that and skip the sort.
-  std::vector<int32_t> lo_c((size_t)NP, INT_MAX), hi_c((size_t)NP, -1);   // caller point order
-  std::vector<char> contig_c((size_t)NP, 1);
+  h->sc_lo.resize((size_t)NP); h->sc_hi.resize((size_t)NP); h->sc_contig.resize((size_t)NP);
+  std::vector<int32_t>& lo_c = h->sc_lo; std::vector<int32_t>& hi_c = h->sc_hi;   // caller point order; INT_MAX / -1 without observations
+  std::vector<char>& contig_c = h->sc_contig;
   int pt_permuted = 0;                        // windows whose internal point order differs from the caller's
   int obs_permuted = 0;                       // windows whose observations had to be reordered
   auto order_window = [&](int w, bool parallel) {
@@ -795,6 +807,8 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
         char cg = 1;
         for (int32_t* i = b + 1; i < e; i++) if (cam_idx[*i] != cam_idx[*(i - 1)] + 1) cg = 0;
         contig_c[p0 + j] = cg;
+      } else {
+        lo_c[p0 + j] = INT_MAX; hi_c[p0 + j] = -1; contig_c[p0 + j] = 1;
       }
     }
     // internal point order: stable by (lowest camera, highest camera), unobserved points last
@@ -816,7 +830,8 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       for (int j = 0; j < np; j++) if (hi_c[p0 + j] >= 0) span = std::max(span, hi_c[p0 + j] - lo_c[p0 + j] + 1);
       const int64_t nk = (int64_t)nc * span + 1;   // last key: unobserved points
       auto ckey = [&](int j) -> int64_t { return hi_c[p0 + j] < 0 ? nk - 1 : (int64_t)lo_c[p0 + j] * span + (hi_c[p0 + j] - lo_c[p0 + j]); };
-      std::vector<int32_t> hist;
+      std::vector<int32_t> hist_local;
+      std::vector<int32_t>& hist = parallel ? h->sc_hist : hist_local;   // windows sorted concurrently need their own
       int T = 1;
 #pragma omp parallel if (parallel)
       {
