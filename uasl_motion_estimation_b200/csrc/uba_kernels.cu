@@ -1296,8 +1296,23 @@ __global__ void __launch_bounds__(256) k_chol_small_la(DevView V, int max_n, int
   const bool panel = t >= NWORK;
   const int pl = t - NWORK, lane = t & 31, warp = t >> 5;
   if (t == 0) s_fail = 0;
-  for (int i = warp; i < n; i += nt >> 5)
-    for (int j = lane; j <= i; j += 32) a[i * ld + j] = A[(size_t)i * n + j];
+  // lower triangle in: four rows x five 32-column pieces per warp pass, all loads issued before the first store (a plain
+  // load-store loop costs one memory round trip per element)
+  for (int i0 = warp; i0 < n; i0 += 4 * (nt >> 5)) {
+    double v[4][5];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * (nt >> 5);
+#pragma unroll
+      for (int c = 0; c < 5; c++) { const int j = lane + 32 * c; v[u][c] = (i < n && j <= i) ? A[(size_t)i * n + j] : 0.0; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * (nt >> 5);
+#pragma unroll
+      for (int c = 0; c < 5; c++) { const int j = lane + 32 * c; if (i < n && j <= i) a[i * ld + j] = v[u][c]; }
+    }
+  }
   for (int i = t; i < n; i += nt) a[n * ld + i] = rhs[i];
   for (int i = t; i < (n + 8) * XS; i += nt) Xbuf[i] = 0.0;
   int cr = 0, ce = pl;                        // corner entry of panel lane pl: (cr, ce), ce <= cr
@@ -2458,7 +2473,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
     return H.dir == 0 ? Ab[(size_t)i * bw1 + c] : Ab[(size_t)(n - 1 - i + beta - c) * bw1 + c];
   };
   for (int i = t; i < ylen; i += NH) y[i] = i < H.nh ? rhs[H.dir == 0 ? i : n - 1 - i] : 0.0;
-  for (int e = t; e < kBandRing * bw1; e += NH) ring[e] = band_entry(e / bw1, e % bw1);
+  // global -> shared staging in batches of 8 independent loads per thread: a plain `dst[e] = src[e]` loop is compiled as one
+  // load-store pair after the other (shared stores may alias generic loads), i.e. one memory round trip per element
+  {
+    constexpr int U = 8;
+    for (int base = 0; base < kBandRing * bw1; base += NH * U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { const int e = base + t + u * NH; v[u] = e < kBandRing * bw1 ? band_entry(e / bw1, e % bw1) : 0.0; }
+#pragma unroll
+      for (int u = 0; u < U; u++) { const int e = base + t + u * NH; if (e < kBandRing * bw1) ring[e] = v[u]; }
+    }
+  }
   for (int i = t; i < 40 * XS; i += NH) Xbuf[i] = 0.0;
   // trailing update W -= X X^T on the FP64 tensor-core path: 8x8 tiles (I >= J) of the beta x beta window, dealt to
   // the 7 worker warps; the X fragments of a tile are 4 shared-memory loads per lane instead of 12 per scalar pair
@@ -2686,7 +2712,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
     __syncthreads();
     forward(nblk, nblk + sw / 6, true);
     // backward substitution inside the separator (factor rows staged from global memory)
-    for (int e = t; e < sw * bw1; e += NH) ring[e] = Lt[(size_t)ne0 * bw1 + e];
+    {
+      constexpr int U = 4;
+      const double* srcp = Lt + (size_t)ne0 * bw1;
+      for (int base = 0; base < sw * bw1; base += NH * U) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int e = base + t + u * NH; v[u] = e < sw * bw1 ? srcp[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int e = base + t + u * NH; if (e < sw * bw1) ring[e] = v[u]; }
+      }
+    }
     __syncthreads();
     for (int c0 = sw - 6; c0 >= 0; c0 -= 6) {
       const double* blk = ring + c0 * bw1;
@@ -2725,9 +2761,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   for (int i1 = H.nh; i1 > 0; i1 -= kChunk) {
     const int i0 = max(0, i1 - kChunk);
     __syncthreads();
-    for (int e = t; e < (i1 - i0) * bw1; e += NH) {
-      const int i = i0 + e / bw1, c = e % bw1;
-      ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
+    {
+      // factor rows of the chunk, batched loads (entries left of column 0 in the first rows are never read)
+      constexpr int U = 8;
+      const int cnt = (i1 - i0) * bw1;
+      const double* srcp = Lt + (size_t)i0 * bw1;
+      for (int base = 0; base < cnt; base += NH * U) {
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int e = base + t + u * NH; v[u] = e < cnt ? srcp[e] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < U; u++) { const int e = base + t + u * NH; if (e < cnt) ring[e] = v[u]; }
+      }
     }
     __syncthreads();
     int it = 0;
