@@ -617,11 +617,14 @@ constexpr int kT2StageD = 8;          // per lane and buffer: point (3) + featur
 constexpr int kT2StageI = 4;          // ... and ints: next chunk's mask, its first-observation offset, obs_cam word, spare
 // Zm capacity in doubles: the worst case over (T, nl) of 8 T * t2_ldz(Pc) is 96 x 84 (T = 12, Pc = 23) for
 // 256-thread CTAs and 32 x 196 (T = 4, Pc = 64) for 128-thread CTAs
-__host__ __device__ constexpr int t2_zm_doubles(int nt) { return nt == 256 ? 8192 : 6400; }
+#ifndef UBA_T2_ZM128
+#define UBA_T2_ZM128 6400
+#endif
+__host__ __device__ constexpr int t2_zm_doubles(int nt) { return nt == 256 ? 8192 : UBA_T2_ZM128; }
 // doubles of the region {Zm | flush scratch} (the scratch aliases Zm): [points x slots][33] <= nt*33, or the
 // (8T) x (8T+1) K-group reduction tile (T <= 12 for 256-thread CTAs, <= 8 for 128-thread ones)
 __host__ __device__ constexpr int t2_main_doubles(int nt) {
-  return nt == 256 ? (96 * 97 > 8192 ? 96 * 97 : 8192) : (6400 > 128 * 33 ? (6400 > 64 * 65 ? 6400 : 64 * 65) : 128 * 33);
+  return nt == 256 ? (96 * 97 > 8192 ? 96 * 97 : 8192) : (UBA_T2_ZM128 > 128 * 33 ? (UBA_T2_ZM128 > 64 * 65 ? UBA_T2_ZM128 : 64 * 65) : 128 * 33);
 }
 // ... followed by the two prefetch staging buffers
 __host__ __device__ constexpr int t2_stage_doubles(int nt) { return 2 * nt * (kT2StageD + kT2StageI / 2); }
