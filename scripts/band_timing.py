@@ -20,3 +20,5 @@ print("CTA 0 busy cycles inside the forward loops (loop top -> step barrier), la
 seg = ["prefetch issue", "row solves", "wait named barrier", "trailing update (DMMA)", "side duties", "reload store"]
 for lbl, off in (("t0 (row solves)", 32), ("t100 (rhs update)", 40), ("t192 (rhs solve)", 48)):
     print(lbl, {n: int(v) for n, v in zip(seg, out[off:off + 6])})
+print("CTA 0 backward: staging, block inverses (M, P^j), sweep [cycles]:", [int(x) for x in out[56:59]])
+print("CTA 0 backward sweep, busy cycles before the step barrier: idle warp 0, helper warp, panel warp:", [int(x) for x in out[59:62]])

@@ -2433,6 +2433,11 @@ __global__ void __launch_bounds__(256) k_chol_banded_la2(DevView V, int w, int b
 // reads CTA 1's separator corner and rhs through distributed shared memory, factors the sw x sw separator system with
 // one warp and writes the separator solution into both CTAs' y; both then back-substitute their half concurrently
 // (with lookahead).  Sequential depth: n/12 + sw/6 block steps on each SM instead of n/6 on one.
+constexpr int kC2ChunkBlocks = 34;      // blocks per chunk of the backward sweep of k_chol_banded_c2
+__host__ __device__ constexpr size_t c2_backward_doubles(int beta) {
+  return (size_t)(kC2ChunkBlocks + (beta + 6) / 6 + 1) * 6 * (beta + 1) + (size_t)kC2ChunkBlocks * ((beta + 6) / 6 + 1) * 36;
+}
+
 template <int PER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c2(DevView V, int w, int beta) {
   extern __shared__ double sm[];
@@ -2463,7 +2468,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   const bool panel = t >= NWORKH;
   const int pl = t - NWORKH;
 #ifdef UBA_BAND_TIMING
-  long long tph[8]; int nph = 0; long long busy = 0; long long seg[6] = {0, 0, 0, 0, 0, 0}; long long tq = 0;
+  long long tph[8]; int nph = 0; long long busy = 0; long long bseg[3] = {0, 0, 0}; long long brole = 0; long long seg[6] = {0, 0, 0, 0, 0, 0}; long long tq = 0;
 #define SG(i) { const long long now_ = clock64(); seg[i] += now_ - tq; tq = now_; }
 #define PH() { if (t == 0) tph[nph++] = clock64(); }
 #else
@@ -2759,86 +2764,116 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   PH()
   cluster.sync();
   PH()
-  // ---- backward substitution of this half (local numbering) with lookahead; separator rows are known ----
-  constexpr int kChunk = 126;
-  for (int i1 = H.nh; i1 > 0; i1 -= kChunk) {
-    const int i0 = max(0, i1 - kChunk);
-    __syncthreads();
-    {
-      // factor rows of the chunk, batched loads (entries left of column 0 in the first rows are never read)
-      constexpr int U = 8;
-      const int cnt = (i1 - i0) * bw1;
-      const double* srcp = Lt + (size_t)i0 * bw1;
-      for (int base = 0; base < cnt; base += NH * U) {
-        double v[U];
+  // ---- backward substitution of this half (local numbering); separator rows are known ----
+  // L^T x = z by 6-row blocks, x_b = L_bb^-T (z_b - sum_{j=1..NJ} L_{b+j,b}^T x_{b+j}).  The solve is taken OFF the sweep's dependent
+  // chain by precomputing, per chunk of blocks and in parallel over all threads, M_b = L_bb^-T and P^j_b = M_b L_{b+j,b}^T:
+  //   x_b = [M_b z_b - sum_{j>=2} P^j_b x_{b+j}] - P^1_b x_{b+1} = u_b - P^1_b x_{b+1}.
+  // One warp prepares u for the NEXT block (its inputs are known one step ahead: 6 x NJ lanes, a 6-term dot product each, shuffle
+  // reduction) while six lanes of the panel warp finish the current one (one 6-term dot product per lane).  Per block the chain is
+  // a dot product and a barrier instead of a 12-deep triangular solve, a dependent 12-term update and a barrier.
+  {
+    const int NJ = (beta + 6) / 6;              // block sub-diagonals inside the band (5 for beta = 29, 6 for 35)
+    const int NG = NJ + 1;                      // groups per block: M, P^1 .. P^NJ
+    double* Lb = Xbuf + 40 * XS + 8;            // [(kC2ChunkBlocks + NJ + 1) * 6][bw1] staged factor rows
+    double* MP = Lb + (size_t)(kC2ChunkBlocks + NJ + 1) * 6 * bw1;   // [kC2ChunkBlocks][NG][6][6]
+    __shared__ double s_part[2][6][6];          // [block parity][group][row]
+    const int nbu = H.ne / 6;                   // unknown blocks 0 .. nbu-1
+    for (int bH = nbu - 1; bH >= 0; bH -= kC2ChunkBlocks) {
+      const int bL = max(0, bH - kC2ChunkBlocks + 1);
+      const int i0 = 6 * bL, itop = min(H.nh, 6 * (bH + 1 + NJ));
+      __syncthreads();
+#ifdef UBA_BAND_TIMING
+      long long tb_ = clock64();
+#endif
+      {
+        // factor rows [i0, itop) of the chunk and of the NJ blocks above it (batched loads); rows beyond the half are zero
+        constexpr int U = 8;
+        const int cnt = (6 * (bH + 1 + NJ) - i0) * bw1, have = (itop - i0) * bw1;
+        const double* srcp = Lt + (size_t)i0 * bw1;
+        for (int base = 0; base < cnt; base += NH * U) {
+          double v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) { const int e = base + t + u * NH; v[u] = e < cnt ? srcp[e] : 0.0; }
+          for (int u = 0; u < U; u++) { const int e = base + t + u * NH; v[u] = e < have ? srcp[e] : 0.0; }
 #pragma unroll
-        for (int u = 0; u < U; u++) { const int e = base + t + u * NH; if (e < cnt) ring[e] = v[u]; }
-      }
-    }
-    __syncthreads();
-    int it = 0;
-    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6, it++) {
-      const double* blk = ring + (c0 - i0) * bw1;
-      const int par = it & 1;
-      if (panel) {
-        if (pl == 0) {
-          double xb[6];
-#pragma unroll
-          for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
-          if (c0 < H.ne) {                          // separator blocks: x already final
-#pragma unroll
-            for (int c = 5; c >= 0; c--) {
-              xb[c] *= blk[c * bw1];
-#pragma unroll
-              for (int mm = 0; mm < 6; mm++) if (mm < c) xb[mm] = fma(-blk[c * bw1 + (c - mm)], xb[c], xb[mm]);
-            }
-#pragma unroll
-            for (int c = 0; c < 6; c++) y[c0 + c] = xb[c];
-          }
-#pragma unroll
-          for (int c = 0; c < 6; c++) s_xb[par][c] = xb[c];
-        }
-        __syncwarp();
-        if (pl < 6) {                               // next block's rows: this block's and the previous block's update
-          const int j = c0 - 6 + pl;
-          if (j >= 0 && j < H.ne) {
-            double v = y[j], v2 = 0.0;
-#pragma unroll
-            for (int c = 0; c < 6; c++) v = fma(-blk[c * bw1 + (c0 + c - j)], s_xb[par][c], v);
-            if (it > 0) {
-              const double* blkp = blk + 6 * bw1;
-#pragma unroll
-              for (int c = 0; c < 6; c++) { const int d = c0 + 6 + c - j; if (d <= beta) v2 = fma(blkp[c * bw1 + d], s_xb[par ^ 1][c], v2); }
-            }
-            y[j] = v - v2;
-          }
-        }
-        __syncwarp();
-      } else if (it > 0 && t < beta - 12) {         // workers, one block behind: rows [cp - beta, cp - 12)
-        const int cp = c0 + 6;
-        const double* blkp = blk + 6 * bw1;
-        const int j = cp - 13 - t;
-        if (j >= 0 && j < H.ne) {
-          double v = y[j];
-#pragma unroll
-          for (int c = 0; c < 6; c++) { const int d = cp + c - j; if (d <= beta) v = fma(-blkp[c * bw1 + d], s_xb[par ^ 1][c], v); }
-          y[j] = v;
+          for (int u = 0; u < U; u++) { const int e = base + t + u * NH; if (e < cnt) Lb[e] = v[u]; }
         }
       }
       __syncthreads();
-    }
-    if (!panel && t < beta - 6) {                   // drain: the chunk's last block still owes the rows beyond the next block
-      const int cp = i0;
-      const double* blkp = ring;
-      const int j = cp - 7 - t;
-      if (j >= 0 && j < H.ne) {
-        double v = y[j];
+#ifdef UBA_BAND_TIMING
+      { const long long n_ = clock64(); bseg[0] += n_ - tb_; tb_ = n_; }
+#endif
+      // M_b and P^j_b: one triangular solve L_bb^T m = v per (block, group, column a)
+      const int nblk_c = bH - bL + 1;
+      for (int e = t; e < nblk_c * NG * 6; e += NH) {
+        const int bl = e / (NG * 6), g = (e / 6) % NG, a = e % 6;
+        const double* Lrow0 = Lb + (size_t)(6 * bl) * bw1;       // row 6 (bL + bl) of the staged rows
+        double v[6];
+        if (g == 0) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) { const int d = cp + c - j; if (d <= beta) v = fma(-blkp[c * bw1 + d], s_xb[(it - 1) & 1][c], v); }
-        y[j] = v;
+          for (int r = 0; r < 6; r++) v[r] = r == a ? 1.0 : 0.0;
+        } else {
+          const double* Lk = Lb + (size_t)(6 * (bl + g) + a) * bw1;  // row a of block b + g
+#pragma unroll
+          for (int r = 0; r < 6; r++) { const int d = 6 * g + a - r; const double l = Lk[d <= beta ? d : 0]; v[r] = d <= beta ? l : 0.0; }
+        }
+#pragma unroll
+        for (int r = 5; r >= 0; r--) {
+          double acc = v[r];
+#pragma unroll
+          for (int c2 = 0; c2 < 6; c2++) if (c2 > r) acc = fma(-Lrow0[c2 * bw1 + (c2 - r)], v[c2], acc);
+          v[r] = acc * Lrow0[r * bw1];
+        }
+        double* dst = MP + ((size_t)bl * NG + g) * 36 + a;
+#pragma unroll
+        for (int r = 0; r < 6; r++) dst[r * 6] = v[r];
       }
+      __syncthreads();
+#ifdef UBA_BAND_TIMING
+      { const long long n_ = clock64(); bseg[1] += n_ - tb_; tb_ = n_; }
+#endif
+      // sweep: step `b` finishes block b (panel warp) while the helper warp prepares u of block b-1; the step before the first
+      // one (b == bH + 1) only prepares u of block bH
+      for (int b = bH + 1; b >= bL; b--) {
+#ifdef UBA_BAND_TIMING
+        const long long ts_ = clock64();
+#endif
+        const int hw = t >> 5, hl = t & 31;
+        if (hw >= 1 && hw <= NJ && hl < 6) {
+          // helper warps 1 .. NJ, one group each (a single warp issuing all ~90 instructions of the five dot products takes
+          // ~550 cycles: dependent-issue latency, not arithmetic): warp q+1 computes row hl of M z_hb (q = 0) or of
+          // P^{q+1} x_{hb+q+1} (q >= 1) for the NEXT block hb = b - 1
+          const int hb = b - 1, q = hw - 1;
+          if (hb >= bL) {
+            const int g = q == 0 ? 0 : q + 1;
+            const double* row = MP + ((size_t)(hb - bL) * NG + g) * 36 + hl * 6;
+            const double* src = y + 6 * (hb + g);
+            double acc = 0.0;
+#pragma unroll
+            for (int c2 = 0; c2 < 6; c2++) acc = fma(row[c2], src[c2], acc);
+            s_part[hb & 1][q][hl] = q == 0 ? acc : -acc;
+          }
+        } else if (panel && pl < 6 && b <= bH) {         // panel warp: x_b = u_b - P^1_b x_{b+1}, u_b = sum of the helpers' parts
+          const double* row = MP + ((size_t)(b - bL) * NG + 1) * 36 + pl * 6;
+          const double* xn = y + 6 * (b + 1);
+          double acc = 0.0;
+#pragma unroll
+          for (int c2 = 0; c2 < 6; c2++) acc = fma(row[c2], xn[c2], acc);
+          double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+          for (int q = 0; q < 6; q += 2) {
+            if (q < NJ) u0 += s_part[b & 1][q][pl];
+            if (q + 1 < NJ) u1 += s_part[b & 1][q + 1][pl];
+          }
+          y[6 * b + pl] = (u0 + u1) - acc;
+        }
+#ifdef UBA_BAND_TIMING
+        brole += clock64() - ts_;
+#endif
+        __syncthreads();
+      }
+#ifdef UBA_BAND_TIMING
+      { const long long n_ = clock64(); bseg[2] += n_ - tb_; tb_ = n_; }
+#endif
     }
   }
   __syncthreads();
@@ -2846,6 +2881,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
 #ifdef UBA_BAND_TIMING
   if (t == 0) for (int q = 0; q < nph; q++) V.Zbuf[half * 8 + q] = (double)(tph[q] - tph[0]);
   if (half == 0 && (t & 31) == 0) V.Zbuf[16 + (t >> 5)] = (double)busy;
+  if (half == 0 && t == 0) for (int q = 0; q < 3; q++) V.Zbuf[56 + q] = (double)bseg[q];
+  if (half == 0 && (t == 0 || t == NWORKH - 32 || t == NWORKH)) V.Zbuf[59 + (t == 0 ? 0 : t == NWORKH ? 2 : 1)] = (double)brole;
   if (half == 0 && (t == 0 || t == 100 || t == 192)) for (int q = 0; q < 6; q++) V.Zbuf[32 + (t == 0 ? 0 : t == 100 ? 8 : 16) + q] = (double)seg[q];
 #endif
 #undef PH
@@ -3463,7 +3500,7 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
         static const bool use_c2 = [] { const char* e = getenv("UBA_BAND_C2"); return !(e && e[0] == '0'); }();
         if (use_la && use_c2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
           const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
-          const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)40 * 9 + 8 + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
+          const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)40 * 9 + 8 + c2_backward_doubles(beta) + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
 #define UBA_C2_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_c2<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_c2<PP>, 2, 256, smem, st, V, w, beta); }
           if (per <= 2) UBA_C2_LAUNCH(2) else UBA_C2_LAUNCH(3)
