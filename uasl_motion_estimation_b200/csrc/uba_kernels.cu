@@ -2429,10 +2429,12 @@ __global__ void __launch_bounds__(256) k_chol_banded_la2(DevView V, int w, int b
 #ifndef UBA_EMU
 // Two-sided band Cholesky on a CLUSTER OF TWO CTAs (two SMs), beta in [11, 35]: CTA 0 eliminates block columns
 // [0, m) top-down, CTA 1 eliminates the rows below the separator bottom-up (top-down on the reversed matrix), each
-// with all 256 threads exactly like k_chol_banded_la (panel warp 7 + 224 workers).  After the forward loops CTA 0
-// reads CTA 1's separator corner and rhs through distributed shared memory, factors the sw x sw separator system with
-// one warp and writes the separator solution into both CTAs' y; both then back-substitute their half concurrently
-// (with lookahead).  Sequential depth: n/12 + sw/6 block steps on each SM instead of n/6 on one.
+// with all 256 threads like k_chol_banded_la (panel warp 7 + 224 workers; trailing update on DMMA tiles, ring refilled
+// every step).  After the forward loops CTA 0 reads CTA 1's separator corner and rhs through distributed shared memory,
+// adds them to its own ring rows, continues its elimination over the separator (sw / 6 more steps), back-substitutes the
+// separator and writes its solution into both CTAs' y; both then back-substitute their half concurrently with a sweep
+// whose triangular solves are precomputed per chunk (see the backward section).  Sequential depth: n/12 + sw/6 block
+// steps on each SM instead of n/6 on one.
 constexpr int kC2ChunkBlocks = 34;      // blocks per chunk of the backward sweep of k_chol_banded_c2
 __host__ __device__ constexpr size_t c2_backward_doubles(int beta) {
   return (size_t)(kC2ChunkBlocks + (beta + 6) / 6 + 1) * 6 * (beta + 1) + (size_t)kC2ChunkBlocks * ((beta + 6) / 6 + 1) * 36;
