@@ -1248,7 +1248,6 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
     CU(h, cudaMemcpy(h->d_ws.p, h->ws_h.data(), sizeof(WinState) * h->nW, cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->d_n_active.p, &n_act, sizeof(int), cudaMemcpyHostToDevice));
   }
-  bool time_capped = false;
   for (int it = 0; it < max_it; it++) {
     rc = run_iteration_fast(h);
     if (rc) return rc;
@@ -1259,7 +1258,7 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
       CU(h, cudaMemcpyAsync(&n_act, h->d_n_active.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CU(h, cudaStreamSynchronize(h->stream));
       if (n_act <= 0) break;
-      if (timed && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() >= h->cfg.max_solver_time_s) { time_capped = true; break; }
+      if (timed && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() >= h->cfg.max_solver_time_s) break;
     }
   }
   cudaEventRecord(h->ev[3], h->stream);
@@ -1278,7 +1277,6 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
   for (int w = 0; w < h->nW; w++) {
     WinState& s = h->ws_h[w];
     if (s.done == 0) s.done = UBA_TERM_NO_CONVERGENCE;  // iteration or wall-clock cap (:417,:464): still usable
-    (void)time_capped;
     if (summaries) {
       uba_summary& o = summaries[w];
       o.termination = s.done; o.usable = s.done != UBA_TERM_FAILURE; o.iterations = s.iter; o.successful_steps = s.n_success;

@@ -1235,7 +1235,6 @@ __global__ void __launch_bounds__(256) k_chol_small(DevView V, int max_n, int ke
   for (int kb = nf - 1; kb >= 0; kb--) {
     const int c0 = 6 * kb;
     if (tid == 0) {
-#pragma unroll
       double xb[6];
 #pragma unroll
       for (int c = 5; c >= 0; c--) {
@@ -2462,7 +2461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   double* Xbuf = y + ylen;
   constexpr int XS = 9;                       // row stride of Xbuf [40][XS]: columns 6..8 and rows >= beta stay zero (DMMA padding)
   __shared__ int s_fail;
-  __shared__ double s_Lkk[2][36], s_invk[2][6], s_z[6], s_xp[36], s_corner[21], s_xb[2][6];
+  __shared__ double s_Lkk[2][36], s_invk[2][6], s_z[6], s_xp[36], s_corner[21];
   double* rhs = V.rhs + (size_t)6 * f0;
   double* A0 = V.A + V.w_red_off[w];
   double* Lt = A0 + (size_t)half * n * bw1;   // this half's factor rows (local row numbering)
@@ -3011,7 +3010,6 @@ __global__ void __launch_bounds__(128) k_solve_epilogue(DevView V) {
 // ---------------------------------------------------------------------------------------------
 template <int M>
 __global__ void __launch_bounds__(128) k_backsub(DevView V) {
-  constexpr int NR = (M == 4) ? 3 : 2;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const bool in_range = p < V.NP;
   int w = in_range ? V.pt_win[p] : V.pt_win[V.NP - 1];
