@@ -11,8 +11,9 @@ library's stream, max over ranks); `e2e` is the same metric through the C-ABI ca
 caller makes (uba_set_problem -> uba_optimise -> uba_get_*) from host buffers, copies included.
 
 Default workload: c4 (BASELINE.json configs[3], the 1M-observation window north_star's targets are
-quoted on).  N > 1 (torchrun, one rank per GPU): c4/c5 are sharded by point with an NCCL allreduce of
-the reduced camera system ("scaling": "strong"); c3 is sharded by window with no collective ("weak").
+quoted on).  N > 1 (torchrun, one rank per GPU): c4/c5 are sharded by point (keyframe ranges) and the reduced
+camera system is summed over NVLink peer memory inside the iteration ("scaling": "strong"; UBA_PEER=0 selects the
+NCCL allreduce fallback); c3 is sharded by window with no collective ("weak").
 --impl reference times the CPU restatement of the reference's Ceres path (oracle/, all host threads):
 the reference itself cannot be built here (needs Ceres, OpenCV C++, glog; none installed, no network).
 """
@@ -86,19 +87,18 @@ class ClockSampler:
 
 
 def build_workload(name, rank, world, windows, scale):
-    """Returns (list of windows for this rank, total observations over all ranks, scaling, parallelism)."""
+    """Returns (windows of this rank, total observations over all ranks or None, scaling, parallelism, local observations)."""
     from uasl_motion_estimation_b200 import sharding, synth
+    nwin, parallelism = workload_shape(name, world, windows)
     if name == "c3":
-        per_rank = windows if windows else 512
-        wins = [synth.config_window("c3", window=rank * per_rank + i, scale=scale) for i in range(per_rank)]
+        wins = [synth.config_window("c3", window=rank * nwin + i, scale=scale) for i in range(nwin)]
         n_local = sum(w.n_obs for w in wins)
-        return wins, None, "weak", f"window-sharded x{world}, no collective", n_local
+        return wins, None, "weak", parallelism, n_local
     win = synth.config_window(name, scale=scale)
     total = win.n_obs
     if world > 1:
         win = sharding.shard_window(win, rank, world)
-        return [win], total, "strong", f"point-sharded x{world}, NCCL allreduce of the reduced camera system", win.n_obs
-    return [win], total, "strong", "single GPU", win.n_obs
+    return [win], total, "strong", parallelism, win.n_obs
 
 
 def algorithmic_work(wins, fixed):
@@ -137,39 +137,66 @@ def h2d_d2h_bytes(wins):
     return h2d, d2h
 
 
+def workload_config(name, n_windows_per_gpu, total_obs, n_local, n_cams, fixed, loss, k_iters, parallelism, scale):
+    """The `config` object: identical keys (and, at the same N, identical values) on both arms."""
+    return {"workload": name, "n_windows_per_gpu": int(n_windows_per_gpu), "n_obs_total": int(total_obs), "n_obs_per_gpu": int(n_local),
+            "n_cams": int(n_cams), "fixed_frames": fixed, "loss": {1: "huber", 2: "cauchy", 0: "trivial"}[loss],
+            "lm_iterations_e2e": k_iters, "parallelism": parallelism, "l2": "flushed between timed iterations (384 MB write)",
+            "scale": scale}
+
+
+def workload_shape(name, world, windows):
+    """(n_windows_per_gpu, parallelism) as build_workload decides them — without generating anything."""
+    if name == "c3":
+        return (windows if windows else 512), f"window-sharded x{world}, no collective"
+    if world > 1:
+        return 1, f"point-sharded x{world} by keyframe range, reduced camera system summed over peer memory (NVLink)"
+    return 1, "single GPU"
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle's LM iteration (Jet autodiff residual blocks, Schur elimination, dense Cholesky,
-    back-substitution, candidate cost) on the host cores; rank 0 only."""
+    back-substitution, candidate cost) on the host cores; rank 0 only.  Steady state: the problem structure is built once,
+    then `warmup` untimed and `steps` timed iterations run inside ONE oracle call (as ceres::Solve iterates on a built
+    Problem).  This process maps oracle/ and the host-only libuba_host.so (generator + defaults) — not the product library."""
     if rank != 0:
         return
     import oracle_binding as ob
     from uasl_motion_estimation_b200 import capi, synth
     ob.build()
-    lib = capi.default_lib()
     name = args.workload
     scale = args.scale
     if name == "c3":
-        wins = [synth.config_window("c3", window=0, scale=scale)]
-        sample = "1 of the batch's 10-frame windows per step"
+        win = synth.config_window("c3", window=0, scale=scale)
+        sample = "1 of the batch's 10-frame windows, one LM iteration per step"
     else:
-        wins = [synth.config_window(name, scale=scale)]
+        win = synth.config_window(name, scale=scale)
         sample = f"the full {name} window, one LM iteration per step"
-    win = wins[0]
-    cfg = capi.default_config(lib, loss_kind=synth.CONFIGS[name]["loss"])
+    loss = synth.CONFIGS[name]["loss"]
+    cfg = capi.default_config(loss_kind=loss)
     # all the host threads it can use — torchrun pins OMP_NUM_THREADS=1, and only rank 0 runs this arm
     ob.lib().uba_ref_set_threads(os.cpu_count() or 1)
     threads = ob.lib().uba_ref_max_threads()
-    for _ in range(args.warmup):
-        ob.time_iteration(win, cfg, 2, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ob.time_iteration(win, cfg, 2, 1)
-    dt = (time.perf_counter() - t0) / args.steps
+    fixed = 2
+    if args.warmup > 0:
+        ob.time_iteration(win, cfg, fixed, args.warmup)
+    dt, _ = ob.time_iteration(win, cfg, fixed, args.steps)      # seconds per iteration, structure building excluded
     value = win.n_obs / dt
+    nwin, parallelism = workload_shape(name, world, args.windows)
+    total = win.n_obs * (nwin * world if name == "c3" else 1)
+    if name == "c3":
+        n_local = None    # every window of the batch has its own observation count: the GPU arm reports its rank 0's sum
+    elif world > 1:
+        from uasl_motion_estimation_b200 import sharding
+        n_local = int(sharding.point_ranks(win, world)[1][0])
+    else:
+        n_local = win.n_obs
+    k_iters = synth.CONFIGS[name]["iters"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if name != "c3" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "n_cams": win.n_cams, "n_pts": win.n_pts, "n_obs": win.n_obs, "scale": scale},
+            "config": workload_config(name, nwin, total, n_local if n_local is not None else win.n_obs * nwin,
+                                      win.n_cams, fixed, loss, k_iters, parallelism, scale),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "lm_iters_per_s": 1.0 / dt,
@@ -251,11 +278,18 @@ def main():
     barrier()
     launches = h.timing()["kernel_launches"] - args.steps  # minus the L2-flush kernels
     # K iterations of a sub-millisecond step end before nvidia-smi (100 ms period) can look: keep the same load running,
-    # untimed, until the sampler has had half a second of it
-    while time.perf_counter() - t_region < 0.5:
-        h.time_iteration(fixed, iterations=max(args.steps, 20), flush_l2=True)
+    # untimed, until the sampler has had about half a second of it.  The number of extra calls is AGREED between the ranks
+    # (max over ranks of the measured call time): on a point-sharded handle every call contains cross-rank exchanges, so a
+    # per-rank clock test around it would let the ranks run different numbers of them and hang.
+    call_s = torch.tensor([time.perf_counter() - t_region], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(call_s, op=dist.ReduceOp.MAX)
+    n_extra = int(min(200, max(1, np.ceil(0.5 / max(float(call_s.item()), 1e-3)))))
+    for _ in range(n_extra):
+        h.time_iteration(fixed, iterations=args.steps, flush_l2=True)
+    barrier()
     clocks = sampler.stop()
-    clocks["sampled_over"] = "the timed region and its untimed continuation (same iterations) up to 0.5 s"
+    clocks["sampled_over"] = f"the timed region and {n_extra} untimed repetitions of it (same iterations, rank-agreed count)"
     # ---- the linearise+Schur pass alone (the roofline kernel) ----
     ms_lin = h.time_linearize(fixed, 1e4, repeats=max(args.steps, 5), flush_l2=True)
     t = torch.tensor([ms_iter, ms_lin], dtype=torch.float64, device="cuda")
@@ -263,6 +297,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_iter, ms_lin = float(t[0]), float(t[1])
     value = total_obs / (ms_iter * 1e-3)
+    t0 = torch.tensor([float(n_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.broadcast(t0, src=0)
+    n_local_rank0 = int(t0.item())
 
     # ---- end to end through the C ABI from host buffers ----
     h2d, d2h = h2d_d2h_bytes(wins)
@@ -298,10 +336,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_iter, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": name, "n_windows_per_gpu": len(wins), "n_obs_total": int(total_obs), "n_obs_per_gpu": int(n_local),
-                       "n_cams": wins[0].n_cams, "fixed_frames": fixed, "loss": {1: "huber", 2: "cauchy", 0: "trivial"}[loss],
-                       "lm_iterations_e2e": k_iters, "parallelism": parallelism, "l2": "flushed between timed iterations (384 MB write)",
-                       "scale": args.scale},
+            "config": workload_config(name, len(wins), total_obs, n_local_rank0, wins[0].n_cams, fixed, loss, k_iters, parallelism, args.scale),
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d // k_iters), "d2h_bytes_per_step": int(d2h // k_iters),
                     "ms_per_call": float(t[0]), "lm_iterations_per_call": k_iters},

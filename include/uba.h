@@ -206,6 +206,18 @@ int uba_comm_init(uba_handle* h, const char id[UBA_NCCL_UNIQUE_ID_BYTES], int ra
  * a subset of points and their observations) and uba_linearize / uba_optimise reduce
  * over ranks.  uba_set_batch problems never communicate. */
 
+/* Host-side sharding helpers (no CUDA; also exported by libuba_host.so).  uba_shard_points assigns every point of a
+ * window to one of n_ranks shards by KEYFRAME RANGE — points ordered by (first keyframe of the track, caller index), cut
+ * into pieces of equal observation count — so that a rank's Schur products touch one stretch of the block band of the
+ * reduced camera system and only neighbouring ranks overlap.  pt_rank [n_pts] out; rank_obs / rank_pts [n_ranks] out or
+ * NULL.  uba_shard_extract writes one rank's points (caller order kept, indices renumbered) and observations and returns
+ * the number of observations written; pt_ids_out [rank_pts] receives the caller point id of each shard point. */
+int uba_shard_points(int n_cams, int n_pts, int64_t n_obs, const int32_t* cam_idx, const int32_t* pt_idx, int n_ranks,
+                     int32_t* pt_rank, int64_t* rank_obs, int32_t* rank_pts);
+int64_t uba_shard_extract(int M, int n_pts, int64_t n_obs, const double* pts3, const double* feats, const int32_t* cam_idx,
+                          const int32_t* pt_idx, const int32_t* cam_id, const int32_t* pt_rank, int rank, double* pts3_out,
+                          double* feats_out, int32_t* cam_idx_out, int32_t* pt_idx_out, int32_t* cam_id_out, int32_t* pt_ids_out);
+
 /* ---- device-side timing for benchmarks (CUDA events on the library's stream) ------- */
 typedef struct uba_timing {
   double linearize_ms;   /* summed over launches since the last reset */

@@ -28,7 +28,7 @@ namespace uba_emu { extern thread_local dim3 t_threadIdx, t_blockIdx, t_blockDim
 #define gridDim uba_emu::t_gridDim
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0 };
+enum { cudaSuccess = 0, cudaErrorNotReady = 600 };
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
@@ -45,6 +45,8 @@ inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyK
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = nullptr; return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamQuery(cudaStream_t) { return 0; }
+inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }

@@ -75,8 +75,6 @@ def test_reference_termination_rules(gpu_lib, oracle):
 _SOLVER_ENVS = {
     "cluster2": {},                                          # default: two-sided band Cholesky on a 2-CTA cluster
     "lookahead": {"UBA_BAND_C2": "0"},                       # one CTA, panel-warp lookahead
-    "two_sided_1cta": {"UBA_BAND_C2": "0", "UBA_BAND_LA2": "1"},
-    "plain_block": {"UBA_BAND_C2": "0", "UBA_BAND_LA": "0"},
 }
 
 

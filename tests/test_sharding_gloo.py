@@ -28,7 +28,7 @@ def _worker(rank, world, port, emu_path, out):
     win = synth.config_window("c4", scale=0.003, lib=lib)
     cfg = capi.default_config(lib)
     full = ob.linearize(win, cfg, 2, 1e4)
-    sh = sharding.shard_window(win, rank, world)
+    sh = sharding.shard_window(win, rank, world, lib)
     # Jacobi scaling and camera damping are global quantities: linearise undamped and add them after the reduce
     part = ob.linearize(sh, cfg, 2, -1.0, jacobi_scale=np.ones(6 * sh.n_cams + 3 * sh.n_pts))
     nfree = int((ob.tables(win.n_cams, win.n_pts, win.cam_idx, win.pt_idx, 2)["free_cam"] >= 0).sum())
@@ -50,8 +50,7 @@ def _worker(rank, world, port, emu_path, out):
         # undamped point blocks differ from the damped full run only through lambda: compare against an undamped full run
         full_u = ob.linearize(win, cfg, 2, -1.0, jacobi_scale=np.ones(6 * win.n_cams + 3 * win.n_pts))
         out["S"] = np.abs(St.numpy() - full_u["S"]).max() / np.abs(full_u["S"]).max()
-        b = sharding.point_ranges(win.pt_idx, win.n_pts, world)
-        out["balance"] = [int(((win.pt_idx >= b[r]) & (win.pt_idx < b[r + 1])).sum()) for r in range(world)]
+        out["balance"] = [int(x) for x in sharding.point_ranks(win, world, lib)[1]]
     dist.destroy_process_group()
 
 
@@ -66,15 +65,30 @@ def test_point_sharded_reduced_system_sums_to_the_full_one(emu_lib):
     assert abs(n[0] - n[1]) <= 0.02 * sum(n)  # balanced by observation count
 
 
-def test_point_ranges_cover_and_balance():
-    rng = np.random.default_rng(0)
-    k = rng.integers(0, 12, size=5000)
-    pt_idx = np.repeat(np.arange(5000), k)
+def test_keyframe_range_shards_cover_balance_and_stay_local():
+    """uba_shard_points: every point lands on exactly one rank, observation counts are balanced, a rank's tracks START
+    inside one contiguous keyframe range (so only neighbouring ranks share cameras), and the extracted shards reassemble
+    the window."""
+    win = synth.config_window("c4", scale=0.02)
     for world in (1, 2, 3, 8):
-        b = sharding.point_ranges(pt_idx, 5000, world)
-        assert b[0] == 0 and b[-1] == 5000 and (np.diff(b) >= 0).all()
-        counts = [int(((pt_idx >= b[r]) & (pt_idx < b[r + 1])).sum()) for r in range(world)]
-        assert sum(counts) == len(pt_idx) and max(counts) - min(counts) <= 12 * world
+        pt_rank, rank_obs, rank_pts = sharding.point_ranks(win, world)
+        assert pt_rank.min() >= 0 and pt_rank.max() < world
+        assert rank_obs.sum() == win.n_obs and rank_pts.sum() == win.n_pts
+        assert rank_obs.max() - rank_obs.min() <= 8 * world
+        lo = np.full(win.n_pts, win.n_cams); np.minimum.at(lo, win.pt_idx, win.cam_idx)
+        first = [lo[(pt_rank == r) & (lo < win.n_cams)] for r in range(world)]
+        for r in range(world - 1):
+            if len(first[r]) and len(first[r + 1]):
+                assert first[r].max() <= first[r + 1].min()        # keyframe ranges are ordered, overlapping in one keyframe at most
+        seen_pts = np.zeros(win.n_pts, int); n_obs = 0
+        for r in range(world):
+            sh, ids = sharding.shard_window(win, r, world, return_ids=True)
+            seen_pts[ids] += 1; n_obs += sh.n_obs
+            assert np.array_equal(sh.pts_init, win.pts_init[ids])
+            sel = pt_rank[win.pt_idx] == r
+            assert np.array_equal(sh.feats, win.feats[sel]) and np.array_equal(sh.cam_idx, win.cam_idx[sel])
+            assert np.array_equal(ids[sh.pt_idx], win.pt_idx[sel])
+        assert (seen_pts == 1).all() and n_obs == win.n_obs
 
 
 def test_window_ranges():

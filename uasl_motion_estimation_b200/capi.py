@@ -15,6 +15,7 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 DEFAULT_LIB = PKG_DIR / "lib" / "libuba.so"
+HOST_LIB = PKG_DIR / "lib" / "libuba_host.so"   # host-only part of the ABI (generator, defaults, boundary maths): no CUDA
 
 UBA_OK = 0
 UBA_ERR_INVALID_ARGUMENT = -1
@@ -112,10 +113,16 @@ _SIGNATURES = [
     ("uba_synth_default_calib", None, [C.POINTER(Calib)]),
     ("uba_synth_generate", C.c_int64, [C.POINTER(SynthSpec), C.POINTER(Calib), C.c_int64, c_double_p, c_double_p, c_double_p,
                                         c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p]),
+    ("uba_shard_points", C.c_int, [C.c_int, C.c_int, C.c_int64, c_int32_p, c_int32_p, C.c_int, c_int32_p, c_int64_p, c_int32_p]),
+    ("uba_shard_extract", C.c_int64, [C.c_int, C.c_int, C.c_int64, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                       C.c_int, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
     ("uba_log_map_quat", None, [c_double_p, c_double_p]),
     ("uba_exp_map_quat", None, [c_double_p, c_double_p]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
+# the subset libuba_host.so carries as well (same sources, compiled without CUDA)
+HOST_SYMBOLS = ["uba_config_default", "uba_synth_default_calib", "uba_synth_generate", "uba_log_map_quat", "uba_exp_map_quat",
+                "uba_shard_points", "uba_shard_extract"]
 
 
 class UbaError(RuntimeError):
@@ -150,7 +157,22 @@ def load(path: str | os.PathLike | None = None) -> C.CDLL:
     return lib
 
 
+def load_host(path: str | os.PathLike | None = None) -> C.CDLL:
+    """Load libuba_host.so: generator, defaults and boundary maths only.  Nothing in it computes bundle adjustment."""
+    p = Path(path) if path is not None else HOST_LIB
+    if not p.exists():
+        raise ImportError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(str(p))
+    for name, res, args in _SIGNATURES:
+        if name in HOST_SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return lib
+
+
 _default_lib = None
+_host_lib = None
 
 
 def default_lib() -> C.CDLL:
@@ -160,8 +182,15 @@ def default_lib() -> C.CDLL:
     return _default_lib
 
 
+def host_lib() -> C.CDLL:
+    global _host_lib
+    if _host_lib is None:
+        _host_lib = load_host()
+    return _host_lib
+
+
 def default_config(lib=None, **overrides) -> Config:
-    lib = lib or default_lib()
+    lib = lib or host_lib()
     cfg = Config()
     lib.uba_config_default(C.byref(cfg))
     for k, v in overrides.items():
@@ -172,7 +201,7 @@ def default_config(lib=None, **overrides) -> Config:
 
 
 def default_calib(lib=None) -> Calib:
-    lib = lib or default_lib()
+    lib = lib or host_lib()
     k = Calib()
     lib.uba_synth_default_calib(C.byref(k))
     return k

@@ -12,12 +12,12 @@ namespace uba {
 // Per-window scalars accumulated by the kernels of one LM iteration (zeroed before each).  They
 // are grouped by how a point-sharded multi-GPU run reduces them:
 //   w_lin  [nW][2]  cost, failures of the lineariser      -> summed over ranks with S (after linearise)
-//   w_post [nW][4]  candidate cost, point parts of the model change / step norm / x norm
+//   w_post [nW][5]  candidate cost, point parts of the model change / step norm / x norm, stop requests (wall-clock cap)
 //                                                          -> summed over ranks (after back-substitution)
 //   w_loc  [nW][4]  camera parts + solver failures          -> identical on every rank, never reduced
 //   w_max  [nW]     projected-gradient max norm             -> max over ranks
 enum WLin { WL_COST = 0, WL_FAIL = 1, WL_COUNT = 2 };
-enum WPost { WP_COSTNEW = 0, WP_MCPT = 1, WP_STEP2 = 2, WP_X2 = 3, WP_COUNT = 4 };
+enum WPost { WP_COSTNEW = 0, WP_MCPT = 1, WP_STEP2 = 2, WP_X2 = 3, WP_STOP = 4, WP_COUNT = 5 };
 enum WLoc { WC_MCCAM = 0, WC_STEP2 = 1, WC_X2 = 2, WC_FAIL = 3, WC_COUNT = 4 };
 
 // Levenberg–Marquardt controller state of one window (device resident).
@@ -128,6 +128,37 @@ struct DebugOut {
   double* lam_pts;    // [NP][3]
 };
 
+// ---- point-sharded windows: the cross-rank sums over NVLink PEER MEMORY (uba_peer.cu) --------------------------------
+// Every rank maps every other rank's accumulator block, flag words and inbox (CUDA IPC, one process per GPU).  Two
+// exchange points per LM iteration, both plain kernels inside the captured iteration graph:
+//   k_peer_reduce  after the lineariser: arrive (a flag word stored into every peer), wait for the peers whose shards
+//                  touch the same cameras, then PULL their partial {B, v, Z h, cost, band of S_acc} straight out of their
+//                  HBM over NVLink and sum in rank order into the local consumer copy (bitwise identical on every rank);
+//   k_peer_post    after the back-substitution: PUSH this rank's {candidate cost, model change, norms, gradient max,
+//                  stop request} into every peer's inbox, arrive, wait, sum the inbox in rank order.
+// A peer that does not arrive within timeout_ns raises *err (the host turns it into UBA_ERR_NCCL) instead of spinning.
+constexpr int kMaxRanks = 16;
+constexpr int kInboxSlots = WP_COUNT + 1;      // w_post sums (incl. the stop request), gradient max-norm
+struct PeerView {
+  int32_t rank, n_ranks;
+  double* acc[kMaxRanks];                  // accumulator block of every rank (own entry: the local pointer)
+  unsigned long long* flags[kMaxRanks];    // arrival words of every rank: flags[p][r] = last exchange rank r reached
+  double* inbox[kMaxRanks];                // [2][n_ranks][nW][kInboxSlots] of every rank
+  unsigned long long* epoch;               // local: [0] exchanges passed, [1] post exchanges passed, [2] CTA completion counter
+  int32_t* err;                            // local: a peer did not arrive in time
+  const int32_t* cam_lo;                   // [n_ranks] first / last global camera index each rank's shard observes
+  const int32_t* cam_hi;
+  const double* stop_req;                  // local scalar set by the host: this rank wants to stop (wall-clock cap)
+  long long timeout_ns;
+};
+// layout of the accumulator block (doubles), identical on every rank
+struct AccLayout {
+  int64_t off_Bacc, off_vacc, off_zh, off_wlin, off_sacc, sum_end;   // [0, sum_end): what the lineariser produces
+  int64_t off_wpost, off_wmax, off_wloc, total;
+};
+int launch_peer_reduce(const DevView& V, const PeerView& P, const AccLayout& L, double* acc_red, int dense, cudaStream_t st);
+int launch_peer_post(const DevView& V, const DevView& Vc, const PeerView& P, cudaStream_t st);
+
 // launchers (uba_kernels.cu); all asynchronous on `st`; return the number of kernels launched
 int launch_cam_prep(const DevView& V, int parity, cudaStream_t st);
 // only_listed: process V.gen_pts instead of every point
@@ -146,7 +177,7 @@ int launch_init_state(const DevView& V, double initial_radius, cudaStream_t st);
 int launch_cov_state(const DevView& V, int enter, cudaStream_t st);
 int launch_cov_blocks(const DevView& V, int n_free_total, int max_n, double* cov36, cudaStream_t st);
 int launch_l2_flush(double* buf, size_t n, cudaStream_t st);
-int launch_rank_max(double* w_max, double* w_rmax, int nW, int rank, int n_ranks, int gather, cudaStream_t st);
+int launch_rank_max(double* w_max, double* w_rmax, double* w_post, const double* stop_req, int nW, int rank, int n_ranks, int gather, cudaStream_t st);
 int launch_ingest_feats(const void* raw, const int32_t* src, double* feat, int64_t NO, int M, int raw_is_f32, cudaStream_t st);
 int launch_dfma_probe(double* out, int iters, cudaStream_t st);
 

@@ -40,10 +40,13 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, Id128, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommGetAsyncError)(void*, int*) = nullptr;
+  int (*CommAbort)(void*) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
-constexpr int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclDouble = 8, kNcclChar = 0, kNcclSum = 0, kNcclMax = 2;
 
 bool load_nccl(NcclApi& api, std::string& err) {
   if (api.lib) return true;
@@ -53,6 +56,9 @@ bool load_nccl(NcclApi& api, std::string& err) {
   api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
   api.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(api.lib, "ncclCommInitRank");
   api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllReduce");
+  api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+  api.CommGetAsyncError = (int (*)(void*, int*))dlsym(api.lib, "ncclCommGetAsyncError");
+  api.CommAbort = (int (*)(void*))dlsym(api.lib, "ncclCommAbort");
   api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
   api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
   if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) { err = "libnccl lacks required symbols"; return false; }
@@ -98,6 +104,7 @@ struct uba_handle {
   cudaEvent_t ev[8] = {};
   // problem (host tables)
   int state = 0;  // 0 uninitialised, 1 problem set, 2 optimised
+  bool device_dirty = false;   // a timing / parity call iterated on the device copy: uba_optimise restores the staged iterate first
   int M = 4, nW = 0, NC = 0, NP = 0;
   int64_t NO = 0;
   uba_calib calib_in{};
@@ -151,17 +158,37 @@ struct uba_handle {
   size_t off_Bacc = 0, off_vacc = 0, off_zh = 0, off_wlin = 0, off_sacc = 0, off_wpost = 0, off_wrmax = 0, off_wmax = 0, off_wloc = 0;
   DevView V{};
   std::vector<WinState> ws_h;
-  // comm
+  // comm: NCCL for the set-up exchanges (and as the fallback data path, UBA_PEER=0); the per-iteration sums of a
+  // point-sharded window go over NVLink peer memory (uba_peer.cu)
   NcclApi nccl;
   void* comm = nullptr;
   int rank = 0, n_ranks = 1;
+  bool any_rank_infeasible = false;           // some rank's point shard starts outside the box: the window fails on every rank
+  bool peer_wanted = true;                    // UBA_PEER=0 keeps the NCCL data path
+  bool peer_on = false;                       // peer mappings are valid for the current buffers
+  DevBuf<unsigned char> d_ctl;                // [flags n u64 | epoch 4 u64 | err (8 B) | stop_req double | cam_lo n i32 | cam_hi n i32 | inbox]
+  size_t ctl_inbox_off = 0, ctl_bytes = 0;
+  DevBuf<double> d_acc_red;                   // consumer copy of the accumulator block (sums over ranks)
+  DevBuf<char> d_xchg;                        // staging of the set-up exchanges
+  void* mapped_acc[kMaxRanks] = {};           // cudaIpcOpenMemHandle results (own rank: null)
+  void* mapped_ctl[kMaxRanks] = {};
+  void* exchanged_acc = nullptr;              // local pointers the current mappings were exchanged for
+  void* exchanged_ctl = nullptr;
+  std::vector<int32_t> rank_cam_lo, rank_cam_hi;
+  int local_cam_lo = 0, local_cam_hi = -1;    // cameras this rank's own observations touch (before the OR over ranks)
+  PeerView P{};
+  AccLayout L{};
+  DevView Vc{};                               // consumer view: V with the accumulator pointers into d_acc_red
+  double* d_stop_req = nullptr;               // device scalar (inside d_ctl, or d_stop_local without peers)
+  DevBuf<double> d_stop_local;
   // CUDA graph of one LM iteration (re-captured whenever the device view changes)
 #ifndef UBA_EMU
   cudaGraphExec_t graph_exec = nullptr;
 #endif
   int64_t graph_kernels = 0;
   std::vector<char> graph_sig;                // host-side launch geometry the captured graph bakes in (see prepare)
-  DevView graph_V;                            // ... and the device view it was captured with (see run_iteration_fast)
+  DevView graph_V, graph_Vc;                  // ... and the device views it was captured with (see run_iteration_fast)
+  PeerView graph_P;
   // timing
   bool profiling = false;
   uba_timing timing{};
@@ -203,6 +230,15 @@ void drop_graph(uba_handle* h) {
 #endif
 }
 
+void refresh_consumer_view(uba_handle* h) {
+  h->Vc = h->V;
+  if (h->peer_on) {
+    double* r = h->d_acc_red.p;
+    h->Vc.Sacc = r + h->off_sacc; h->Vc.Bacc = r + h->off_Bacc; h->Vc.vacc = r + h->off_vacc; h->Vc.zh = r + h->off_zh;
+    h->Vc.w_lin = r + h->off_wlin; h->Vc.w_post = r + h->off_wpost; h->Vc.w_max = r + h->off_wmax; h->Vc.w_loc = r + h->off_wloc;
+  }
+}
+
 void fill_view_static(uba_handle* h) {
   DevView& V = h->V;                          // (a captured graph is re-validated against the view in prepare())
   V.M = h->M; V.nW = h->nW; V.NC = h->NC; V.NP = h->NP; V.NO = h->NO;
@@ -224,9 +260,14 @@ void fill_view_static(uba_handle* h) {
   c.max_lm_diagonal = h->cfg.max_lm_diagonal; c.max_consecutive_invalid_steps = h->cfg.max_consecutive_invalid_steps;
   c.fixed_iterations = h->cfg.fixed_iterations; c.max_iterations = h->cfg.max_iterations;
   c.jacobi_scaling = h->cfg.jacobi_scaling; c.use_bounds = h->cfg.use_bounds;
+  refresh_consumer_view(h);
 }
 
 int allreduce(uba_handle* h, double* buf, size_t count, int op);
+int comm_wait(uba_handle* h);
+int allgather_bytes(uba_handle* h, const void* mine, size_t bytes, std::vector<char>& all);
+int peer_exchange(uba_handle* h);
+void peer_close(uba_handle* h);
 
 // UBA_TRACE=1: host-side phase times on stderr
 #define TT(label) if (getenv("UBA_TRACE")) { auto now_ = std::chrono::steady_clock::now(); fprintf(stderr, "  [trace] %-28s %.2f ms\n", label, std::chrono::duration<double, std::milli>(now_ - tt_).count()); tt_ = now_; }
@@ -384,8 +425,23 @@ int prepare(uba_handle* h, int fixed_frames) {
     int rc = allreduce(h, h->d_cam_lam.p, NC, kNcclMax);
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(seen.data(), h->d_cam_lam.p, sizeof(double) * NC, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    rc = comm_wait(h);
+    if (rc) return rc;
     for (int c = 0; c < NC; c++) h->cam_seen[c] = seen[c] > 0.0;
+    // which cameras each rank's shard touches (keyframe-range shards: a short stretch), and whether any rank's
+    // start is infeasible — every rank must take the same decisions in uba_optimise
+    struct Info { int32_t lo, hi, infeasible, pad; } mine{h->local_cam_lo, h->local_cam_hi, 0, 0};
+    for (int w = 0; w < nW; w++) if (h->win_infeasible[w]) mine.infeasible = 1;
+    std::vector<char> all;
+    rc = allgather_bytes(h, &mine, sizeof(mine), all);
+    if (rc) return rc;
+    h->rank_cam_lo.assign(h->n_ranks, 0); h->rank_cam_hi.assign(h->n_ranks, -1);
+    h->any_rank_infeasible = false;
+    for (int r = 0; r < h->n_ranks; r++) {
+      const Info& in = reinterpret_cast<const Info*>(all.data())[r];
+      h->rank_cam_lo[r] = in.lo; h->rank_cam_hi[r] = in.hi;
+      if (in.infeasible) h->any_rank_infeasible = true;
+    }
   }
   h->free_cam_h.assign(NC, -1);
   h->free_list_h.clear();
@@ -432,14 +488,15 @@ int prepare(uba_handle* h, int fixed_frames) {
       int rc = allreduce(h, h->d_cam_lam.p, 1, kNcclMax);
       if (rc) return rc;
       CU(h, cudaMemcpyAsync(&v, h->d_cam_lam.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      CU(h, cudaStreamSynchronize(h->stream));
+      rc = comm_wait(h);
+      if (rc) return rc;
       bw = (int)v;
     }
     const int beta = 6 * bw + 5;
     // the banded solver keeps {factor rows of both halves, assembled band} = 3 n (beta + 1) doubles in the window's
     // n x n slot of the matrix buffer
     const int64_t nn = h->win_n[w];
-    if (beta <= kBandMaxBeta && h->cfg.solver != 1 && 3 * nn * (beta + 1) <= nn * nn) h->win_beta[w] = beta;
+    if (beta >= 11 && beta <= kBandMaxBeta && h->cfg.solver != 1 && 3 * nn * (beta + 1) <= nn * nn) h->win_beta[w] = beta;
   }
 #ifdef UBA_EMU
   h->win_beta.assign(nW, 0);  // the emulation only has the dense stand-in solver
@@ -490,6 +547,19 @@ int prepare(uba_handle* h, int fixed_frames) {
   else h->zero_ranges.emplace_back(h->off_wpost, h->acc_total - h->off_wpost);
   CU(h, h->d_A.reserve(red));
   CU(h, h->d_rhs.reserve(6 * nfree));
+  h->L.off_Bacc = (int64_t)h->off_Bacc; h->L.off_vacc = (int64_t)h->off_vacc; h->L.off_zh = (int64_t)h->off_zh;
+  h->L.off_wlin = (int64_t)h->off_wlin; h->L.off_sacc = (int64_t)h->off_sacc; h->L.sum_end = (int64_t)h->acc_sum1;
+  h->L.off_wpost = (int64_t)h->off_wpost; h->L.off_wmax = (int64_t)h->off_wmax; h->L.off_wloc = (int64_t)h->off_wloc;
+  h->L.total = (int64_t)h->acc_total;
+  if (h->comm) {
+    const int rc = peer_exchange(h);
+    if (rc) return rc;
+  }
+  if (!h->peer_on) {
+    CU(h, h->d_stop_local.reserve(1));
+    CU(h, cudaMemsetAsync(h->d_stop_local.p, 0, sizeof(double), h->stream));
+    h->d_stop_req = h->d_stop_local.p;
+  }
   TT("prepare: free cams, band")
   // lineariser choice: 1 = generic only; otherwise the tiled kernel plus the generic one for leftovers
   h->use_tile = h->cfg.linearizer != 1;
@@ -518,6 +588,10 @@ int prepare(uba_handle* h, int fixed_frames) {
   V.w_lin = h->d_acc.p + h->off_wlin; V.w_post = h->d_acc.p + h->off_wpost; V.w_max = h->d_acc.p + h->off_wmax;
   V.w_loc = h->d_acc.p + h->off_wloc;
   V.A = h->d_A.p; V.rhs = h->d_rhs.p;
+  // consumer view: what assemble / solve / epilogue / controller read.  Without peers it IS the producer view (NCCL sums in
+  // place); with peers the sums over ranks live in d_acc_red (same layout) and the local partials stay untouched for the
+  // other ranks to pull.
+  refresh_consumer_view(h);
   // The captured iteration graph stays valid when nothing it bakes in has changed: the host-side launch geometry
   // (checked here) and the device view passed to every kernel by value (checked at launch, run_iteration_fast).
   // A sliding window re-submitted with the same shape (the per-frame case) then skips capture + instantiation.
@@ -526,6 +600,7 @@ int prepare(uba_handle* h, int fixed_frames) {
     auto put = [&](const void* ptr, size_t n) { const char* c = (const char*)ptr; sig.insert(sig.end(), c, c + n); };
     put(h->variant_off, sizeof(h->variant_off)); put(&h->max_n, sizeof(h->max_n));
     put(&h->acc_total, sizeof(h->acc_total)); put(&h->use_tile, sizeof(h->use_tile)); put(&h->use_tile2, sizeof(h->use_tile2));
+    put(&h->peer_on, sizeof(h->peer_on));
     if (nW) { put(h->win_n.data(), sizeof(int) * nW); put(h->win_beta.data(), sizeof(int) * nW); }
     if (sig != h->graph_sig) { drop_graph(h); h->graph_sig.swap(sig); }
   }
@@ -538,6 +613,165 @@ int allreduce(uba_handle* h, double* buf, size_t count, int op) {
   const int rc = h->nccl.AllReduce(buf, buf, count, kNcclDouble, op, h->comm, h->stream);
   if (rc != 0) return fail(h, UBA_ERR_NCCL, "ncclAllReduce failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?");
   return UBA_OK;
+}
+
+double env_seconds(const char* name, double dflt) {
+  const char* e = std::getenv(name);
+  if (!e || !*e) return dflt;
+  const double v = std::atof(e);
+  return v > 0.0 ? v : dflt;
+}
+
+// Waits for the handle's stream with a bound: a rank whose peers never show up (mismatched call sequences, a dead
+// process) gets UBA_ERR_NCCL after UBA_COMM_TIMEOUT_S seconds (default 120) instead of spinning inside a collective
+// until some watchdog kills the job; asynchronous NCCL errors are polled meanwhile.
+int comm_wait(uba_handle* h) {
+  if (!h->comm) {
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    return e == cudaSuccess ? UBA_OK : fail(h, UBA_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(e));
+  }
+  static const double limit = env_seconds("UBA_COMM_TIMEOUT_S", 120.0);
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int spin = 0;; spin++) {
+    const cudaError_t q = cudaStreamQuery(h->stream);
+    if (q == cudaSuccess) return UBA_OK;
+    if (q != cudaErrorNotReady) return fail(h, UBA_ERR_CUDA, "stream failed while waiting for the other ranks: %s", cudaGetErrorString(q));
+    if ((spin & 255) == 255) {
+      int async = 0;
+      if (h->nccl.CommGetAsyncError && h->nccl.CommGetAsyncError(h->comm, &async) == 0 && async != 0) {
+        if (h->nccl.CommAbort) h->nccl.CommAbort(h->comm);
+        h->comm = nullptr; h->peer_on = false;
+        return fail(h, UBA_ERR_NCCL, "NCCL reported an asynchronous error: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(async) : "?");
+      }
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit) {
+        if (h->nccl.CommAbort) h->nccl.CommAbort(h->comm);
+        h->comm = nullptr; h->peer_on = false;
+        return fail(h, UBA_ERR_NCCL, "rank %d waited %.0f s for the other ranks (mismatched call sequence?): communicator aborted", h->rank, limit);
+      }
+    }
+  }
+}
+
+// every rank's `bytes` bytes, rank-major, into `all` (set-up exchanges only)
+int allgather_bytes(uba_handle* h, const void* mine, size_t bytes, std::vector<char>& all) {
+  const size_t n = (size_t)h->n_ranks;
+  all.resize(n * bytes);
+  if (!h->nccl.AllGather) return fail(h, UBA_ERR_NCCL, "libnccl lacks ncclAllGather");
+  CU(h, h->d_xchg.reserve((n + 1) * bytes));
+  CU(h, cudaMemcpyAsync(h->d_xchg.p + n * bytes, mine, bytes, cudaMemcpyHostToDevice, h->stream));
+  const int rc = h->nccl.AllGather(h->d_xchg.p + n * bytes, h->d_xchg.p, bytes, kNcclChar, h->comm, h->stream);
+  if (rc != 0) return fail(h, UBA_ERR_NCCL, "ncclAllGather failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?");
+  CU(h, cudaMemcpyAsync(all.data(), h->d_xchg.p, n * bytes, cudaMemcpyDeviceToHost, h->stream));
+  return comm_wait(h);
+}
+
+void peer_close(uba_handle* h) {
+#ifndef UBA_EMU
+  for (int r = 0; r < kMaxRanks; r++) {
+    if (h->mapped_acc[r]) { cudaIpcCloseMemHandle(h->mapped_acc[r]); h->mapped_acc[r] = nullptr; }
+    if (h->mapped_ctl[r]) { cudaIpcCloseMemHandle(h->mapped_ctl[r]); h->mapped_ctl[r] = nullptr; }
+  }
+#endif
+  h->exchanged_acc = h->exchanged_ctl = nullptr;
+  h->peer_on = false;
+}
+
+// Maps every rank's accumulator block and control block into this process (CUDA IPC) and fills the PeerView.  Called
+// from prepare() on every rank of a point-sharded handle; re-done only when some rank's buffers moved.  When IPC is not
+// available between two of the GPUs every rank falls back to the NCCL data path together.
+int peer_exchange(uba_handle* h) {
+#ifdef UBA_EMU
+  h->peer_on = false;
+  return UBA_OK;
+#else
+  const int n = h->n_ranks, nW = h->nW;
+  if (!h->peer_wanted || n > kMaxRanks) { h->peer_on = false; return UBA_OK; }
+  // control block layout
+  const size_t off_flags = 0, off_epoch = off_flags + 8 * (size_t)n, off_err = off_epoch + 32, off_stop = off_err + 8,
+               off_lo = off_stop + 8, off_hi = off_lo + 4 * (size_t)((n + 1) & ~1), off_inbox = off_hi + 4 * (size_t)((n + 1) & ~1);
+  const size_t inbox_doubles = (size_t)2 * n * nW * kInboxSlots;
+  const size_t bytes = off_inbox + 8 * inbox_doubles;
+  const bool ctl_grows = bytes > h->d_ctl.cap;
+  if (ctl_grows) {
+    if (h->peer_on) { CU(h, cudaStreamSynchronize(h->stream)); }
+    CU(h, h->d_ctl.reserve(bytes + bytes / 2));
+  }
+  h->ctl_inbox_off = off_inbox; h->ctl_bytes = bytes;
+  CU(h, h->d_acc_red.reserve(h->acc_total));
+  // did anything move, on any rank?
+  double moved = (h->exchanged_acc != (void*)h->d_acc.p || h->exchanged_ctl != (void*)h->d_ctl.p || !h->peer_on) ? 1.0 : 0.0;
+  CU(h, cudaMemcpyAsync(h->d_cam_lam.p, &moved, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = allreduce(h, h->d_cam_lam.p, 1, kNcclMax);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(&moved, h->d_cam_lam.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  rc = comm_wait(h);
+  if (rc) return rc;
+  if (moved > 0.0) {
+    // Every rank must be out of its previous exchanges before mappings are replaced: the allreduce above orders that.
+    // The exchange counters restart from zero on EVERY rank (they are compared across ranks); the memset is
+    // stream-ordered before the allgather below, so nobody leaves the allgather before every control block is clean.
+    peer_close(h);
+    CU(h, cudaMemsetAsync(h->d_ctl.p, 0, h->d_ctl.cap, h->stream));
+    struct Pack { cudaIpcMemHandle_t acc, ctl; int ok; int pad; } mine;
+    std::memset(&mine, 0, sizeof(mine));
+    mine.ok = cudaIpcGetMemHandle(&mine.acc, h->d_acc.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.ctl, h->d_ctl.p) == cudaSuccess;
+    if (!mine.ok) cudaGetLastError();
+    std::vector<char> all;
+    rc = allgather_bytes(h, &mine, sizeof(mine), all);
+    if (rc) return rc;
+    bool ok = true;
+    for (int r = 0; r < n; r++) ok = ok && reinterpret_cast<const Pack*>(all.data())[r].ok;
+    if (ok) {
+      for (int r = 0; r < n && ok; r++) {
+        if (r == h->rank) continue;
+        const Pack& pk = reinterpret_cast<const Pack*>(all.data())[r];
+        ok = cudaIpcOpenMemHandle(&h->mapped_acc[r], pk.acc, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+             cudaIpcOpenMemHandle(&h->mapped_ctl[r], pk.ctl, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+      }
+      if (!ok) cudaGetLastError();
+    }
+    // all or nothing: one rank without mappings sends everybody to the NCCL path
+    double bad = ok ? 0.0 : 1.0;
+    CU(h, cudaMemcpyAsync(h->d_cam_lam.p, &bad, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = allreduce(h, h->d_cam_lam.p, 1, kNcclMax);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(&bad, h->d_cam_lam.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    rc = comm_wait(h);
+    if (rc) return rc;
+    if (bad > 0.0) {
+      peer_close(h);
+      h->peer_wanted = false;
+      if (getenv("UBA_TRACE")) fprintf(stderr, "  [trace] rank %d: no CUDA IPC between the GPUs, using the NCCL data path\n", h->rank);
+      return UBA_OK;
+    }
+    h->exchanged_acc = h->d_acc.p; h->exchanged_ctl = h->d_ctl.p;
+    h->peer_on = true;
+  }
+  // camera ranges of the shards, local copy in the control block
+  {
+    std::vector<int32_t> lohi(2 * (size_t)((n + 1) & ~1), 0);
+    for (int r = 0; r < n; r++) { lohi[r] = h->rank_cam_lo[r]; lohi[((n + 1) & ~1) + r] = h->rank_cam_hi[r]; }
+    CU(h, cudaMemcpyAsync(h->d_ctl.p + off_lo, lohi.data(), lohi.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  PeerView& P = h->P;
+  std::memset(&P, 0, sizeof(P));
+  P.rank = h->rank; P.n_ranks = n;
+  for (int r = 0; r < n; r++) {
+    unsigned char* ctl = r == h->rank ? h->d_ctl.p : (unsigned char*)h->mapped_ctl[r];
+    P.acc[r] = r == h->rank ? h->d_acc.p : (double*)h->mapped_acc[r];
+    P.flags[r] = (unsigned long long*)(ctl + off_flags);
+    P.inbox[r] = (double*)(ctl + off_inbox);
+  }
+  P.epoch = (unsigned long long*)(h->d_ctl.p + off_epoch);
+  P.err = (int32_t*)(h->d_ctl.p + off_err);
+  P.stop_req = (const double*)(h->d_ctl.p + off_stop);
+  P.cam_lo = (const int32_t*)(h->d_ctl.p + off_lo);
+  P.cam_hi = (const int32_t*)(h->d_ctl.p + off_hi);
+  P.timeout_ns = (long long)(env_seconds("UBA_PEER_TIMEOUT_S", 20.0) * 1e9);
+  h->d_stop_req = (double*)(h->d_ctl.p + off_stop);
+  return UBA_OK;
+#endif
 }
 
 struct PhaseTimer {
@@ -585,6 +819,12 @@ int run_linearize(uba_handle* h, const DebugOut& dbg) {
   t.stop();
   if (h->comm) {
     PhaseTimer tc(h, 4);
+#ifndef UBA_EMU
+    if (h->peer_on) {
+      // exchange 1 over NVLink peer memory: pull + sum the other ranks' partials into the consumer copy
+      h->timing.kernel_launches += launch_peer_reduce(h->V, h->P, h->L, h->d_acc_red.p, h->dense_override ? 1 : 0, h->stream);
+    } else
+#endif
     if (h->dense_override) {
       int rc = allreduce(h, h->d_acc.p, h->acc_sum1, kNcclSum);
       if (rc) return rc;
@@ -605,28 +845,36 @@ int run_iteration(uba_handle* h) {
   if (rc) return rc;
   {
     PhaseTimer t(h, 1);
-    h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
-    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), h->win_beta.data(), solve_small_limit(), h->stream);
+    h->timing.kernel_launches += launch_assemble(h->Vc, h->max_n, h->stream);
+    h->timing.kernel_launches += launch_solve(h->Vc, h->win_n.data(), h->win_beta.data(), solve_small_limit(), h->stream);
     t.stop();
   }
   {
     PhaseTimer t(h, 2);
-    h->timing.kernel_launches += launch_backsub(h->V, h->stream);
+    h->timing.kernel_launches += launch_backsub(h->V, h->stream);   // producer view: its partial sums go to the local block
     t.stop();
   }
   if (h->comm) {
     PhaseTimer tc(h, 4);
-    // one collective for {candidate cost, model change, norms} (sums) and the gradient max-norm: every rank writes its
-    // max into its own slot of w_rmax, the slots are summed with the rest, the max over slots is taken locally
-    h->timing.kernel_launches += launch_rank_max(h->d_acc.p + h->off_wmax, h->d_acc.p + h->off_wrmax, h->nW, h->rank, h->n_ranks, 0, h->stream);
-    rc = allreduce(h, h->d_acc.p + h->off_wpost, (size_t)h->nW * (WP_COUNT + h->n_ranks), kNcclSum);
-    if (rc) return rc;
-    h->timing.kernel_launches += launch_rank_max(h->d_acc.p + h->off_wmax, h->d_acc.p + h->off_wrmax, h->nW, h->rank, h->n_ranks, 1, h->stream);
+#ifndef UBA_EMU
+    if (h->peer_on) {
+      // exchange 2: push {candidate cost, model change, norms, gradient max, stop request} into every rank's inbox
+      h->timing.kernel_launches += launch_peer_post(h->V, h->Vc, h->P, h->stream);
+    } else
+#endif
+    {
+      // one collective for {candidate cost, model change, norms, stop requests} (sums) and the gradient max-norm: every rank
+      // writes its max into its own slot of w_rmax, the slots are summed with the rest, the max over slots is taken locally
+      h->timing.kernel_launches += launch_rank_max(h->d_acc.p + h->off_wmax, h->d_acc.p + h->off_wrmax, h->d_acc.p + h->off_wpost, h->d_stop_req, h->nW, h->rank, h->n_ranks, 0, h->stream);
+      rc = allreduce(h, h->d_acc.p + h->off_wpost, (size_t)h->nW * (WP_COUNT + h->n_ranks), kNcclSum);
+      if (rc) return rc;
+      h->timing.kernel_launches += launch_rank_max(h->d_acc.p + h->off_wmax, h->d_acc.p + h->off_wrmax, h->d_acc.p + h->off_wpost, h->d_stop_req, h->nW, h->rank, h->n_ranks, 1, h->stream);
+    }
     tc.stop();
   }
   {
     PhaseTimer t(h, 3);
-    h->timing.kernel_launches += launch_lm_update(h->V, h->stream);
+    h->timing.kernel_launches += launch_lm_update(h->Vc, h->stream);
     t.stop();
   }
   return UBA_OK;
@@ -636,15 +884,18 @@ int run_iteration(uba_handle* h) {
 // (no per-phase profiling, no NCCL on this handle).
 int run_iteration_fast(uba_handle* h) {
 #ifndef UBA_EMU
-  // Point-sharded handles launch directly: capturing the NCCL collectives into the graph works (UBA_COMM_GRAPH=1,
+  // Point-sharded handles: with the peer-memory exchanges the iteration is kernels only and is captured like the
+  // single-GPU one.  On the NCCL fallback path they launch directly: capturing the collectives works (UBA_COMM_GRAPH=1,
   // results identical) but measured SLOWER on 2 B200 (0.44 vs 0.36 ms per iteration)
   static const bool comm_graph = [] { const char* e = getenv("UBA_COMM_GRAPH"); return e && e[0] == '1'; }();
-  if (!h->profiling && (!h->comm || comm_graph)) {
-    // the graph bakes the device view in by value: any change of it (sizes, pointers, solver settings) invalidates it
-    if (h->graph_exec && std::memcmp(&h->V, &h->graph_V, sizeof(DevView)) != 0) drop_graph(h);
+  if (!h->profiling && (!h->comm || h->peer_on || comm_graph)) {
+    // the graph bakes the device views in by value: any change of them (sizes, pointers, solver settings) invalidates it
+    if (h->graph_exec && (std::memcmp(&h->V, &h->graph_V, sizeof(DevView)) != 0 || std::memcmp(&h->Vc, &h->graph_Vc, sizeof(DevView)) != 0 ||
+                          std::memcmp(&h->P, &h->graph_P, sizeof(PeerView)) != 0)) drop_graph(h);
     if (!h->graph_exec) {
       cudaGraph_t g = nullptr;
-      std::memcpy(&h->graph_V, &h->V, sizeof(DevView));
+      std::memcpy(&h->graph_V, &h->V, sizeof(DevView)); std::memcpy(&h->graph_Vc, &h->Vc, sizeof(DevView));
+      std::memcpy(&h->graph_P, &h->P, sizeof(PeerView));
       const int64_t before = h->timing.kernel_launches, lin_before = h->timing.linearize_launches;
       if (getenv("UBA_TRACE")) fprintf(stderr, "  [trace] capturing the iteration graph\n");
       CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -769,6 +1020,8 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     for (int w = 0; w < nW; w++) bad += count_window(w, false);
   }
   if (bad) return fail(h, UBA_ERR_INVALID_ARGUMENT, "camIdx / ptIdx out of range (%d offences)", bad);
+  h->local_cam_lo = NC; h->local_cam_hi = -1;
+  for (int c = 0; c < NC; c++) if (h->cam_seen[c]) { h->local_cam_lo = std::min(h->local_cam_lo, c); h->local_cam_hi = std::max(h->local_cam_hi, c); }
   TT("validate+count: passes")
   for (int j = 0; j < NP; j++) h->pt_obs_off_caller[j + 1] = h->pt_obs_off_caller[j] + cnt[j];
   TT("validate+count")
@@ -1007,6 +1260,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   h->V.rec_stride = rec_stride;
   h->ws_h.assign(nW, WinState{});
   h->state = 1;
+  h->device_dirty = false;
   return UBA_OK;
 }
 
@@ -1032,9 +1286,9 @@ int compute_covariances(uba_handle* h) {
   int rc = run_linearize(h, none);
   h->dense_override = false;
   if (!rc) {
-    h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
-    h->timing.kernel_launches += launch_solve(h->V, h->win_n.data(), zeros.data(), solve_small_limit(), h->stream, true);
-    h->timing.kernel_launches += launch_cov_blocks(h->V, (int)h->free_list_h.size(), h->max_n, h->d_cov.p, h->stream);
+    h->timing.kernel_launches += launch_assemble(h->Vc, h->max_n, h->stream);
+    h->timing.kernel_launches += launch_solve(h->Vc, h->win_n.data(), zeros.data(), solve_small_limit(), h->stream, true);
+    h->timing.kernel_launches += launch_cov_blocks(h->Vc, (int)h->free_list_h.size(), h->max_n, h->d_cov.p, h->stream);
   }
   h->profiling = was_profiling;
   h->timing.kernel_launches += launch_cov_state(h->V, 0, h->stream);
@@ -1052,33 +1306,6 @@ int compute_covariances(uba_handle* h) {
 extern "C" {
 
 int uba_version(void) { return UBA_VERSION; }
-
-void uba_config_default(uba_config* c) {
-  if (!c) return;
-  std::memset(c, 0, sizeof(*c));
-  c->loss_kind = UBA_LOSS_HUBER;          // new ceres::HuberLoss(1.0), BundleAdjuster.h:397,:447
-  c->loss_scale = 1.0;
-  c->max_iterations = 50;                 // Ceres default
-  c->function_tolerance = 1e-3;           // :419,:466
-  c->gradient_tolerance = 1e-10;
-  c->parameter_tolerance = 1e-8;
-  c->initial_radius = 1e4;
-  c->max_radius = 1e16;
-  c->min_radius = 1e-32;
-  c->min_relative_decrease = 1e-3;
-  c->min_lm_diagonal = 1e-6;
-  c->max_lm_diagonal = 1e32;
-  c->max_consecutive_invalid_steps = 5;
-  c->max_solver_time_s = 1.0;             // :417,:464
-  c->fixed_iterations = 0;
-  c->jacobi_scaling = 1;
-  c->use_bounds = 1;                      // :455-460
-  const char* lr = std::getenv("LOCAL_RANK");
-  c->device = lr ? std::atoi(lr) : 0;
-  c->linearizer = 0;
-  c->compute_covariance = 0;              // CalibrationParameters::compute_cov defaults to false (:42-43)
-  c->solver = 0;
-}
 
 const char* uba_last_error(const uba_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -1110,7 +1337,9 @@ void uba_destroy(uba_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graph(h);
+  peer_close(h);
   if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
+  h->d_ctl.release(); h->d_acc_red.release(); h->d_xchg.release(); h->d_stop_local.release();
   h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release(); h->h_obs_internal.release();
   h->d_cams.release(); h->d_camR.release(); h->d_cam_s2.release(); h->d_cam_lam.release(); h->d_cam_y.release(); h->d_pts.release();
   h->d_pt_s2.release(); h->d_pt_rec.release(); h->d_feat.release(); h->d_acc.release(); h->d_A.release(); h->d_rhs.release();
@@ -1175,6 +1404,9 @@ int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearizat
   cudaSetDevice(h->device);
   const double saved_radius = h->cfg.initial_radius;
   h->cfg.initial_radius = radius;
+  // the device copy is about to be used as scratch: results of an earlier uba_optimise are gone, the getters fall back
+  // to the staged initial iterate and a later uba_optimise starts from it again
+  h->state = 1; h->device_dirty = true; h->cov_h.clear();
   int rc = upload_state(h);
   if (!rc) rc = start_solve(h, fixed_frames);
   h->cfg.initial_radius = saved_radius;
@@ -1194,9 +1426,10 @@ int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearizat
   rc = run_linearize(h, D);
   h->dense_override = false;
   if (rc) { cudaMemcpyAsync(h->d_w_beta.p, h->win_beta.data(), sizeof(int32_t) * h->nW, cudaMemcpyHostToDevice, h->stream); return rc; }
-  h->timing.kernel_launches += launch_assemble(h->V, h->max_n, h->stream);
+  h->timing.kernel_launches += launch_assemble(h->Vc, h->max_n, h->stream);
   CU(h, cudaMemcpyAsync(h->d_w_beta.p, h->win_beta.data(), sizeof(int32_t) * h->nW, cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaStreamSynchronize(h->stream));
+  rc = comm_wait(h);
+  if (rc) return rc;
   CU(h, cudaGetLastError());
   std::vector<double> tmp;
   auto fetch = [&](const double* dev, size_t n) -> const double* { tmp.resize(n); cudaMemcpy(tmp.data(), dev, n * sizeof(double), cudaMemcpyDeviceToHost); return tmp.data(); };
@@ -1206,14 +1439,14 @@ int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearizat
   if (out->C) { const double* r = fetch(D.C, n_C); for (int s = 0; s < NP; s++) std::memcpy(out->C + (size_t)h->pt_order[s] * 9, r + (size_t)s * 9, sizeof(double) * 9); }
   if (out->grad_pts) { const double* r = fetch(D.grad_pts, n_g); for (int s = 0; s < NP; s++) std::memcpy(out->grad_pts + (size_t)h->pt_order[s] * 3, r + (size_t)s * 3, sizeof(double) * 3); }
   if (out->lm_diag_pts) { const double* r = fetch(D.lam_pts, n_l); for (int s = 0; s < NP; s++) std::memcpy(out->lm_diag_pts + (size_t)h->pt_order[s] * 3, r + (size_t)s * 3, sizeof(double) * 3); }
-  if (out->cost) { const double* r = fetch(h->V.w_lin, (size_t)h->nW * WL_COUNT); for (int w = 0; w < h->nW; w++) out->cost[w] = r[(size_t)w * WL_COUNT + WL_COST]; }
-  if (out->grad_cams) { const double* r = fetch(h->V.vacc, (size_t)NC * 6); std::memcpy(out->grad_cams, r, sizeof(double) * 6 * NC); }
+  if (out->cost) { const double* r = fetch(h->Vc.w_lin, (size_t)h->nW * WL_COUNT); for (int w = 0; w < h->nW; w++) out->cost[w] = r[(size_t)w * WL_COUNT + WL_COST]; }
+  if (out->grad_cams) { const double* r = fetch(h->Vc.vacc, (size_t)NC * 6); std::memcpy(out->grad_cams, r, sizeof(double) * 6 * NC); }
   if (out->lm_diag_cams) {
     const double* r = fetch(h->V.cam_lam, (size_t)NC * 6);
     for (int c = 0; c < NC; c++) for (int a = 0; a < 6; a++) out->lm_diag_cams[(size_t)c * 6 + a] = h->free_cam_h[c] >= 0 ? r[(size_t)c * 6 + a] : 0.0;
   }
   if (out->B) {
-    const double* r = fetch(h->V.Bacc, (size_t)NC * 36);
+    const double* r = fetch(h->Vc.Bacc, (size_t)NC * 36);
     for (int c = 0; c < NC; c++) for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++)
       out->B[(size_t)c * 36 + a * 6 + b] = r[(size_t)c * 36 + std::min(a, b) * 6 + std::max(a, b)];
   }
@@ -1230,16 +1463,19 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
   const auto t_start = std::chrono::steady_clock::now();
   cudaEventRecord(h->ev[2], h->stream);
   auto tt_ = std::chrono::steady_clock::now();
-  int rc = start_solve(h, fixed_frames);
+  int rc = UBA_OK;
+  if (h->device_dirty) { rc = upload_state(h); if (rc) return rc; h->device_dirty = false; }
+  rc = start_solve(h, fixed_frames);
   if (rc) return rc;
   TT("optimise: start_solve")
   const bool fixedK = h->cfg.fixed_iterations > 0;
   const int max_it = fixedK ? h->cfg.fixed_iterations : h->cfg.max_iterations;
   const bool timed = !fixedK && h->cfg.max_solver_time_s > 0.0;
-  // infeasible windows fail before the first iteration
+  // infeasible windows fail before the first iteration; on a point-sharded handle the window fails on EVERY rank when any
+  // rank's shard starts outside the box (agreed in prepare), so that all ranks run the same sequence of exchanges
   std::vector<char> infeasible(h->nW, 0);
   bool any_infeasible = false;
-  for (int w = 0; w < h->nW; w++) if (!window_feasible(h, w)) { infeasible[w] = 1; any_infeasible = true; }
+  for (int w = 0; w < h->nW; w++) if (!window_feasible(h, w) || (h->comm && h->any_rank_infeasible)) { infeasible[w] = 1; any_infeasible = true; }
   if (any_infeasible) {
     CU(h, cudaStreamSynchronize(h->stream));
     CU(h, cudaMemcpy(h->ws_h.data(), h->d_ws.p, sizeof(WinState) * h->nW, cudaMemcpyDeviceToHost));
@@ -1248,6 +1484,8 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
     CU(h, cudaMemcpy(h->d_ws.p, h->ws_h.data(), sizeof(WinState) * h->nW, cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->d_n_active.p, &n_act, sizeof(int), cudaMemcpyHostToDevice));
   }
+  CU(h, cudaMemsetAsync(h->d_stop_req, 0, sizeof(double), h->stream));
+  bool stop_sent = false;
   for (int it = 0; it < max_it; it++) {
     rc = run_iteration_fast(h);
     if (rc) return rc;
@@ -1256,19 +1494,34 @@ int uba_optimise(uba_handle* h, int fixed_frames, uba_summary* summaries) {
       // convergence is decided on the device; the host only needs to know when every window is done
       int n_act = 0;
       CU(h, cudaMemcpyAsync(&n_act, h->d_n_active.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CU(h, cudaStreamSynchronize(h->stream));
+      rc = comm_wait(h);
+      if (rc) return rc;
       if (n_act <= 0) break;
-      if (timed && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() >= h->cfg.max_solver_time_s) break;
+      if (timed && std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count() >= h->cfg.max_solver_time_s) {
+        // wall-clock cap (:417,:464).  Alone, this rank just stops.  Point-sharded, every rank has its own clock: the request
+        // travels with the next iteration's exchange and the controller stops all ranks after that iteration.
+        if (!h->comm) break;
+        if (!stop_sent) { const double one = 1.0; CU(h, cudaMemcpyAsync(h->d_stop_req, &one, sizeof(double), cudaMemcpyHostToDevice, h->stream)); stop_sent = true; }
+      }
     }
   }
   cudaEventRecord(h->ev[3], h->stream);
-  CU(h, cudaStreamSynchronize(h->stream));
+  rc = comm_wait(h);
+  if (rc) return rc;
   CU(h, cudaGetLastError());
+  if (h->peer_on) {
+    int32_t perr = 0;
+    CU(h, cudaMemcpy(&perr, h->P.err, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (perr) {
+      CU(h, cudaMemset(h->P.err, 0, sizeof(int32_t)));
+      return fail(h, UBA_ERR_NCCL, "rank %d: rank %d did not reach an exchange of the iteration within the time-out (UBA_PEER_TIMEOUT_S)", h->rank, perr - 1);
+    }
+  }
   TT("optimise: iterations")
   float ms = 0; cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]);
   h->timing.total_ms += ms;
   h->cov_h.clear();
-  if (h->cfg.compute_covariance && !h->comm) {
+  if (h->cfg.compute_covariance) {
     rc = compute_covariances(h);
     if (rc) return rc;
   }
@@ -1377,7 +1630,11 @@ int uba_comm_init(uba_handle* h, const char id[UBA_NCCL_UNIQUE_ID_BYTES], int ra
   if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return UBA_ERR_INVALID_ARGUMENT;
   std::string err;
   if (!load_nccl(h->nccl, err)) return fail(h, UBA_ERR_NCCL, "%s", err.c_str());
+  // one communicator per handle, set before the problem: the camera tables of a resident problem were built without it
+  if (h->comm) return fail(h, UBA_ERR_STATE, "uba_comm_init: this handle already has a communicator");
+  if (h->state != 0) return fail(h, UBA_ERR_STATE, "uba_comm_init must come before uba_set_problem");
   cudaSetDevice(h->device);
+  if (const char* e = std::getenv("UBA_PEER")) h->peer_wanted = !(e[0] == '0');
   Id128 u; std::memcpy(u.internal, id, UBA_NCCL_UNIQUE_ID_BYTES);
   const int rc = h->nccl.CommInitRank(&h->comm, n_ranks, u, rank);
   if (rc != 0) { h->comm = nullptr; return fail(h, UBA_ERR_NCCL, "ncclCommInitRank failed: %s", h->nccl.GetErrorString ? h->nccl.GetErrorString(rc) : "?"); }
@@ -1409,6 +1666,7 @@ int uba_time_linearize(uba_handle* h, int fixed_frames, double radius, int repea
   cudaSetDevice(h->device);
   const double saved = h->cfg.initial_radius;
   h->cfg.initial_radius = radius;
+  h->state = 1; h->device_dirty = true; h->cov_h.clear();
   int rc = upload_state(h);
   if (!rc) rc = start_solve(h, fixed_frames);
   h->cfg.initial_radius = saved;
@@ -1438,6 +1696,7 @@ int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int do_f
   const int saved_fixed = h->cfg.fixed_iterations;
   h->cfg.fixed_iterations = iterations;  // no convergence tests: every iteration runs all phases
   fill_view_static(h);
+  h->state = 1; h->device_dirty = true; h->cov_h.clear();
   int rc = upload_state(h);
   if (!rc) rc = start_solve(h, fixed_frames);
   // Each iteration sits between its own pair of events (the L2 flush before it is outside the pair); the host does not
@@ -1469,13 +1728,15 @@ int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int do_f
   return UBA_OK;
 }
 
-// debug: first `count` doubles of the generic lineariser's scratch (kernel instrumentation builds only)
+#ifdef UBA_BAND_TIMING
+// instrumentation builds only (scripts/band_timing.py): the clocks the band solver leaves in the generic lineariser's scratch
 int uba_debug_read_zbuf(uba_handle* h, double* out, int count) {
-  if (!h || !out) return UBA_ERR_INVALID_ARGUMENT;
+  if (!h || !out || count < 0 || (size_t)count > h->d_Zbuf.cap) return UBA_ERR_INVALID_ARGUMENT;
   cudaSetDevice(h->device);
   CU(h, cudaMemcpy(out, h->d_Zbuf.p, sizeof(double) * count, cudaMemcpyDeviceToHost));
   return UBA_OK;
 }
+#endif
 
 // fp64 FMA peak probe (TFLOP/s), used for the second roofline ceiling of the lineariser
 int uba_probe_fp64_tflops(uba_handle* h, double* tflops) {

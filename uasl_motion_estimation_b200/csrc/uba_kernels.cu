@@ -1568,236 +1568,16 @@ __global__ void __launch_bounds__(256) k_chol_update(DevView V, int w, int j0) {
 
 
 // ---- banded reduced systems (large windows whose camera co-visibility is a band: c4, c5) ------
-// Sequential band LDL^T in shared memory, one CTA, ONE barrier per scalar column:
-//   a_ik -= a_ij a_kj / a_jj  for j < k <= i <= j + beta   (the pivot reciprocal is recomputed by
-//   every thread, so no broadcast step is needed), the right-hand side is eliminated in the same
-//   step, and the unit-lower column l_ij = a_ij / a_jj goes to global memory for the backward pass.
-// The matrix is never materialised densely: entries are assembled on the fly from the Schur
-// accumulator, the camera blocks B and the LM damping.  Rows live in a ring of kBandRing rows.
+// The matrix is never materialised densely: k_assemble writes the damped band (Ab) from the Schur accumulator, the
+// camera blocks B and the LM damping; rows stream through a ring of kBandRing rows in shared memory.
 constexpr int kBandRing = 126;  // multiple of 6: a block of rows never straddles the wrap
 
-// Band Cholesky by 6-wide block columns (right-looking), one CTA.  Per block column:
-//   (2) one thread: serial 6x6 factor of the diagonal block (register resident, right-looking);
-//   (3) thread per row below the block inside the band (+ one thread for the rhs "row"): X L_kk^T = A;
-//   (4) trailing update of the band window (PER (row,row) pairs per thread, 6 FMAs each), rhs update,
-//       factor rows out to global memory (Lt[i] = {1/L_ii, L_{i,i-1}, ..., L_{i,i-beta}}).
-// Three barriers per BLOCK column.  The band was assembled by k_assemble (Ab); rows stream through a
-// ring of kBandRing rows in shared memory.  The backward substitution is blocked the same way with the
-// factor rows staged back through shared memory.
-template <int PER>
-__global__ void __launch_bounds__(256) k_chol_banded(DevView V, int w, int beta) {
-  extern __shared__ double sm[];
-  const WinState* st = &V.ws[w];
-  if (st->done) return;
-  const int f0 = V.w_free_off[w];
-  const int n = 6 * (V.w_free_off[w + 1] - f0);
-  const int bw1 = beta + 1;
-  const int ring_size = kBandRing * bw1;
-  double* ring = sm;                          // [kBandRing][bw1]: row i holds A[i][i-beta .. i]
-  double* y = ring + ring_size;               // [n + beta + 7] (tail zero-padded)
-  __shared__ int s_fail;
-  __shared__ double s_inv[6], s_z[6];
-  double* rhs = V.rhs + (size_t)6 * f0;
-  double* Lt = V.A + V.w_red_off[w];
-  const double* Ab = Lt + (size_t)2 * n * bw1;
-  const int t = threadIdx.x, nt = blockDim.x;
-  if (t == 0) s_fail = 0;
-  for (int i = t; i < n + beta + 7; i += nt) y[i] = i < n ? rhs[i] : 0.0;
-  // rows beyond n are zero-filled, so the elimination needs no bounds checks
-  auto load_rows = [&](int r0, int r1) {
-    for (int e = t; e < (r1 - r0) * bw1; e += nt) {
-      const int i = r0 + e / bw1;
-      ring[(i % kBandRing) * bw1 + e % bw1] = i < n ? Ab[(size_t)r0 * bw1 + e] : 0.0;
-    }
-  };
-  load_rows(0, kBandRing);
-  // trailing-update pairs (ti >= tk) over the beta rows below the block
-  const int npairs = beta * (beta + 1) / 2;
-  int pti[PER], ptk[PER];
-#pragma unroll
-  for (int q = 0; q < PER; q++) {
-    const int e = t + q * 256;
-    int ti = -1, tk = 0;
-    if (e < npairs) {
-      int d0 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((d0 + 1) * (d0 + 2) / 2 <= e) d0++;
-      while (d0 * (d0 + 1) / 2 > e) d0--;
-      ti = d0; tk = e - d0 * (d0 + 1) / 2;
-    }
-    pti[q] = ti; ptk[q] = tk;
-  }
-  const int nblk = n / 6;
-  int o0 = 0;                                 // ring offset of row c0 (blocks never straddle the wrap)
-#ifdef UBA_BAND_TIMING
-  long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long tq = clock64();
-#define TICK(k) { const long long now_ = clock64(); tm[k] += now_ - tq; tq = now_; }
-#else
-#define TICK(k)
-#endif
-  for (int kb = 0; kb < nblk; kb++) {
-    const int c0 = 6 * kb;
-    // ring reload (30 rows every 5 blocks): global loads are issued here and land in registers while the
-    // block is processed; they are written to the (dead) ring slots just before the block's last barrier
-    constexpr int kPre = (30 * (kBandMaxBeta + 1) + 255) / 256;
-    double pre[kPre];
-    const bool reload = kb > 0 && (kb % 5) == 0;
-    if (reload) {
-      const int r0 = c0 + kBandRing - 30;
-#pragma unroll
-      for (int q = 0; q < kPre; q++) {
-        const int e = t + q * 256;
-        const int i = r0 + e / bw1;
-        pre[q] = (e < 30 * bw1 && i < n) ? Ab[(size_t)r0 * bw1 + e] : 0.0;
-      }
-    }
-    TICK(0)
-    const double* blk = ring + o0;            // rows c0 .. c0+5: entry (c0+r, c0+c) at blk[r*bw1 + beta - r + c]
-    // (2) serial factor of the diagonal block
-    if (t == 0) {
-      double L[6][6], iv[6];
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-#pragma unroll
-        for (int c = 0; c < 6; c++) L[r][c] = c <= r ? blk[r * bw1 + beta - r + c] : 0.0;
-      if (!chol6(L, iv)) s_fail = 1;
-#pragma unroll
-      for (int r = 0; r < 6; r++) {
-        s_inv[r] = iv[r];
-#pragma unroll
-        for (int c = 0; c < 6; c++) if (c <= r) ring[o0 + r * bw1 + beta - r + c] = L[r][c];
-      }
-    }
-    TICK(1)
-    __syncthreads();
-    TICK(2)
-    // (3) rows below the block inside the band, and the rhs: X L_kk^T = A (right-looking in registers)
-    if (t <= beta) {
-      const bool is_rhs = t == beta;
-      int orow = o0 + (6 + t) * bw1; if (orow >= ring_size) orow -= ring_size;
-      double* row = ring + orow;
-      const int base = beta - 6 - t;          // column offset of (i, c0); entries with base + c < 0 lie outside the band
-      double x[6];
-#pragma unroll
-      for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((base + c >= 0) ? row[base + c] : 0.0);
-#pragma unroll
-      for (int c = 0; c < 6; c++) {
-        x[c] *= s_inv[c];
-#pragma unroll
-        for (int m = 0; m < 6; m++) if (m > c) x[m] = fma(-x[c], blk[m * bw1 + beta - m + c], x[m]);
-      }
-      if (is_rhs) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) { s_z[c] = x[c]; y[c0 + c] = x[c]; }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 6; c++) if (base + c >= 0) row[base + c] = x[c];
-      }
-    }
-    TICK(3)
-    __syncthreads();
-    TICK(4)
-    // (4) trailing update of the band window, rhs update, factor rows out
-#pragma unroll
-    for (int q = 0; q < PER; q++) {
-      const int ti = pti[q], tk = ptk[q];
-      if (ti >= 0) {
-        int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
-        int ok = o0 + (6 + tk) * bw1; if (ok >= ring_size) ok -= ring_size;
-        const double* ri = ring + oi + (beta - 6 - ti);
-        const double* rk = ring + ok + (beta - 6 - tk);
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; c++) if (beta - 6 - ti + c >= 0) acc = fma(ri[c], rk[c], acc);
-        ring[oi + (beta - ti + tk)] -= acc;
-      }
-    }
-    if (t >= 64 && t < 64 + beta) {
-      // rhs: y_i -= sum_c L[i][c0+c] z_c ; and row i of the factor (this block's columns) to global memory
-      const int tt = t - 64, i = c0 + 6 + tt;
-      int orow = o0 + (6 + tt) * bw1; if (orow >= ring_size) orow -= ring_size;
-      const double* row = ring + orow;
-      const int base = beta - 6 - tt;
-      double acc = 0.0;
-#pragma unroll
-      for (int c = 0; c < 6; c++)
-        if (base + c >= 0) {
-          const double l = row[base + c];
-          acc = fma(l, s_z[c], acc);
-          if (i < n) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
-        }
-      y[i] -= acc;
-    } else if (t >= 160 && t < 166) {
-      // rows of the diagonal block
-      const int r = t - 160;
-      Lt[(size_t)(c0 + r) * bw1] = s_inv[r];
-      for (int c = 0; c < r; c++) Lt[(size_t)(c0 + r) * bw1 + (r - c)] = blk[r * bw1 + beta - r + c];
-    }
-    if (reload) {
-      const int r0 = c0 + kBandRing - 30;
-#pragma unroll
-      for (int q = 0; q < kPre; q++) {
-        const int e = t + q * 256;
-        if (e < 30 * bw1) ring[((r0 + e / bw1) % kBandRing) * bw1 + e % bw1] = pre[q];
-      }
-    }
-    TICK(5)
-    __syncthreads();
-    TICK(6)
-    o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
-  }
-#ifdef UBA_BAND_TIMING
-  if (t == 0 || t == 1 || t == 70 || t == 200) { for (int k = 0; k < 8; k++) V.Zbuf[(t == 0 ? 0 : t == 1 ? 8 : t == 70 ? 16 : 24) + k] = (double)tm[k]; }
-  tq = clock64();
-#endif
-  // backward substitution L^T x = z, blocked; factor rows staged through shared memory in chunks
-  constexpr int kChunk = 126;
-  for (int i1 = n; i1 > 0; i1 -= kChunk) {
-    const int i0 = max(0, i1 - kChunk);
-    for (int e = t; e < (i1 - i0) * bw1; e += nt) {
-      const int i = i0 + e / bw1, c = e % bw1;
-      ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
-    }
-    __syncthreads();
-    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6) {
-      const double* blk = ring + (c0 - i0) * bw1;   // row c0 + m at blk + m*bw1: [0] = 1/L, [d] = L[c0+m][c0+m-d]
-      if (t == 0) {
-        double xb[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
-#pragma unroll
-        for (int c = 5; c >= 0; c--) {
-          xb[c] *= blk[c * bw1];
-#pragma unroll
-          for (int m = 0; m < 6; m++) if (m < c) xb[m] = fma(-blk[c * bw1 + (c - m)], xb[c], xb[m]);
-        }
-#pragma unroll
-        for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_z[c] = xb[c]; }
-      }
-      __syncthreads();
-      if (t < beta) {
-        const int j = c0 - 1 - t;
-        if (j >= 0) {
-          double v = y[j];
-#pragma unroll
-          for (int c = 0; c < 6; c++) { const int d = c0 + c - j; if (d <= beta) v = fma(-blk[c * bw1 + d], s_z[c], v); }
-          y[j] = v;
-        }
-      }
-      __syncthreads();
-    }
-  }
-#ifdef UBA_BAND_TIMING
-  if (t == 0) V.Zbuf[32] = (double)(clock64() - tq);
-#endif
-  const bool failed = s_fail != 0;
-  for (int i = t; i < n; i += nt) rhs[i] = failed ? 0.0 : y[i];
-  if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
-}
-
-// Band Cholesky with LOOKAHEAD (beta >= 11): same algorithm as k_chol_banded, but the serial part of a
-// block step no longer stalls the CTA.  Warp 7 is the "panel" warp: during step k it computes, for the rows
-// of block k+1 only, their triangular solve against L_kk(k), the update of the next diagonal block, and its
+// Band Cholesky by 6-wide block columns (right-looking) with LOOKAHEAD, one CTA, beta >= 11.  Per block column:
+// serial 6x6 factor of the diagonal block; thread per row below the block inside the band (+ one for the rhs "row"):
+// X L_kk^T = A; trailing update of the band window, rhs update, factor rows out to global memory
+// (Lt[i] = {1/L_ii, L_{i,i-1}, ..., L_{i,i-beta}}).  The band was assembled by k_assemble (Ab); rows stream through a ring
+// of kBandRing rows in shared memory.  The serial part of a block step does not stall
+// the CTA: warp 7 is the "panel" warp: during step k it computes, for the rows of block k+1 only, their triangular solve against L_kk(k), the update of the next diagonal block, and its
 // 6x6 factor L_kk(k+1) — while warps 0..6 do step k's triangular solves for all rows (into Xbuf, not in place,
 // so the panel warp still sees the untouched entries) and the trailing update of the band window (minus the
 // corner the panel warp owns).  One CTA-wide barrier per block step instead of three.
@@ -2099,332 +1879,6 @@ __global__ void __launch_bounds__(256) k_chol_banded_la(DevView V, int w, int be
   if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
 
-// Two-sided band Cholesky with lookahead ("burn at both ends"), beta in [11, 35]: the CTA is split into two
-// halves of 128 threads.  Half 0 eliminates block columns [0, m) top-down, half 1 eliminates the rows below the
-// separator bottom-up, i.e. top-down on the REVERSED matrix (i' = n-1-i keeps the band structure), each exactly
-// like k_chol_banded_la (panel warp + 3 worker warps, named barriers, no CTA-wide barrier in the loop).  They
-// meet at a separator of sw >= beta+1 rows whose Schur complement  A_ss + (T - A_ss) + (B - A_ss)  is factored
-// densely by one warp; then both halves back-substitute concurrently.  Sequential depth: n/12 + sw/6 block
-// steps instead of n/6.
-struct BandHalf {
-  int dir;        // 0: natural order, 1: reversed
-  int nh;         // rows of the half's local system (eliminated rows + separator)
-  int ne;         // rows eliminated by this half (multiple of 6)
-};
-
-template <int PER>
-__global__ void __launch_bounds__(256) k_chol_banded_la2(DevView V, int w, int beta) {
-  extern __shared__ double sm[];
-  const WinState* st = &V.ws[w];
-  if (st->done) return;
-  constexpr int NH = 128, NWORKH = 96;        // threads per half; workers per half (warp 3 of the half is the panel warp)
-  const int f0 = V.w_free_off[w];
-  const int n = 6 * (V.w_free_off[w + 1] - f0);
-  const int bw1 = beta + 1;
-  const int sw = ((beta + 1 + 5) / 6) * 6;    // separator rows
-  const int m = (((n - sw) / 2) / 6) * 6;     // rows eliminated by the top half
-  const int ring_size = kBandRing * bw1;
-  const int t = threadIdx.x;
-  const int half = t >> 7, tl = t & 127;
-  BandHalf H;
-  H.dir = half; H.ne = half == 0 ? m : n - m - sw; H.nh = H.ne + sw;
-  // shared memory: per half {ring, y, Xbuf}, then the separator system
-  const int ylen = (n - m) + beta + 8;        // >= nh of either half + tail
-  double* base = sm + (size_t)half * (ring_size + ylen + beta * 6 + 8);
-  double* ring = base;
-  double* y = ring + ring_size;
-  double* Xbuf = y + ylen;
-  double* sep = sm + 2 * (size_t)(ring_size + ylen + beta * 6 + 8);   // [sw][sw + 1] + rhs [sw]
-  __shared__ int s_fail;
-  __shared__ double s_Lkk[2][2][36], s_invk[2][2][6], s_z[2][6], s_xp[2][36], s_corner[2][21];
-  double* rhs = V.rhs + (size_t)6 * f0;
-  double* A0 = V.A + V.w_red_off[w];
-  double* Lt = A0 + (size_t)half * n * bw1;   // this half's factor rows (local row numbering)
-  const double* Ab = A0 + (size_t)2 * n * bw1;
-  const bool panel = tl >= NWORKH;
-  const int pl = tl - NWORKH;
-  if (t == 0) s_fail = 0;
-  // local lower-band entry (i, k = i - beta + c) of this half's system
-  auto band_entry = [&](int i, int c) -> double {
-    if (i >= H.nh || i - beta + c < 0) return 0.0;
-    return H.dir == 0 ? Ab[(size_t)i * bw1 + c] : Ab[(size_t)(n - 1 - i + beta - c) * bw1 + c];
-  };
-  for (int i = tl; i < ylen; i += NH) y[i] = i < H.nh ? rhs[H.dir == 0 ? i : n - 1 - i] : 0.0;
-  for (int e = tl; e < kBandRing * bw1; e += NH) ring[e] = band_entry(e / bw1, e % bw1);
-  const int npairs = beta * (beta + 1) / 2;
-  int pti[PER], ptk[PER];
-#pragma unroll
-  for (int q = 0; q < PER; q++) {
-    const int e = tl + q * NWORKH;
-    int ti = -1, tk = 0;
-    if (!panel && e < npairs) {
-      int d0 = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while ((d0 + 1) * (d0 + 2) / 2 <= e) d0++;
-      while (d0 * (d0 + 1) / 2 > e) d0--;
-      ti = d0; tk = e - d0 * (d0 + 1) / 2;
-      if (ti < 6) ti = -1;                    // corner pair: owned by the panel warp
-    }
-    pti[q] = ti; ptk[q] = tk;
-  }
-  // corner entry of panel lane pl: (r, e), e <= r
-  int cr = 0, ce = pl;
-  while (ce > cr) { ce -= cr + 1; cr++; }
-#ifdef UBA_LA2_ONEHALF
-  const int nblk = half == 0 ? H.ne / 6 : 0;   // timing experiment: bottom half idle (results are wrong)
-#else
-  const int nblk = H.ne / 6;
-#endif
-  __syncthreads();
-  if (tl == NWORKH) {                         // prologue: factor of block 0
-    double L[6][6], iv[6];
-#pragma unroll
-    for (int r = 0; r < 6; r++)
-#pragma unroll
-      for (int c = 0; c < 6; c++) L[r][c] = c <= r ? ring[r * bw1 + beta - r + c] : 0.0;
-    if (!chol6(L, iv)) s_fail = 1;
-#pragma unroll
-    for (int r = 0; r < 6; r++) {
-      s_invk[half][0][r] = iv[r];
-#pragma unroll
-      for (int c = 0; c < 6; c++) s_Lkk[half][0][r * 6 + c] = L[r][c];
-    }
-  }
-  __syncthreads();
-  int o0 = 0;
-  for (int kb = 0; kb < nblk; kb++) {
-    const int c0 = 6 * kb, par = kb & 1;
-    const double* Lk = s_Lkk[half][par];
-    const double* ivk = s_invk[half][par];
-    if (panel) {
-      {
-        // the block after the last eliminated one is the first separator block: it still needs its corner update
-        // (written back to the ring), it is just not factored here
-        const bool last = kb + 1 == nblk;
-        int on = o0 + 6 * bw1; if (on >= ring_size) on -= ring_size;
-        if (pl < 6) {
-          const double* row = ring + on + pl * bw1 + (beta - 6 - pl);
-          double x[6];
-#pragma unroll
-          for (int c = 0; c < 6; c++) x[c] = row[c];
-#pragma unroll
-          for (int c = 0; c < 6; c++) {
-            x[c] *= ivk[c];
-#pragma unroll
-            for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
-          }
-#pragma unroll
-          for (int c = 0; c < 6; c++) s_xp[half][pl * 6 + c] = x[c];
-        }
-        __syncwarp();
-        if (pl < 21) {
-          double v = ring[on + cr * bw1 + beta - cr + ce];
-#pragma unroll
-          for (int mm = 0; mm < 6; mm++) v = fma(-s_xp[half][cr * 6 + mm], s_xp[half][ce * 6 + mm], v);
-          if (last) ring[on + cr * bw1 + beta - cr + ce] = v;
-          s_corner[half][pl] = v;
-        }
-        __syncwarp();
-        if (pl == 0 && !last) {
-          double L[6][6], iv[6];
-#pragma unroll
-          for (int r = 0; r < 6; r++)
-#pragma unroll
-            for (int c = 0; c < 6; c++) L[r][c] = c <= r ? s_corner[half][r * (r + 1) / 2 + c] : 0.0;
-          if (!chol6(L, iv)) s_fail = 1;
-#pragma unroll
-          for (int r = 0; r < 6; r++) {
-            s_invk[half][par ^ 1][r] = iv[r];
-#pragma unroll
-            for (int c = 0; c < 6; c++) s_Lkk[half][par ^ 1][r * 6 + c] = L[r][c];
-          }
-        }
-      }
-    } else {
-      constexpr int kPre = (30 * 36 + NWORKH - 1) / NWORKH;   // beta <= 35
-      double pre[kPre];
-      const bool reload = kb > 0 && (kb % 5) == 0;
-      if (reload) {
-        const int r0 = c0 + kBandRing - 30;
-#pragma unroll
-        for (int q = 0; q < kPre; q++) {
-          const int e = tl + q * NWORKH;
-          pre[q] = e < 30 * bw1 ? band_entry(r0 + e / bw1, e % bw1) : 0.0;
-        }
-      }
-      if (tl <= beta) {
-        const bool is_rhs = tl == beta;
-        int orow = o0 + (6 + tl) * bw1; if (orow >= ring_size) orow -= ring_size;
-        const double* row = ring + orow;
-        const int basec = beta - 6 - tl;
-        double x[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++) x[c] = is_rhs ? y[c0 + c] : ((basec + c >= 0) ? row[basec + c] : 0.0);
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-          x[c] *= ivk[c];
-#pragma unroll
-          for (int mm = 0; mm < 6; mm++) if (mm > c) x[mm] = fma(-x[c], Lk[mm * 6 + c], x[mm]);
-        }
-        if (is_rhs) {
-#pragma unroll
-          for (int c = 0; c < 6; c++) { s_z[half][c] = x[c]; y[c0 + c] = x[c]; }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 6; c++) Xbuf[tl * 6 + c] = x[c];
-        }
-      }
-      if (half == 0) asm volatile("bar.sync 1, %0;" ::"n"(NWORKH)); else asm volatile("bar.sync 2, %0;" ::"n"(NWORKH));
-#pragma unroll
-      for (int q = 0; q < PER; q++) {
-        const int ti = pti[q], tk = ptk[q];
-        if (ti >= 0) {
-          int oi = o0 + (6 + ti) * bw1; if (oi >= ring_size) oi -= ring_size;
-          const double* xi = Xbuf + ti * 6;
-          const double* xk = Xbuf + tk * 6;
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < 6; c++) acc = fma(xi[c], xk[c], acc);
-          ring[oi + (beta - ti + tk)] -= acc;
-        }
-      }
-      if (tl >= 32 && tl < 32 + beta) {
-        const int tt = tl - 32, i = c0 + 6 + tt;
-        const int basec = beta - 6 - tt;
-        double acc = 0.0;
-#pragma unroll
-        for (int c = 0; c < 6; c++) {
-          const double l = Xbuf[tt * 6 + c];
-          acc = fma(l, s_z[half][c], acc);
-          if (basec + c >= 0 && i < H.nh) Lt[(size_t)i * bw1 + (6 + tt - c)] = l;
-        }
-        y[i] -= acc;
-      } else if (tl >= 80 && tl < 86) {
-        const int r = tl - 80;
-        Lt[(size_t)(c0 + r) * bw1] = ivk[r];
-        for (int c = 0; c < r; c++) Lt[(size_t)(c0 + r) * bw1 + (r - c)] = Lk[r * 6 + c];
-      }
-      if (reload) {
-        const int r0 = c0 + kBandRing - 30;
-#pragma unroll
-        for (int q = 0; q < kPre; q++) {
-          const int e = tl + q * NWORKH;
-          if (e < 30 * bw1) ring[((r0 + e / bw1) % kBandRing) * bw1 + e % bw1] = pre[q];
-        }
-      }
-    }
-    if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
-    o0 += 6 * bw1; if (o0 >= ring_size) o0 -= ring_size;
-  }
-  __syncthreads();
-  // ---- separator: S = T + B - A_ss (lower), rhs = y_top + y_bot - b_s, in ORIGINAL separator order ----
-  {
-    double* ring0 = sm; double* y0 = ring0 + ring_size;
-    double* ring1 = sm + (ring_size + ylen + beta * 6 + 8); double* y1 = ring1 + ring_size;
-    const int ne0 = m, ne1 = n - m - sw;
-    const int lds = sw + 1;
-    for (int e = t; e < sw * sw; e += 256) {
-      const int a = e / sw, b = e % sw;
-      if (b > a) continue;
-      double v = 0.0;
-      if (a - b <= beta) {
-        const int it = ne0 + a, kt = ne0 + b;                    // top: local = original
-        const double tv = ring0[(it % kBandRing) * bw1 + (kt - it + beta)];
-        const int ib = ne1 + (sw - 1 - b), kbm = ne1 + (sw - 1 - a);   // bottom (reversed): row >= col
-        const double bv = ring1[(ib % kBandRing) * bw1 + (kbm - ib + beta)];
-        v = tv + bv - Ab[(size_t)(m + a) * bw1 + (b - a + beta)];
-      }
-      sep[a * lds + b] = v;
-    }
-    for (int a = t; a < sw; a += 256) sep[sw * lds + a] = y0[ne0 + a] + y1[ne1 + (sw - 1 - a)] - rhs[m + a];
-    __syncthreads();
-    if (t < 32) {                             // dense Cholesky + solve of the sw x sw separator system by one warp
-      double* rs = sep + sw * lds;
-      for (int j = 0; j < sw; j++) {
-        const double d = sep[j * lds + j];
-        if (t == 0 && (!(d > 0.0) || !isfinite(d))) s_fail = 1;
-        const double iv = rsqrt(fmax(d, 1e-300));
-        __syncwarp();
-        for (int i = j + t; i < sw; i += 32) sep[i * lds + j] *= iv;   // includes the diagonal: d * iv = sqrt(d)
-        __syncwarp();
-        for (int e = t; e < (sw - j - 1) * (sw - j - 1); e += 32) {
-          const int i = j + 1 + e / (sw - j - 1), k = j + 1 + e % (sw - j - 1);
-          if (k <= i) sep[i * lds + k] = fma(-sep[i * lds + j], sep[k * lds + j], sep[i * lds + k]);
-        }
-        __syncwarp();
-      }
-      for (int i = 0; i < sw; i++) {          // forward
-        double sacc = 0.0;
-        for (int k = t; k < i; k += 32) sacc = fma(sep[i * lds + k], rs[k], sacc);
-        sacc = warp_sum(sacc);
-        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
-        __syncwarp();
-      }
-      for (int i = sw - 1; i >= 0; i--) {     // backward
-        double sacc = 0.0;
-        for (int k = i + 1 + t; k < sw; k += 32) sacc = fma(sep[k * lds + i], rs[k], sacc);
-        sacc = warp_sum(sacc);
-        if (t == 0) rs[i] = (rs[i] - sacc) / sep[i * lds + i];
-        __syncwarp();
-      }
-    }
-    __syncthreads();
-    // the separator solution becomes known boundary values of both halves
-    for (int a = t; a < sw; a += 256) { const double x = sep[sw * lds + a]; y0[ne0 + a] = x; y1[ne1 + (sw - 1 - a)] = x; }
-    __syncthreads();
-  }
-  // ---- backward substitution of both halves, concurrently (local numbering); separator rows are known ----
-  constexpr int kChunk = 126;
-#ifdef UBA_LA2_ONEHALF
-  for (int i1 = (half == 0 ? H.nh : 0); i1 > 0; i1 -= kChunk) {
-#else
-  for (int i1 = H.nh; i1 > 0; i1 -= kChunk) {
-#endif
-    const int i0 = max(0, i1 - kChunk);
-    for (int e = tl; e < (i1 - i0) * bw1; e += NH) {
-      const int i = i0 + e / bw1, c = e % bw1;
-      ring[e] = (c <= i) ? Lt[(size_t)i0 * bw1 + e] : 0.0;
-    }
-    if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
-    for (int c0 = i1 - 6; c0 >= i0; c0 -= 6) {
-      const double* blk = ring + (c0 - i0) * bw1;
-      const bool known = c0 >= H.ne;          // separator block: x already final
-      if (tl == 0) {
-        double xb[6];
-#pragma unroll
-        for (int c = 0; c < 6; c++) xb[c] = y[c0 + c];
-        if (!known) {
-#pragma unroll
-          for (int c = 5; c >= 0; c--) {
-            xb[c] *= blk[c * bw1];
-#pragma unroll
-            for (int mm = 0; mm < 6; mm++) if (mm < c) xb[mm] = fma(-blk[c * bw1 + (c - mm)], xb[c], xb[mm]);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 6; c++) { y[c0 + c] = xb[c]; s_z[half][c] = xb[c]; }
-      }
-      if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
-      if (tl < beta) {
-        const int j = c0 - 1 - tl;
-        if (j >= 0 && j < H.ne) {             // only pending rows; separator rows are final
-          double v = y[j];
-#pragma unroll
-          for (int c = 0; c < 6; c++) { const int d = c0 + c - j; if (d <= beta) v = fma(-blk[c * bw1 + d], s_z[half][c], v); }
-          y[j] = v;
-        }
-      }
-      if (half == 0) asm volatile("bar.sync 3, %0;" ::"n"(NH)); else asm volatile("bar.sync 4, %0;" ::"n"(NH));
-    }
-  }
-  __syncthreads();
-  const bool failed = s_fail != 0;
-  for (int i = tl; i < H.nh; i += NH) {
-    if (H.dir == 1 && i >= H.ne) continue;    // the separator is written once, by the top half
-    rhs[H.dir == 0 ? i : n - 1 - i] = failed ? 0.0 : y[i];
-  }
-  if (t == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
-}
-
 #ifndef UBA_EMU
 // Two-sided band Cholesky on a CLUSTER OF TWO CTAs (two SMs), beta in [11, 35]: CTA 0 eliminates block columns
 // [0, m) top-down, CTA 1 eliminates the rows below the separator bottom-up (top-down on the reversed matrix), each
@@ -2434,6 +1888,11 @@ __global__ void __launch_bounds__(256) k_chol_banded_la2(DevView V, int w, int b
 // separator and writes its solution into both CTAs' y; both then back-substitute their half concurrently with a sweep
 // whose triangular solves are precomputed per chunk (see the backward section).  Sequential depth: n/12 + sw/6 block
 // steps on each SM instead of n/6 on one.
+struct BandHalf {
+  int dir;        // 0: natural order, 1: reversed
+  int nh;         // rows of the half's local system (eliminated rows + separator)
+  int ne;         // rows eliminated by this half (multiple of 6)
+};
 constexpr int kC2ChunkBlocks = 34;      // blocks per chunk of the backward sweep of k_chol_banded_c2
 __host__ __device__ constexpr size_t c2_backward_doubles(int beta) {
   return (size_t)(kC2ChunkBlocks + (beta + 6) / 6 + 1) * 6 * (beta + 1) + (size_t)kC2ChunkBlocks * ((beta + 6) / 6 + 1) * 36;
@@ -3185,6 +2644,8 @@ __global__ void k_lm_update(DevView V) {
     }
     if (it < V.rec_stride) recs[it] = r;
     if (!done && it >= max_it) done = 4;  // NO_CONVERGENCE: iteration cap
+    // point-sharded handles: some rank ran into max_solver_time_s — every rank sees the same sum and stops here
+    if (!done && !fixedK && apost[WP_STOP] > 0.0) done = 4;
   }
   st.scale_ready = 1;
   st.done = done;
@@ -3288,10 +2749,14 @@ __global__ void k_ingest_feats(const TRaw* __restrict__ raw, const int32_t* __re
 
 // point-sharded runs: per-window gradient max-norm through a SUM allreduce — scatter (gather = 0): this rank's max into its
 // slot; gather (gather = 1, after the allreduce): max over the ranks' slots
-__global__ void k_rank_max(double* w_max, double* w_rmax, int nW, int rank, int n_ranks, int gather) {
+__global__ void k_rank_max(double* w_max, double* w_rmax, double* w_post, const double* stop_req, int nW, int rank, int n_ranks, int gather) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= nW) return;
-  if (!gather) { w_rmax[(size_t)w * n_ranks + rank] = w_max[w]; return; }
+  if (!gather) {
+    w_rmax[(size_t)w * n_ranks + rank] = w_max[w];
+    w_post[(size_t)w * WP_COUNT + WP_STOP] = *stop_req;   // summed with the rest: any rank over its wall-clock cap stops all
+    return;
+  }
   double m = 0.0;
   for (int r = 0; r < n_ranks; r++) m = fmax(m, w_rmax[(size_t)w * n_ranks + r]);
   w_max[w] = m;
@@ -3480,25 +2945,10 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
       const int n = h_win_n[w];
       if (h_win_beta[w] > 0) {
         const int beta = h_win_beta[w];
-        static const bool use_la = [] { const char* e = getenv("UBA_BAND_LA"); return !(e && e[0] == '0'); }();
-        // two-sided variant: correct (tests/test_gpu_parity.py runs it through UBA_BAND_LA2=1) but only ~7 % faster on
-        // c4 and slower on c5 on B200, so it is opt-in
-        static const bool use_la2 = [] { const char* e = getenv("UBA_BAND_LA2"); return e && e[0] == '1'; }();
-        if (use_la && use_la2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
-          const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
-          const size_t per_half = (size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)beta * 6 + 8;
-          const size_t smem = (2 * per_half + (size_t)(sw + 1) * (sw + 1) + 8) * sizeof(double);
-          const int per = (beta * (beta + 1) / 2 + 95) / 96;
-#define UBA_LA2_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_la2<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_la2<PP>, 1, 256, smem, st, V, w, beta); }
-          if (per <= 5) UBA_LA2_LAUNCH(5) else UBA_LA2_LAUNCH(7)
-#undef UBA_LA2_LAUNCH
-          launches++;
-          continue;
-        }
 #ifndef UBA_EMU
         // default for long bands: the two halves of the band on a cluster of two CTAs
         static const bool use_c2 = [] { const char* e = getenv("UBA_BAND_C2"); return !(e && e[0] == '0'); }();
-        if (use_la && use_c2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
+        if (use_c2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
           const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
           const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)40 * 9 + 8 + c2_backward_doubles(beta) + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
@@ -3509,7 +2959,7 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
           continue;
         }
 #endif
-        if (use_la && beta >= 11) {
+        if (beta >= 11) {
           const size_t smem = ((size_t)kBandRing * (beta + 1) + n + beta + 8 + (size_t)beta * 6 + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
 #define UBA_LA_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_la<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_la<PP>, 1, 256, smem, st, V, w, beta); }
@@ -3518,14 +2968,7 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
           launches++;
           continue;
         }
-        const size_t smem = ((size_t)kBandRing * (beta + 1) + n + beta + 8) * sizeof(double);
-        const int per = (beta * (beta + 1) / 2 + 255) / 256;
-        if (per <= 1) { cudaFuncSetAttribute(k_chol_banded<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<1>, 1, 256, smem, st, V, w, beta); }
-        else if (per <= 2) { cudaFuncSetAttribute(k_chol_banded<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<2>, 1, 256, smem, st, V, w, beta); }
-        else if (per <= 4) { cudaFuncSetAttribute(k_chol_banded<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<4>, 1, 256, smem, st, V, w, beta); }
-        else { cudaFuncSetAttribute(k_chol_banded<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded<8>, 1, 256, smem, st, V, w, beta); }
-        launches++;
-        continue;
+        continue;   // unreachable: prepare() only marks windows with beta >= 11 as banded
       }
       if (n <= max_small_n) continue;
       for (int j0 = 0; j0 < n; j0 += NB) {
@@ -3578,8 +3021,8 @@ int launch_ingest_feats(const void* raw, const int32_t* src, double* feat, int64
   return 1;
 }
 
-int launch_rank_max(double* w_max, double* w_rmax, int nW, int rank, int n_ranks, int gather, cudaStream_t st) {
-  UBA_LAUNCH(k_rank_max, (nW + 127) / 128, 128, 0, st, w_max, w_rmax, nW, rank, n_ranks, gather);
+int launch_rank_max(double* w_max, double* w_rmax, double* w_post, const double* stop_req, int nW, int rank, int n_ranks, int gather, cudaStream_t st) {
+  UBA_LAUNCH(k_rank_max, (nW + 127) / 128, 128, 0, st, w_max, w_rmax, w_post, stop_req, nW, rank, n_ranks, gather);
   return 1;
 }
 

@@ -16,6 +16,7 @@
 // cv::Point2f -> double does at BundleAdjuster.h:371.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -144,6 +145,101 @@ int64_t uba_synth_generate(const uba_synth_spec* spec, const uba_calib* calib, i
     }
   }
   return no;
+}
+
+// ---- point sharding of one large window ---------------------------------------
+// Points go to ranks by KEYFRAME RANGE: order them by (first keyframe of the track, caller index) and cut that order
+// into n_ranks pieces with equal observation counts.  A rank's tracks then start inside one contiguous camera range,
+// so its Schur products touch only that stretch of the block band of the reduced camera system (plus the track length)
+// and the cross-rank sum involves neighbouring ranks only.  Points without observations go to the last rank.
+int uba_shard_points(int n_cams, int n_pts, int64_t n_obs, const int32_t* cam_idx, const int32_t* pt_idx, int n_ranks,
+                     int32_t* pt_rank, int64_t* rank_obs, int32_t* rank_pts) {
+  if (n_cams <= 0 || n_pts < 0 || n_obs < 0 || n_ranks <= 0 || !pt_rank || (n_obs && (!cam_idx || !pt_idx))) return UBA_ERR_INVALID_ARGUMENT;
+  std::vector<int32_t> lo((size_t)n_pts, n_cams), cnt((size_t)n_pts, 0);
+  for (int64_t o = 0; o < n_obs; o++) {
+    const int c = cam_idx[o], p = pt_idx[o];
+    if (c < 0 || c >= n_cams || p < 0 || p >= n_pts) return UBA_ERR_INVALID_ARGUMENT;
+    if (c < lo[p]) lo[p] = c;
+    cnt[p]++;
+  }
+  std::vector<int64_t> before((size_t)n_cams + 2, 0);      // observations of the tracks starting before keyframe c
+  for (int p = 0; p < n_pts; p++) before[(size_t)lo[p] + 1] += cnt[p];
+  for (int c = 0; c <= n_cams; c++) before[(size_t)c + 1] += before[c];
+  std::vector<int64_t> run(before.begin(), before.end() - 1);
+  if (rank_obs) for (int r = 0; r < n_ranks; r++) rank_obs[r] = 0;
+  if (rank_pts) for (int r = 0; r < n_ranks; r++) rank_pts[r] = 0;
+  for (int p = 0; p < n_pts; p++) {
+    int r = n_ranks - 1;
+    if (cnt[p] > 0) {
+      const int64_t pos = run[lo[p]];                    // observations ahead of this track in (first keyframe, index) order
+      run[lo[p]] += cnt[p];
+      r = (int)((__int128)pos * n_ranks / (n_obs > 0 ? n_obs : 1));
+      if (r >= n_ranks) r = n_ranks - 1;
+    }
+    pt_rank[p] = r;
+    if (rank_obs) rank_obs[r] += cnt[p];
+    if (rank_pts) rank_pts[r]++;
+  }
+  return UBA_OK;
+}
+
+// One rank's shard: its points (caller order kept) with window-local point indices renumbered 0..; returns the number of
+// observations written.  Output arrays are sized from uba_shard_points' rank_obs / rank_pts.
+int64_t uba_shard_extract(int M, int n_pts, int64_t n_obs, const double* pts3, const double* feats, const int32_t* cam_idx,
+                          const int32_t* pt_idx, const int32_t* cam_id, const int32_t* pt_rank, int rank, double* pts3_out,
+                          double* feats_out, int32_t* cam_idx_out, int32_t* pt_idx_out, int32_t* cam_id_out, int32_t* pt_ids_out) {
+  if ((M != 2 && M != 4) || n_pts < 0 || n_obs < 0 || !pt_rank || (n_pts && !pts3) || (n_obs && (!feats || !cam_idx || !pt_idx)))
+    return UBA_ERR_INVALID_ARGUMENT;
+  std::vector<int32_t> local((size_t)n_pts, -1);
+  int np = 0;
+  for (int p = 0; p < n_pts; p++) {
+    if (pt_rank[p] != rank) continue;
+    local[p] = np;
+    if (pts3_out) std::memcpy(pts3_out + (size_t)np * 3, pts3 + (size_t)p * 3, sizeof(double) * 3);
+    if (pt_ids_out) pt_ids_out[np] = p;
+    np++;
+  }
+  int64_t no = 0;
+  for (int64_t o = 0; o < n_obs; o++) {
+    const int p = pt_idx[o];
+    if (p < 0 || p >= n_pts) return UBA_ERR_INVALID_ARGUMENT;
+    if (local[p] < 0) continue;
+    if (feats_out) std::memcpy(feats_out + (size_t)no * M, feats + (size_t)o * M, sizeof(double) * M);
+    if (cam_idx_out) cam_idx_out[no] = cam_idx[o];
+    if (pt_idx_out) pt_idx_out[no] = local[p];
+    if (cam_id_out) cam_id_out[no] = cam_id ? cam_id[o] : 0;
+    no++;
+  }
+  return no;
+}
+
+// Solver defaults: the reference's hard-coded options (BundleAdjuster.h:416-420,:463-467) over the Ceres defaults it
+// inherits.  Lives here (host-only translation unit) so that libuba_host.so carries it without any CUDA dependency.
+void uba_config_default(uba_config* c) {
+  if (!c) return;
+  std::memset(c, 0, sizeof(*c));
+  c->loss_kind = UBA_LOSS_HUBER;          // new ceres::HuberLoss(1.0), BundleAdjuster.h:397,:447
+  c->loss_scale = 1.0;
+  c->max_iterations = 50;                 // Ceres default
+  c->function_tolerance = 1e-3;           // :419,:466
+  c->gradient_tolerance = 1e-10;
+  c->parameter_tolerance = 1e-8;
+  c->initial_radius = 1e4;
+  c->max_radius = 1e16;
+  c->min_radius = 1e-32;
+  c->min_relative_decrease = 1e-3;
+  c->min_lm_diagonal = 1e-6;
+  c->max_lm_diagonal = 1e32;
+  c->max_consecutive_invalid_steps = 5;
+  c->max_solver_time_s = 1.0;             // :417,:464
+  c->fixed_iterations = 0;
+  c->jacobi_scaling = 1;
+  c->use_bounds = 1;                      // :455-460
+  const char* lr = std::getenv("LOCAL_RANK");
+  c->device = lr ? std::atoi(lr) : 0;
+  c->linearizer = 0;
+  c->compute_covariance = 0;              // CalibrationParameters::compute_cov defaults to false (:42-43)
+  c->solver = 0;
 }
 
 // log_map_Quat (rotation_utils.h:199-204) with acos clamped to [-1, 1].

@@ -1,38 +1,47 @@
-"""Point sharding of one large window across ranks.
+"""Point sharding of one large window across ranks — ctypes plumbing over the C ABI.
 
-Observations are point-major (BundleAdjuster.h:364-374), so a contiguous point range is a
-contiguous observation range.  Every rank keeps ALL cameras and a contiguous range of points
-balanced by observation count; the reduced camera system is the only thing that crosses ranks
-(NCCL allreduce inside libuba).  Batches of independent windows shard by window, no collective.
+The partition itself lives behind ``uba_shard_points`` / ``uba_shard_extract`` (include/uba.h; host-only code, carried by
+libuba_host.so and libuba.so) so that the C++ drop-in header can shard the same way.  Points are assigned to ranks by
+KEYFRAME RANGE: ordered by (first keyframe of the track, caller index) and cut into pieces of equal observation count.
+Every rank keeps ALL cameras; a rank's Schur products touch one stretch of the block band of the reduced camera system,
+which is the only thing that crosses ranks (summed over NVLink peer memory inside libuba).  Batches of independent
+windows shard by window, no collective.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
+from . import capi
 from .synth import Window
 
 
-def point_ranges(pt_idx: np.ndarray, n_pts: int, n_ranks: int) -> np.ndarray:
-    """[n_ranks+1] point boundaries: contiguous ranges with (nearly) equal observation counts."""
-    counts = np.bincount(np.asarray(pt_idx, dtype=np.int64), minlength=n_pts)
-    csum = np.concatenate([[0], np.cumsum(counts)])
-    total = csum[-1]
-    bounds = np.zeros(n_ranks + 1, np.int64)
-    for r in range(1, n_ranks):
-        bounds[r] = np.searchsorted(csum, total * r / n_ranks, side="left")
-    bounds[n_ranks] = n_pts
-    return np.maximum.accumulate(bounds)
+def point_ranks(win: Window, n_ranks: int, lib=None):
+    """(pt_rank [n_pts], rank_obs [n_ranks], rank_pts [n_ranks])."""
+    lib = lib or capi.host_lib()
+    pt_rank = np.zeros(win.n_pts, np.int32); rank_obs = np.zeros(n_ranks, np.int64); rank_pts = np.zeros(n_ranks, np.int32)
+    rc = lib.uba_shard_points(win.n_cams, win.n_pts, win.n_obs, capi.i32ptr(win.cam_idx), capi.i32ptr(win.pt_idx), n_ranks,
+                              capi.i32ptr(pt_rank), capi.i64ptr(rank_obs), capi.i32ptr(rank_pts))
+    if rc != 0:
+        raise capi.UbaError(rc, "uba_shard_points failed")
+    return pt_rank, rank_obs, rank_pts
 
 
-def shard_window(win: Window, rank: int, n_ranks: int) -> Window:
-    """This rank's shard: all cameras, points [b[rank], b[rank+1]) and their observations."""
-    b = point_ranges(win.pt_idx, win.n_pts, n_ranks)
-    lo, hi = int(b[rank]), int(b[rank + 1])
-    sel = (win.pt_idx >= lo) & (win.pt_idx < hi)
-    return Window(win.M, win.cams_gt, win.cams_init, win.pts_gt[lo:hi], np.ascontiguousarray(win.pts_init[lo:hi]),
-                  np.ascontiguousarray(win.feats[sel]), np.ascontiguousarray(win.cam_idx[sel]),
-                  np.ascontiguousarray(win.pt_idx[sel] - lo).astype(np.int32), np.ascontiguousarray(win.cam_id[sel]),
-                  win.fixed_frames, win.calib)
+def shard_window(win: Window, rank: int, n_ranks: int, lib=None, return_ids: bool = False):
+    """This rank's shard: all cameras, the points whose tracks start in the rank's keyframe range, their observations."""
+    lib = lib or capi.host_lib()
+    pt_rank, rank_obs, rank_pts = point_ranks(win, n_ranks, lib)
+    npt, no, M = int(rank_pts[rank]), int(rank_obs[rank]), win.M
+    pts = np.zeros((npt, 3)); feats = np.zeros((no, M)); ci = np.zeros(no, np.int32); pi = np.zeros(no, np.int32)
+    cid = np.zeros(no, np.int32); ids = np.zeros(npt, np.int32)
+    n = lib.uba_shard_extract(M, win.n_pts, win.n_obs, capi.dptr(win.pts_init), capi.dptr(win.feats), capi.i32ptr(win.cam_idx),
+                              capi.i32ptr(win.pt_idx), capi.i32ptr(win.cam_id), capi.i32ptr(pt_rank), rank, capi.dptr(pts),
+                              capi.dptr(feats), capi.i32ptr(ci), capi.i32ptr(pi), capi.i32ptr(cid), capi.i32ptr(ids))
+    if n != no:
+        raise capi.UbaError(int(n), "uba_shard_extract failed")
+    shard = Window(M, win.cams_gt, win.cams_init, np.ascontiguousarray(win.pts_gt[ids]), pts, feats, ci, pi, cid, win.fixed_frames, win.calib)
+    return (shard, ids) if return_ids else shard
 
 
 def window_ranges(n_windows: int, n_ranks: int) -> np.ndarray:

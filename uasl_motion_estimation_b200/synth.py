@@ -56,7 +56,7 @@ CONFIGS = {
 
 def generate(n_cams, n_pts, track_min, track_max, full_tracks=0, outliers=0.0, seed=BASE_SEED, M=4, fixed_frames=2,
              calib=None, lib=None, pixel_sigma=0.5, pose_t_sigma=0.05, pose_r_sigma=0.005, point_rel_sigma=0.01) -> Window:
-    lib = lib or capi.default_lib()
+    lib = lib or capi.host_lib()
     calib = calib or capi.default_calib(lib)
     spec = capi.SynthSpec(M=M, n_cams=n_cams, n_pts=n_pts, track_min=track_min, track_max=track_max, full_tracks=full_tracks,
                           outlier_fraction=outliers, pixel_sigma=pixel_sigma, pose_t_sigma=pose_t_sigma,
