@@ -276,7 +276,9 @@ def main():
     t_region = time.perf_counter()
     ms_iter = h.time_iteration(fixed, iterations=args.steps, flush_l2=True)
     barrier()
-    launches = h.timing()["kernel_launches"] - args.steps  # minus the L2-flush kernels
+    # minus the benchmark's own scaffolding: one L2-flush kernel per iteration, plus the device-side rank rendezvous that
+    # follows it on point-sharded handles (absent on the NCCL fallback path; the count is then one per step too high)
+    launches = h.timing()["kernel_launches"] - args.steps * (2 if sharded and os.environ.get("UBA_PEER", "1") != "0" else 1)
     # K iterations of a sub-millisecond step end before nvidia-smi (100 ms period) can look: keep the same load running,
     # untimed, until the sampler has had about half a second of it.  The number of extra calls is AGREED between the ranks
     # (max over ranks of the measured call time): on a point-sharded handle every call contains cross-rank exchanges, so a

@@ -241,6 +241,42 @@ int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int flus
  * roofline ceiling of the lineariser (MEASURED_PEAKS.json carries no fp64 figure). */
 int uba_probe_fp64_tflops(uba_handle* h, double* tflops);
 
+/* ---- pose-only mode: the numerical core of the frame-to-frame stereo visual odometry ---- *
+ * Replaces, for me::StereoVisualOdometry (reference src/vo/StereoVisualOdometry.cpp): project3D (:22-32, triangulation from
+ * disparity), reproject (:116-143), updateJacobian (:291-329), optimize (:165-283, Gauss-Newton or Levenberg-Marquardt on
+ * 3 Euler angles + translation with the points fixed), computeInliers (:94-114) and the RANSAC loop of process (:59-75) —
+ * with every hypothesis fitted and scored concurrently on the device.  The caller keeps drawing the random triples (the
+ * reference uses rand(), :145-163) and passes them in, so a run is reproducible against the reference's own stream.
+ * Deliberate difference: optimize()'s loop ends when a stop condition is set or after max_iter iterations; the reference's
+ * condition (:277) compares the iteration counter with the StopCondition enum value and does not terminate on ordinary
+ * data. */
+typedef struct uba_vo_params {
+  double fu1, fv1, cu1, cv1, fu2, fv2, cu2, cv2, baseline;   /* StereoVisualOdometry::parameters (vo/StereoVisualOdometry.h:26-35) */
+  int32_t method;             /* 0 Gauss-Newton (reference default), 1 Levenberg-Marquardt (VisualOdometry.h:16) */
+  int32_t max_iter;           /* default 100 */
+  double e1, e2, e3, e4;      /* mean squared reprojection error, gradient, increment, relative decrease thresholds */
+  double inlier_threshold;    /* pixels; default 2.0 */
+} uba_vo_params;
+void uba_vo_params_default(uba_vo_params* p);
+/* quads8 [n][8] float: previous left (x,y), previous right, current left, current right — StereoOdoMatchesf f1..f4.
+ * Uploads the matches, triangulates them on the device (project3D) and keeps points + observations resident. */
+int uba_vo_set_matches(uba_handle* h, const uba_vo_params* params, int n, const float* quads8);
+int uba_vo_get_points(uba_handle* h, double* pts4 /*[n][4] normalised homogeneous*/);
+/* Parity / debug: one evaluation at state6 = {roll, pitch, yaw, tx, ty, tz} over `selection`: A = J J^T [6][6], B = J r [6],
+ * residuals [n_sel][4] (observed - predicted), J [6][4 n_sel] (the layout of m_J).  Any output may be NULL. */
+int uba_vo_linearize(uba_handle* h, const double state6[6], int n_sel, const int32_t* selection, double* A36, double* B6,
+                     double* residuals, double* J);
+/* All RANSAC hypotheses at once: triples [n_hyp][3] match indices; a hypothesis is skipped (ok = 0) when twice the area of
+ * its current-left triangle is <= 1000 px^2 (:66) or its fit does not converge; best_hyp = the EARLIEST hypothesis with the
+ * most inliers (-1: none).  The inlier set of the best hypothesis stays on the device for uba_vo_refine. */
+int uba_vo_ransac(uba_handle* h, const double init6[6], int n_hyp, const int32_t* triples, int32_t* best_hyp, int32_t* inlier_counts,
+                  int32_t* hyp_ok, double* hyp_states);
+int uba_vo_get_inliers(uba_handle* h, int32_t* idx, int32_t* n_inliers);
+/* optimize() from init6 over `selection` (or, selection == NULL, over the inliers of the last uba_vo_ransac);
+ * converged = optimize()'s return value. */
+int uba_vo_refine(uba_handle* h, const double init6[6], int n_sel, const int32_t* selection, double state6[6], int32_t* converged,
+                  int32_t* iterations);
+
 /* ---- synthetic stereo-rig generator; host only, deterministic ---- */
 typedef struct uba_synth_spec {
   int32_t M;               /* 4 stereo, 2 mono/two-camera */

@@ -236,6 +236,19 @@ int uba_refsrc_vo_optimize(const double* p10, const double* opt6, int n, const d
   return ok ? 1 : 0;
 }
 
+// computeInliers() (:94-114) at a given state
+int uba_refsrc_vo_inliers(const double* p10, int n, const double* quads8, const double* state6, int32_t* inliers_out) {
+  Silence quiet;
+  StereoVisualOdometry vo(vo_params(p10, nullptr, 0, 0));
+  auto matches = vo_matches(n, quads8);
+  vo.project3D(matches);
+  vo.updateObservations(matches);
+  for (int a = 0; a < 6; a++) vo.m_state(a) = state6[a];
+  const std::vector<int> in = vo.computeInliers();
+  if (inliers_out) for (size_t i = 0; i < in.size(); i++) inliers_out[i] = in[i];
+  return (int)in.size();
+}
+
 // process() (:34-92) with RANSAC driven by the C library's rand() after srand(seed); returns its bool; the motion as
 // state6 (Euler angles + translation), the inlier indices.
 int uba_refsrc_vo_process(const double* p10, const double* opt6, int n_ransac, unsigned seed, int n, const double* quads8,

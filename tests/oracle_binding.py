@@ -56,6 +56,15 @@ def lib():
         L.uba_ref_time_iteration.restype = C.c_double
         L.uba_ref_time_iteration.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, dp, dp, dp, ip, ip, ip, C.POINTER(capi.Calib),
                                              C.POINTER(capi.Config), C.c_int, C.c_int, dp]
+        fp = C.POINTER(C.c_float); vp = C.POINTER(capi.VoParams)
+        L.uba_ref_vo_project3d.argtypes = [vp, C.c_int, fp, dp]
+        L.uba_ref_vo_linearize.argtypes = [vp, C.c_int, fp, dp, C.c_int, ip, dp, dp, dp, dp]
+        L.uba_ref_vo_optimize.restype = C.c_int
+        L.uba_ref_vo_optimize.argtypes = [vp, C.c_int, fp, dp, C.c_int, ip, dp, ip, ip]
+        L.uba_ref_vo_inliers.restype = C.c_int
+        L.uba_ref_vo_inliers.argtypes = [vp, C.c_int, fp, dp, ip]
+        L.uba_ref_vo_ransac.restype = C.c_int
+        L.uba_ref_vo_ransac.argtypes = [vp, C.c_int, fp, dp, C.c_int, ip, ip, ip, dp]
         L.uba_ref_max_threads.restype = C.c_int
         L.uba_ref_set_threads.argtypes = [C.c_int]
         _lib = L
@@ -127,3 +136,42 @@ def time_iteration(win, cfg, fixed_frames, repeats=1):
                                      capi.dptr(win.feats), capi.i32ptr(win.cam_idx), capi.i32ptr(win.pt_idx), capi.i32ptr(win.cam_id),
                                      C.byref(win.calib), C.byref(cfg), fixed_frames, repeats, capi.dptr(lin))
     return t, lin[0]
+
+
+# ---- pose-only (stereo visual odometry) oracle: oracle/uba_vo_oracle.cpp ----
+def _q(quads):
+    q = np.ascontiguousarray(quads, dtype=np.float32).reshape(-1, 8)
+    return q, q.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def vo_project3d(params, quads):
+    q, qp = _q(quads); out = np.zeros((len(q), 4))
+    lib().uba_ref_vo_project3d(C.byref(params), len(q), qp, capi.dptr(out))
+    return out
+
+
+def vo_linearize(params, quads, state, selection):
+    q, qp = _q(quads); state = capi.as_f64(state); sel = capi.as_i32(selection); n = len(sel)
+    A = np.zeros((6, 6)); B = np.zeros(6); res = np.zeros((n, 4)); J = np.zeros((6, 4 * n))
+    lib().uba_ref_vo_linearize(C.byref(params), len(q), qp, capi.dptr(state), n, capi.i32ptr(sel), capi.dptr(A), capi.dptr(B), capi.dptr(res), capi.dptr(J))
+    return dict(A=A, B=B, res=res, J=J)
+
+
+def vo_optimize(params, quads, init, selection):
+    q, qp = _q(quads); init = capi.as_f64(init); sel = capi.as_i32(selection)
+    out = np.zeros(6); it = C.c_int32(0); st = C.c_int32(0)
+    ok = lib().uba_ref_vo_optimize(C.byref(params), len(q), qp, capi.dptr(init), len(sel), capi.i32ptr(sel), capi.dptr(out), C.byref(it), C.byref(st))
+    return bool(ok), out, it.value, st.value
+
+
+def vo_inliers(params, quads, state):
+    q, qp = _q(quads); state = capi.as_f64(state); idx = np.zeros(len(q), np.int32)
+    n = lib().uba_ref_vo_inliers(C.byref(params), len(q), qp, capi.dptr(state), capi.i32ptr(idx))
+    return idx[:n].copy()
+
+
+def vo_ransac(params, quads, init, triples):
+    q, qp = _q(quads); init = capi.as_f64(init); tr = capi.as_i32(triples).reshape(-1, 3); nh = len(tr)
+    cnt = np.zeros(nh, np.int32); ok = np.zeros(nh, np.int32); st = np.zeros((nh, 6))
+    best = lib().uba_ref_vo_ransac(C.byref(params), len(q), qp, capi.dptr(init), nh, capi.i32ptr(tr), capi.i32ptr(cnt), capi.i32ptr(ok), capi.dptr(st))
+    return dict(best=best, counts=cnt, ok=ok, states=st)

@@ -39,6 +39,8 @@ def lib():
         L.uba_refsrc_vo_project3d.argtypes = [dp, C.c_int, dp, dp]
         L.uba_refsrc_vo_linearize.restype = C.c_int
         L.uba_refsrc_vo_linearize.argtypes = [dp, C.c_int, dp, dp, C.c_int, ip, dp, dp, dp, dp, dp]
+        L.uba_refsrc_vo_inliers.restype = C.c_int
+        L.uba_refsrc_vo_inliers.argtypes = [dp, C.c_int, dp, dp, ip]
         L.uba_refsrc_vo_optimize.restype = C.c_int
         L.uba_refsrc_vo_optimize.argtypes = [dp, dp, C.c_int, dp, dp, C.c_int, ip, dp, ip, ip]
         L.uba_refsrc_vo_process.restype = C.c_int
@@ -116,6 +118,12 @@ def vo_linearize(p10, quads, state, selection):
     lib().uba_refsrc_vo_linearize(capi.dptr(p10), len(quads), capi.dptr(quads), capi.dptr(state), n, capi.i32ptr(sel), capi.dptr(pred),
                                   capi.dptr(res), capi.dptr(J), capi.dptr(A), capi.dptr(B))
     return dict(pred=pred, res=res, J=J, A=A, B=B)
+
+
+def vo_inliers(p10, quads, state):
+    quads = capi.as_f64(quads); state = capi.as_f64(state); inl = np.zeros(len(quads), np.int32)
+    n = lib().uba_refsrc_vo_inliers(capi.dptr(p10), len(quads), capi.dptr(quads), capi.dptr(state), capi.i32ptr(inl))
+    return inl[:n].copy()
 
 
 def vo_optimize(p10, opt6, quads, state, selection):

@@ -77,6 +77,11 @@ class Timing(C.Structure):
                 ("comm_ms", C.c_double), ("total_ms", C.c_double), ("linearize_launches", C.c_int64), ("kernel_launches", C.c_int64)]
 
 
+class VoParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("fu1", "fv1", "cu1", "cv1", "fu2", "fv2", "cu2", "cv2", "baseline")] + \
+               [("method", C.c_int32), ("max_iter", C.c_int32)] + [(n, C.c_double) for n in ("e1", "e2", "e3", "e4", "inlier_threshold")]
+
+
 class SynthSpec(C.Structure):
     _fields_ = [("M", C.c_int32), ("n_cams", C.c_int32), ("n_pts", C.c_int32), ("track_min", C.c_int32), ("track_max", C.c_int32),
                 ("full_tracks", C.c_int32), ("outlier_fraction", C.c_double), ("pixel_sigma", C.c_double),
@@ -113,6 +118,13 @@ _SIGNATURES = [
     ("uba_synth_default_calib", None, [C.POINTER(Calib)]),
     ("uba_synth_generate", C.c_int64, [C.POINTER(SynthSpec), C.POINTER(Calib), C.c_int64, c_double_p, c_double_p, c_double_p,
                                         c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p]),
+    ("uba_vo_params_default", None, [C.POINTER(VoParams)]),
+    ("uba_vo_set_matches", C.c_int, [C.c_void_p, C.POINTER(VoParams), C.c_int, C.POINTER(C.c_float)]),
+    ("uba_vo_get_points", C.c_int, [C.c_void_p, c_double_p]),
+    ("uba_vo_linearize", C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    ("uba_vo_ransac", C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
+    ("uba_vo_get_inliers", C.c_int, [C.c_void_p, c_int32_p, c_int32_p]),
+    ("uba_vo_refine", C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int32_p, c_double_p, c_int32_p, c_int32_p]),
     ("uba_shard_points", C.c_int, [C.c_int, C.c_int, C.c_int64, c_int32_p, c_int32_p, C.c_int, c_int32_p, c_int64_p, c_int32_p]),
     ("uba_shard_extract", C.c_int64, [C.c_int, C.c_int, C.c_int64, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                        C.c_int, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
@@ -122,7 +134,7 @@ _SIGNATURES = [
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 # the subset libuba_host.so carries as well (same sources, compiled without CUDA)
 HOST_SYMBOLS = ["uba_config_default", "uba_synth_default_calib", "uba_synth_generate", "uba_log_map_quat", "uba_exp_map_quat",
-                "uba_shard_points", "uba_shard_extract"]
+                "uba_shard_points", "uba_shard_extract", "uba_vo_params_default"]
 
 
 class UbaError(RuntimeError):
@@ -368,6 +380,41 @@ class Handle:
         v = C.c_double(0)
         self._check(self.lib.uba_probe_fp64_tflops(self._h, C.byref(v)))
         return v.value
+
+    # ---- pose-only mode (stereo visual odometry) ----
+    def vo_set_matches(self, params: "VoParams", quads) -> np.ndarray:
+        q = np.ascontiguousarray(quads, dtype=np.float32).reshape(-1, 8)
+        self._check(self.lib.uba_vo_set_matches(self._h, C.byref(params), q.shape[0], q.ctypes.data_as(C.POINTER(C.c_float))))
+        self.vo_n = q.shape[0]
+        return q
+
+    def vo_points(self) -> np.ndarray:
+        a = np.zeros((self.vo_n, 4))
+        self._check(self.lib.uba_vo_get_points(self._h, dptr(a)))
+        return a
+
+    def vo_linearize(self, state, selection):
+        state = as_f64(state); sel = as_i32(selection); n = len(sel)
+        A = np.zeros((6, 6)); B = np.zeros(6); res = np.zeros((n, 4)); J = np.zeros((6, 4 * n))
+        self._check(self.lib.uba_vo_linearize(self._h, dptr(state), n, i32ptr(sel), dptr(A), dptr(B), dptr(res), dptr(J)))
+        return dict(A=A, B=B, res=res, J=J)
+
+    def vo_ransac(self, init, triples):
+        init = as_f64(init); tr = as_i32(triples).reshape(-1, 3); nh = tr.shape[0]
+        best = C.c_int32(-1); cnt = np.zeros(nh, np.int32); ok = np.zeros(nh, np.int32); st = np.zeros((nh, 6))
+        self._check(self.lib.uba_vo_ransac(self._h, dptr(init), nh, i32ptr(tr), C.byref(best), i32ptr(cnt), i32ptr(ok), dptr(st)))
+        return dict(best=best.value, counts=cnt, ok=ok, states=st)
+
+    def vo_inliers(self) -> np.ndarray:
+        n = C.c_int32(0); idx = np.zeros(max(self.vo_n, 1), np.int32)
+        self._check(self.lib.uba_vo_get_inliers(self._h, i32ptr(idx), C.byref(n)))
+        return idx[:n.value].copy()
+
+    def vo_refine(self, init, selection=None):
+        init = as_f64(init); out = np.zeros(6); conv = C.c_int32(0); it = C.c_int32(0)
+        sel = None if selection is None else as_i32(selection)
+        self._check(self.lib.uba_vo_refine(self._h, dptr(init), 0 if sel is None else len(sel), i32ptr(sel), dptr(out), C.byref(conv), C.byref(it)))
+        return bool(conv.value), out, it.value
 
     # ---- multi-GPU ----
     def comm_unique_id(self) -> bytes:

@@ -158,6 +158,7 @@ struct AccLayout {
 };
 int launch_peer_reduce(const DevView& V, const PeerView& P, const AccLayout& L, double* acc_red, int dense, cudaStream_t st);
 int launch_peer_post(const DevView& V, const DevView& Vc, const PeerView& P, cudaStream_t st);
+int launch_peer_barrier(const PeerView& P, cudaStream_t st);
 
 // launchers (uba_kernels.cu); all asynchronous on `st`; return the number of kernels launched
 int launch_cam_prep(const DevView& V, int parity, cudaStream_t st);

@@ -26,6 +26,9 @@
 
 #include "../../include/uba.h"
 #include "uba_device.h"
+#ifndef UBA_EMU
+#include "uba_vo.h"
+#endif
 
 using namespace uba;
 
@@ -192,6 +195,9 @@ struct uba_handle {
   // timing
   bool profiling = false;
   uba_timing timing{};
+#ifndef UBA_EMU
+  uba_vo_state* vo = nullptr;                 // pose-only mode (uba_vo.cu), created on first use
+#endif
 };
 
 namespace {
@@ -1338,6 +1344,9 @@ void uba_destroy(uba_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graph(h);
   peer_close(h);
+#ifndef UBA_EMU
+  uba_vo_free(h->vo);
+#endif
   if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
   h->d_ctl.release(); h->d_acc_red.release(); h->d_xchg.release(); h->d_stop_local.release();
   h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release(); h->h_obs_internal.release();
@@ -1712,6 +1721,11 @@ int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int do_f
     for (int i = 0; i < nb && !rc; i++) {
       if (do_flush) rc = flush_l2(h);
       if (rc) break;
+#ifndef UBA_EMU
+      // point-sharded: line the ranks up after the flush, otherwise the iteration's first exchange waits for whichever
+      // peer is still flushing and that wait lands inside this rank's event pair
+      if (h->peer_on) h->timing.kernel_launches += launch_peer_barrier(h->P, h->stream);
+#endif
       cudaEventRecord(evs[2 * i], h->stream);
       rc = run_iteration_fast(h);
       cudaEventRecord(evs[2 * i + 1], h->stream);
@@ -1757,3 +1771,14 @@ int uba_probe_fp64_tflops(uba_handle* h, double* tflops) {
 }
 
 }  // extern "C"
+
+#ifndef UBA_EMU
+uba_vo_state* uba_vo_get(uba_handle* h, bool create) {
+  cudaSetDevice(h->device);
+  if (!h->vo && create) h->vo = uba_vo_new();
+  return h->vo;
+}
+cudaStream_t uba_vo_stream(uba_handle* h) { return h->stream; }
+int uba_vo_fail(uba_handle* h, int code, const char* what, const char* detail) { return fail(h, code, "%s: %s", what, detail); }
+void uba_vo_count(uba_handle* h, int kernels) { h->timing.kernel_launches += kernels; }
+#endif

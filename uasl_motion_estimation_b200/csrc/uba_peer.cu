@@ -158,6 +158,21 @@ __global__ void __launch_bounds__(128) k_peer_post(DevView V, DevView Vc, PeerVi
   }
 }
 
+// Plain rendezvous of the ranks on the device (no payload).  The benchmark puts one between the L2 flush and the start
+// event of every timed iteration, so that an iteration's exchanges do not wait for a peer that is still flushing.
+__global__ void k_peer_barrier(PeerView P) {
+  if (threadIdx.x == 0) {
+    const unsigned long long e = *(volatile unsigned long long*)&P.epoch[0] + 1;
+    arrive_and_wait(P, e, true);
+    *(volatile unsigned long long*)&P.epoch[0] = e;
+  }
+}
+
+int launch_peer_barrier(const PeerView& P, cudaStream_t st) {
+  k_peer_barrier<<<1, 32, 0, st>>>(P);
+  return 1;
+}
+
 int launch_peer_reduce(const DevView& V, const PeerView& P, const AccLayout& L, double* acc_red, int dense, cudaStream_t st) {
   const int64_t blocks = (L.sum_end + 255) / 256;
   const int grid = (int)(blocks < 296 ? (blocks > 0 ? blocks : 1) : 296);

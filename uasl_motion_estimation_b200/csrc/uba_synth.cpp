@@ -147,6 +147,15 @@ int64_t uba_synth_generate(const uba_synth_spec* spec, const uba_calib* calib, i
   return no;
 }
 
+// Defaults of the pose-only mode (uba_vo.cu); host-only so that libuba_host.so carries them.
+void uba_vo_params_default(uba_vo_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  // StereoVisualOdometry::parameters() and VisualOdometry::parameters() (vo/StereoVisualOdometry.h:34, vo/VisualOdometry.h:32)
+  p->fu1 = p->fv1 = p->fu2 = p->fv2 = 1.0; p->baseline = 1.0;
+  p->method = 0; p->max_iter = 100; p->e1 = 1e-3; p->e2 = 1e-12; p->e3 = 1e-12; p->e4 = 1e-15; p->inlier_threshold = 2.0;
+}
+
 // ---- point sharding of one large window ---------------------------------------
 // Points go to ranks by KEYFRAME RANGE: order them by (first keyframe of the track, caller index) and cut that order
 // into n_ranks pieces with equal observation counts.  A rank's tracks then start inside one contiguous camera range,

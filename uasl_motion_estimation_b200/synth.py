@@ -111,3 +111,32 @@ def concat_windows(wins) -> dict:
                 feats=np.concatenate([w.feats for w in wins]), cam_idx=np.concatenate([w.cam_idx for w in wins]),
                 pt_idx=np.concatenate([w.pt_idx for w in wins]), cam_id=np.concatenate([w.cam_id for w in wins]),
                 calib=wins[0].calib)
+
+
+def vo_params(calib, lib=None, **overrides) -> "capi.VoParams":
+    """StereoVisualOdometry::parameters for the synthetic rig (defaults of the reference, vo/VisualOdometry.h:32)."""
+    lib = lib or capi.host_lib()
+    p = capi.VoParams()
+    lib.uba_vo_params_default(C.byref(p))
+    p.fu1, p.fv1, p.cu1, p.cv1 = calib.fx0, calib.fy0, calib.cx0, calib.cy0
+    p.fu2, p.fv2, p.cu2, p.cv2 = calib.fx1, calib.fy1, calib.cx1, calib.cy1
+    p.baseline = calib.baseline
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+def vo_quads(n_matches: int, outlier_fraction: float = 0.0, seed: int = BASE_SEED + 7000, lib=None):
+    """Quad matches of two consecutive stereo frames (StereoOdoMatchesf f1..f4): the two keyframes of a synthetic 2-frame
+    window, points seen in both; a fraction of the CURRENT-frame features is replaced by uniform-random pixels.
+    Returns (quads [n][8] float32, outlier mask)."""
+    win = generate(2, n_matches, 2, 2, full_tracks=1, seed=seed, lib=lib)
+    both = np.flatnonzero(np.bincount(win.pt_idx, minlength=win.n_pts) == 2)     # tracks that stayed inside both images
+    first = np.searchsorted(win.pt_idx, both)                                   # observations are point-major, frame-ascending
+    quads = np.ascontiguousarray(np.concatenate([win.feats[first], win.feats[first + 1]], axis=1), dtype=np.float32)
+    rng = np.random.default_rng(seed)
+    out = rng.random(len(quads)) < outlier_fraction
+    k = int(out.sum())
+    quads[out, 4] = rng.uniform(20, 1221, k); quads[out, 5] = rng.uniform(20, 356, k)
+    quads[out, 6] = quads[out, 4] - rng.uniform(2, 90, k).astype(np.float32); quads[out, 7] = quads[out, 5]
+    return quads, out
