@@ -94,6 +94,8 @@ typedef struct uba_config {
                                       atomics), 2 tiled with DFMA Schur products (first generation) */
   int32_t compute_covariance;      /* CalibrationParameters::compute_cov (:40); default 0 */
   int32_t solver;                  /* 0 auto (banded LDL^T for large block-banded systems), 1 dense Cholesky only */
+  int32_t sliding_window;          /* 1: keep the window's observation rows resident so that uba_window_advance can slide it
+                                      (per-frame BA, BASELINE config c2); default 0 */
 } uba_config;
 
 /* Per-window result of uba_optimise (ceres::Solver::Summary, as far as the reference uses it). */
@@ -170,6 +172,24 @@ int uba_set_batch(uba_handle* h, int M, int n_windows,
                   const double* cams6, const double* pts3, const double* feats,
                   const int32_t* cam_idx, const int32_t* pt_idx, const int32_t* cam_id,
                   const uba_calib* calib);
+
+/* Sliding window (per-frame BA; replaces re-running initialiseObservations, BundleAdjuster.h:351-376, over the whole track
+ * container, core/feature_types.h:121-191, for every frame).  Needs uba_config.sliding_window = 1, a single window whose
+ * tracks are runs of consecutive keyframes (what WBA_Point::addMatch asserts) given point-major / frame-ascending, and one
+ * camID per track; otherwise UBA_ERR_UNSUPPORTED and the caller re-submits with uba_set_problem.
+ *   - the n_drop oldest keyframes leave: their observations are removed, camera indices shift down by n_drop;
+ *   - tracks left without observations are ERASED and the surviving points renumbered densely in order (what a caller does
+ *     with its std::vector<WBA_Point>); pt_id_map [old n_pts] (may be NULL) receives the new id of every old point or -1;
+ *   - n_new_cams keyframes are appended (new_cams6), n_new_pts new points are appended after the survivors (new_pts3,
+ *     new_pt_cam_id or NULL), and n_new_obs observations are added: cam_idx in the NEW window numbering and >= the first
+ *     new keyframe, pt_idx in the NEW point numbering, each extending its track by consecutive keyframes;
+ *   - cams6_all / pts3_all: initial iterate of the new window for ALL its cameras / points, or NULL to keep what the last
+ *     uba_optimise left on the device (plus new_cams6 / new_pts3 for the newcomers).
+ * Everything happens on the device apart from O(n_pts) index work; the handle is then in the same state as after
+ * uba_set_problem of the equivalent window (uba_optimise, uba_get_*, uba_get_tables work as usual). */
+int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* new_cams6, int n_new_pts, const double* new_pts3,
+                       const int32_t* new_pt_cam_id, int n_new_obs, const double* feats, const int32_t* cam_idx, const int32_t* pt_idx,
+                       const double* cams6_all, const double* pts3_all, int32_t* pt_id_map);
 
 /* ---- the hot path ----------------------------------------------------------------- */
 /* One linearisation at the current iterate: residuals, analytic Jacobians, robust

@@ -26,7 +26,8 @@ def emu_lib():
     from uasl_motion_estimation_b200 import capi
     d = ROOT / "tests" / "emu"
     subprocess.run(["make", "-s", "-C", str(d)], check=True, capture_output=True)
-    return capi.load(d / "libuba_emu.so")
+    # the pose-only VO kernels are shared-memory kernels: not part of the emulation build
+    return capi.load(d / "libuba_emu.so", allow_missing=tuple(n for n in capi.EXPORTED_SYMBOLS if n.startswith("uba_vo_")))
 
 
 @pytest.fixture(scope="session")

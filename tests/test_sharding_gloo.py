@@ -24,7 +24,7 @@ def _worker(rank, world, port, emu_path, out):
     import oracle_binding as ob
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lib = capi.load(emu_path)  # only for the generator + defaults (host code)
+    lib = capi.load_host()  # generator, defaults and shard tables: the host-only library
     win = synth.config_window("c4", scale=0.003, lib=lib)
     cfg = capi.default_config(lib)
     full = ob.linearize(win, cfg, 2, 1e4)

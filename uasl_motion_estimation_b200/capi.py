@@ -47,7 +47,8 @@ class Config(C.Structure):
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
                 ("max_consecutive_invalid_steps", C.c_int32), ("max_solver_time_s", C.c_double),
                 ("fixed_iterations", C.c_int32), ("jacobi_scaling", C.c_int32), ("use_bounds", C.c_int32),
-                ("device", C.c_int32), ("linearizer", C.c_int32), ("compute_covariance", C.c_int32), ("solver", C.c_int32)]
+                ("device", C.c_int32), ("linearizer", C.c_int32), ("compute_covariance", C.c_int32), ("solver", C.c_int32),
+                ("sliding_window", C.c_int32)]
 
 
 class Summary(C.Structure):
@@ -100,6 +101,8 @@ _SIGNATURES = [
                                    c_int32_p, c_int32_p, c_int32_p, C.POINTER(Calib)]),
     ("uba_set_batch", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int32_p, c_int32_p, c_int64_p, c_double_p, c_double_p, c_double_p,
                                  c_int32_p, c_int32_p, c_int32_p, C.POINTER(Calib)]),
+    ("uba_window_advance", C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, c_double_p, c_int32_p, C.c_int, c_double_p, c_int32_p,
+                                      c_int32_p, c_double_p, c_double_p, c_int32_p]),
     ("uba_linearize", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.POINTER(LinearizationOut)]),
     ("uba_optimise", C.c_int, [C.c_void_p, C.c_int, C.POINTER(Summary)]),
     ("uba_get_cameras", C.c_int, [C.c_void_p, c_double_p]),
@@ -155,14 +158,17 @@ def i64ptr(a):
     return None if a is None else a.ctypes.data_as(c_int64_p)
 
 
-def load(path: str | os.PathLike | None = None) -> C.CDLL:
-    """Load libuba.  Fails loudly when the CUDA library has not been built."""
+def load(path: str | os.PathLike | None = None, allow_missing: tuple = ()) -> C.CDLL:
+    """Load libuba.  Fails loudly when the CUDA library has not been built.  `allow_missing` names entry points a TEST build
+    (tests/emu, which cannot emulate the shared-memory kernels) may lack; the product library must export everything."""
     p = Path(path) if path is not None else DEFAULT_LIB
     if not p.exists():
         raise ImportError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           f"(nvcc, sm_100a).  uasl_motion_estimation_b200 has no CPU implementation.")
     lib = C.CDLL(str(p))
     for name, res, args in _SIGNATURES:
+        if name in allow_missing and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
@@ -293,6 +299,24 @@ class Handle:
         self.M = M
         self.n_windows, self.n_cams, self.n_pts, self.n_obs = len(wc) - 1, cams6.shape[0], pts3.shape[0], feats.shape[0]
         self.win_cam_off = wc
+
+    def window_advance(self, n_drop, new_cams6, new_pts3, feats, cam_idx, pt_idx, new_pt_cam_id=None, cams6_all=None, pts3_all=None):
+        """uba_window_advance; returns pt_id_map (new id of every old point, -1 for erased tracks)."""
+        M = self.M
+        new_cams6 = as_f64(new_cams6, (-1, 6)); new_pts3 = as_f64(new_pts3, (-1, 3)); feats = as_f64(feats, (-1, M))
+        cam_idx = as_i32(cam_idx); pt_idx = as_i32(pt_idx)
+        cid = None if new_pt_cam_id is None else as_i32(new_pt_cam_id)
+        ca = None if cams6_all is None else as_f64(cams6_all, (-1, 6)); pa = None if pts3_all is None else as_f64(pts3_all, (-1, 3))
+        id_map = np.zeros(max(self.n_pts, 1), np.int32)
+        self._check(self.lib.uba_window_advance(self._h, n_drop, new_cams6.shape[0], dptr(new_cams6), new_pts3.shape[0], dptr(new_pts3),
+                                                i32ptr(cid), feats.shape[0], dptr(feats), i32ptr(cam_idx), i32ptr(pt_idx), dptr(ca), dptr(pa),
+                                                i32ptr(id_map)))
+        id_map = id_map[:self.n_pts]
+        nc = C.c_int(0); npt = C.c_int(0); no = C.c_int64(0); nw = C.c_int(0)
+        self._check(self.lib.uba_get_sizes(self._h, C.byref(nw), C.byref(nc), C.byref(npt), C.byref(no)))
+        self.n_cams, self.n_pts, self.n_obs = nc.value, npt.value, int(no.value)
+        self.win_cam_off = np.array([0, self.n_cams], np.int32)
+        return id_map
 
     # ---- hot path ----
     def optimise(self, fixed_frames: int, check: bool = True):

@@ -181,6 +181,15 @@ int launch_l2_flush(double* buf, size_t n, cudaStream_t st);
 int launch_rank_max(double* w_max, double* w_rmax, double* w_post, const double* stop_req, int nW, int rank, int n_ranks, int gather, cudaStream_t st);
 int launch_ingest_feats(const void* raw, const int32_t* src, double* feat, int64_t NO, int M, int raw_is_f32, cudaStream_t st);
 int launch_dfma_probe(double* out, int iters, cudaStream_t st);
+// sliding window (uba_window_advance)
+int launch_win_shift(const double* old_rows, const int32_t* old_off, const int32_t* dropped, const int32_t* id_map, const int32_t* new_off,
+                     int old_np, int M, double* new_rows, cudaStream_t st);
+int launch_win_append(const double* feats, const int32_t* pt_idx, const int32_t* cam_idx, const int32_t* lo, const int32_t* off, int n, int M,
+                      double* rows, cudaStream_t st);
+int launch_win_pack(const double* rows, const int32_t* off_c, const int32_t* lo_c, const unsigned char* cid_c, const int32_t* pt_order,
+                    const int32_t* off_i, int NP, int64_t NO, int M, double* feat, int32_t* obs_cam, cudaStream_t st);
+int launch_win_points(const double* old_pts, const int32_t* src_slot, const double* fresh, int NP, double* out, cudaStream_t st);
+int launch_win_rows(const void* raw, int raw_is_f32, double* rows, int64_t n, cudaStream_t st);
 
 }  // namespace uba
 #endif

@@ -192,6 +192,18 @@ struct uba_handle {
   std::vector<char> graph_sig;                // host-side launch geometry the captured graph bakes in (see prepare)
   DevView graph_V, graph_Vc;                  // ... and the device views it was captured with (see run_iteration_fast)
   PeerView graph_P;
+  // sliding window (uba_window_advance): per-track table in caller point order + canonical observation rows on the device
+  bool tracks_valid = false;
+  std::vector<int32_t> tr_lo, tr_cnt;         // [NP] first keyframe / length of each track (0: no observation)
+  std::vector<unsigned char> tr_cid;          // [NP] camID != 0
+  DevBuf<double> d_rows[2];                   // canonical rows [NO][M] (caller point order), ping-pong across advances
+  DevBuf<int32_t> d_tr_off[2];                // their CSR offsets [NP+1]
+  int rows_cur = 0;
+  DevBuf<int32_t> d_tr_tmp;                   // per-advance index tables
+  DevBuf<unsigned char> d_tr_cid;
+  DevBuf<double> d_fresh;                     // new rows / new points of an advance
+  bool host_obs_valid = true;                 // obs_order / h_obs_internal / h_obs_cam describe the resident window
+  bool host_iter_pending = false;             // a device -> host copy into h_pts is still in flight on the stream
   // timing
   bool profiling = false;
   uba_timing timing{};
@@ -273,6 +285,7 @@ int allreduce(uba_handle* h, double* buf, size_t count, int op);
 int comm_wait(uba_handle* h);
 int allgather_bytes(uba_handle* h, const void* mine, size_t bytes, std::vector<char>& all);
 int peer_exchange(uba_handle* h);
+int ensure_host_obs_tables(uba_handle* h);
 void peer_close(uba_handle* h);
 
 // UBA_TRACE=1: host-side phase times on stderr
@@ -333,7 +346,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
         s = e - 1;
         continue;
       }
-      // general track: explicit camera list
+      // general track: explicit camera list (never reached after uba_window_advance: its tracks are contiguous)
       cams_p.clear();
       bool ascending = true;
       int nfree = 0;
@@ -1267,6 +1280,55 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   h->ws_h.assign(nW, WinState{});
   h->state = 1;
   h->device_dirty = false;
+  h->host_obs_valid = true;
+  h->tracks_valid = false;
+  if (h->cfg.sliding_window && nW == 1 && !h->comm && obs_permuted == 0) {
+    // every track a run of consecutive keyframes with one camID: the window can then be slid on the device
+    int bad_track = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad_track)
+    for (int j = 0; j < NP; j++) {
+      if (!contig_c[j]) { bad_track++; continue; }
+      if (cam_id) for (int64_t o = h->pt_obs_off_caller[j] + 1; o < h->pt_obs_off_caller[j + 1]; o++) if ((cam_id[o] != 0) != (cam_id[o - 1] != 0)) bad_track++;
+    }
+    if (!bad_track) {
+      h->tr_lo.resize(NP); h->tr_cnt.resize(NP); h->tr_cid.resize(NP);
+      std::vector<int32_t> off32((size_t)NP + 1);
+      for (int j = 0; j < NP; j++) {
+        h->tr_cnt[j] = cnt[j]; h->tr_lo[j] = cnt[j] > 0 ? lo_c[j] : 0;
+        h->tr_cid[j] = (cnt[j] > 0 && cam_id && cam_id[h->pt_obs_off_caller[j]] != 0) ? 1 : 0;
+        off32[j] = (int32_t)h->pt_obs_off_caller[j];
+      }
+      off32[NP] = (int32_t)h->pt_obs_off_caller[NP];
+      h->rows_cur = 0;
+      CU(h, h->d_rows[0].reserve((size_t)NO * M + 1)); CU(h, h->d_tr_off[0].reserve((size_t)NP + 1));
+      CU(h, cudaMemcpyAsync(h->d_tr_off[0].p, off32.data(), sizeof(int32_t) * ((size_t)NP + 1), cudaMemcpyHostToDevice, st));
+      CU(h, cudaStreamSynchronize(st));       // off32 is a local
+      // the raw rows are still in the scratch they were uploaded to (nothing has run on it since k_ingest_feats)
+      h->timing.kernel_launches += launch_win_rows(h->d_Zbuf.p, feat_f32 ? 1 : 0, h->d_rows[0].p, (int64_t)NO * M, st);
+      h->tracks_valid = true;
+    }
+  }
+  return UBA_OK;
+}
+
+// obs_order / h_obs_internal / h_obs_cam are O(n_obs) host tables that only the parity dumps, uba_get_tables and the plan of
+// non-contiguous tracks read; after uba_window_advance they are rebuilt on demand from the track table.
+int ensure_host_obs_tables(uba_handle* h) {
+  if (h->host_obs_valid) return UBA_OK;
+  const int NP = h->NP; const int64_t NO = h->NO;
+  h->obs_order.resize(NO);
+  for (int64_t o = 0; o < NO; o++) h->obs_order[o] = (int32_t)o;
+  CU(h, h->h_obs_internal.reserve((size_t)NO)); CU(h, h->h_obs_cam.reserve((size_t)NO));
+  for (int s = 0; s < NP; s++) {
+    const int j = h->pt_order[s];
+    const int32_t dst = h->pt_obs_off_int[s];
+    const int k = h->pt_obs_off_int[s + 1] - dst;
+    for (int q = 0; q < k; q++) {
+      h->h_obs_internal.p[dst + q] = (int32_t)(h->pt_obs_off_caller[j] + q);
+      h->h_obs_cam.p[dst + q] = (h->tr_lo[j] + q) | (h->tr_cid[j] ? (1 << 30) : 0);
+    }
+  }
+  h->host_obs_valid = true;
   return UBA_OK;
 }
 
@@ -1383,6 +1445,196 @@ int uba_set_problem(uba_handle* h, int M, int n_cams, int n_pts, int n_obs, cons
   return build_problem(h, M, 1, wc, wp, wo, cams6, pts3, feats, cam_idx, pt_idx, cam_id, calib);
 }
 
+int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* new_cams6, int n_new_pts, const double* new_pts3,
+                       const int32_t* new_pt_cam_id, int n_new_obs, const double* feats, const int32_t* cam_idx, const int32_t* pt_idx,
+                       const double* cams6_all, const double* pts3_all, int32_t* pt_id_map) {
+  if (!h) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no window is resident");
+  if (!h->tracks_valid)
+    return fail(h, UBA_ERR_UNSUPPORTED, "uba_window_advance needs uba_config.sliding_window = 1 and a single window of contiguous, "
+                                        "point-major tracks with one camID each: re-submit the window with uba_set_problem");
+  const int NCo = h->NC, NPo = h->NP, M = h->M;
+  const int NCn = NCo - n_drop + n_new_cams;
+  if (n_drop < 0 || n_drop > NCo || n_new_cams < 0 || n_new_pts < 0 || n_new_obs < 0 || NCn <= 0 || (n_new_cams && !new_cams6 && !cams6_all) ||
+      (n_new_pts && !new_pts3 && !pts3_all) || (n_new_obs && (!feats || !cam_idx || !pt_idx)))
+    return fail(h, UBA_ERR_INVALID_ARGUMENT, "uba_window_advance: bad sizes or null arrays");
+  cudaSetDevice(h->device);
+  cudaStream_t st = h->stream;
+  auto tt_ = std::chrono::steady_clock::now();
+  // ---- 1. survivors ------------------------------------------------------------------------------------------------
+  std::vector<int32_t> dropped(NPo), id_map(NPo);
+  int n_alive = 0;
+  for (int j = 0; j < NPo; j++) {
+    const int d = std::min(std::max(n_drop - h->tr_lo[j], 0), h->tr_cnt[j]);
+    dropped[j] = d;
+    id_map[j] = h->tr_cnt[j] - d > 0 ? n_alive++ : -1;
+  }
+  const int NPn = n_alive + n_new_pts;
+  if (NPn <= 0) return fail(h, UBA_ERR_INVALID_ARGUMENT, "uba_window_advance: the new window has no points");
+  std::vector<int32_t> lo_n(NPn, 0), cnt_n(NPn, 0), old_of(NPn, -1);
+  std::vector<unsigned char> cid_n(NPn, 0);
+  for (int j = 0; j < NPo; j++) {
+    const int nj = id_map[j];
+    if (nj < 0) continue;
+    lo_n[nj] = std::max(h->tr_lo[j] - n_drop, 0); cnt_n[nj] = h->tr_cnt[j] - dropped[j]; cid_n[nj] = h->tr_cid[j]; old_of[nj] = j;
+  }
+  for (int k = 0; k < n_new_pts; k++) cid_n[n_alive + k] = (new_pt_cam_id && new_pt_cam_id[k] != 0) ? 1 : 0;
+  // ---- 2. the new observations extend their tracks by consecutive keyframes ------------------------------------------
+  {
+    std::vector<int32_t> add(NPn, 0), minc(NPn, INT_MAX), maxc(NPn, -1);
+    std::vector<int64_t> sumc(NPn, 0);
+    const int first_new = NCo - n_drop;
+    for (int i = 0; i < n_new_obs; i++) {
+      const int j = pt_idx[i], c = cam_idx[i];
+      if (j < 0 || j >= NPn || c < first_new || c >= NCn) return fail(h, UBA_ERR_INVALID_ARGUMENT, "uba_window_advance: observation %d has ptIdx %d / camIdx %d out of range", i, j, c);
+      add[j]++; minc[j] = std::min(minc[j], c); maxc[j] = std::max(maxc[j], c); sumc[j] += c;
+    }
+    for (int j = 0; j < NPn; j++) {
+      if (!add[j]) continue;
+      const int64_t a = add[j];
+      const bool run = maxc[j] - minc[j] + 1 == add[j] && sumc[j] == a * minc[j] + a * (a - 1) / 2;
+      const bool joins = cnt_n[j] == 0 || minc[j] == lo_n[j] + cnt_n[j];
+      if (!run || !joins) return fail(h, UBA_ERR_UNSUPPORTED, "uba_window_advance: the new observations of point %d do not extend its track by consecutive keyframes", j);
+      if (cnt_n[j] == 0) lo_n[j] = minc[j];
+      cnt_n[j] += add[j];
+    }
+  }
+  std::vector<int32_t> off_n((size_t)NPn + 1, 0);
+  for (int j = 0; j < NPn; j++) off_n[j + 1] = off_n[j] + cnt_n[j];
+  const int64_t NOn = off_n[NPn];
+  TT("advance: track tables")
+  // ---- 3. internal point order: stable by (first keyframe, last keyframe), unobserved points last --------------------
+  std::vector<int32_t> order(NPn), off_i((size_t)NPn + 1, 0);
+  {
+    int span = 1;
+    for (int j = 0; j < NPn; j++) span = std::max(span, cnt_n[j]);
+    const int64_t nk = (int64_t)NCn * span + 1;
+    auto key = [&](int j) -> int64_t { return cnt_n[j] == 0 ? nk - 1 : (int64_t)lo_n[j] * span + (cnt_n[j] - 1); };
+    std::vector<int32_t> hist((size_t)nk + 1, 0);
+    for (int j = 0; j < NPn; j++) hist[key(j) + 1]++;
+    for (int64_t k = 0; k < nk; k++) hist[k + 1] += hist[k];
+    for (int j = 0; j < NPn; j++) order[hist[key(j)]++] = j;
+  }
+  std::vector<int32_t> old_slot(NPo, -1), src_slot(NPn);
+  for (int s = 0; s < NPo; s++) old_slot[h->pt_order[s]] = s;
+  h->pt_lo.resize(NPn); h->pt_hi.resize(NPn); h->pt_contig.assign(NPn, 1);
+  for (int s = 0; s < NPn; s++) {
+    const int j = order[s];
+    off_i[s + 1] = off_i[s] + cnt_n[j];
+    h->pt_lo[s] = cnt_n[j] ? lo_n[j] : -1; h->pt_hi[s] = cnt_n[j] ? lo_n[j] + cnt_n[j] - 1 : -1;
+    src_slot[s] = j < n_alive ? old_slot[old_of[j]] : -(j - n_alive) - 1;
+  }
+  TT("advance: order")
+  // ---- 4. device: shift, append, pack ------------------------------------------------------------------------------
+  const int cur = h->rows_cur, nxt = cur ^ 1;
+  CU(h, h->d_rows[nxt].reserve((size_t)NOn * M + 1)); CU(h, h->d_tr_off[nxt].reserve((size_t)NPn + 1));
+  const size_t t_drop = 0, t_map = t_drop + NPo, t_pt = t_map + NPo, t_cam = t_pt + n_new_obs, t_src = t_cam + n_new_obs, t_lo = t_src + NPn,
+               t_order = t_lo + NPn, t_offi = t_order + NPn, t_end = t_offi + NPn + 1;
+  CU(h, h->d_tr_tmp.reserve(t_end)); CU(h, h->d_tr_cid.reserve(NPn));
+  CU(h, h->d_fresh.reserve((size_t)n_new_obs * M + (size_t)n_new_pts * 3 + 1));
+  int32_t* T = h->d_tr_tmp.p;
+  CU(h, cudaMemcpyAsync(T + t_drop, dropped.data(), sizeof(int32_t) * NPo, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(T + t_map, id_map.data(), sizeof(int32_t) * NPo, cudaMemcpyHostToDevice, st));
+  if (n_new_obs) {
+    CU(h, cudaMemcpyAsync(T + t_pt, pt_idx, sizeof(int32_t) * n_new_obs, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(T + t_cam, cam_idx, sizeof(int32_t) * n_new_obs, cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->d_fresh.p, feats, sizeof(double) * (size_t)n_new_obs * M, cudaMemcpyHostToDevice, st));
+  }
+  CU(h, cudaMemcpyAsync(T + t_src, src_slot.data(), sizeof(int32_t) * NPn, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(T + t_lo, lo_n.data(), sizeof(int32_t) * NPn, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(T + t_order, order.data(), sizeof(int32_t) * NPn, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(T + t_offi, off_i.data(), sizeof(int32_t) * ((size_t)NPn + 1), cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_tr_off[nxt].p, off_n.data(), sizeof(int32_t) * ((size_t)NPn + 1), cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_tr_cid.p, cid_n.data(), NPn, cudaMemcpyHostToDevice, st));
+  h->timing.kernel_launches += launch_win_shift(h->d_rows[cur].p, h->d_tr_off[cur].p, T + t_drop, T + t_map, h->d_tr_off[nxt].p, NPo, M, h->d_rows[nxt].p, st);
+  h->timing.kernel_launches += launch_win_append(h->d_fresh.p, T + t_pt, T + t_cam, T + t_lo, h->d_tr_off[nxt].p, n_new_obs, M, h->d_rows[nxt].p, st);
+  // points: what the last solve left (its accepted iterate), re-slotted, plus the newcomers — or the caller's values
+  const int rec_stride = std::max(h->cfg.max_iterations, h->cfg.fixed_iterations) + 2;
+  CU(h, h->h_pts.reserve((size_t)NPn * 3)); CU(h, h->h_cams.reserve((size_t)NCn * 6));
+  const uba::Calib kc = make_calib(h->calib_in, M, h->cfg.use_bounds != 0);
+  auto inside = [&](const double* p) { return p[0] >= kc.lo[0] && p[0] <= kc.hi[0] && p[1] >= kc.lo[1] && p[1] <= kc.hi[1] && p[2] >= kc.lo[2] && p[2] <= kc.hi[2]; };
+  h->win_infeasible.assign(1, 0);
+  if (h->device_dirty) { const int rcu = upload_state(h); if (rcu) return rcu; h->device_dirty = false; h->state = 1; }
+  const int par = h->state == 2 && h->ws_h[0].done != UBA_TERM_FAILURE ? (h->ws_h[0].cur & 1) : 0;
+  std::vector<double> cams_old;
+  if (!cams6_all) {
+    cams_old.resize((size_t)NCo * 6);
+    CU(h, cudaMemcpyAsync(cams_old.data(), h->d_cams.p + (size_t)par * NCo * 6, sizeof(double) * 6 * NCo, cudaMemcpyDeviceToHost, st));
+  }
+  CU(h, h->d_pt_rec.reserve((size_t)std::max(NPn, NPo) * kPtRec));     // scratch for the re-slotted points
+  if (pts3_all) {
+    CU(h, cudaStreamSynchronize(st));          // h_pts may still feed an earlier upload
+    for (int s = 0; s < NPn; s++) {
+      const double* p = pts3_all + (size_t)order[s] * 3;
+      std::memcpy(h->h_pts.p + (size_t)s * 3, p, sizeof(double) * 3);
+      if (h->cfg.use_bounds && cnt_n[order[s]] > 0 && !inside(p)) h->win_infeasible[0] = 1;
+    }
+  } else {
+    if (n_new_pts) {
+      CU(h, cudaMemcpyAsync(h->d_fresh.p + (size_t)n_new_obs * M, new_pts3, sizeof(double) * 3 * n_new_pts, cudaMemcpyHostToDevice, st));
+      if (h->cfg.use_bounds) for (int k = 0; k < n_new_pts; k++) if (cnt_n[n_alive + k] > 0 && !inside(new_pts3 + (size_t)k * 3)) h->win_infeasible[0] = 1;
+    }
+    h->timing.kernel_launches += launch_win_points(h->d_pts.p + (size_t)par * NPo * 3, T + t_src, h->d_fresh.p + (size_t)n_new_obs * M, NPn, h->d_pt_rec.p, st);
+  }
+  CU(h, cudaStreamSynchronize(st));            // the gathers above read buffers that are re-sized below; host vectors are free again
+  TT("advance: shift + append")
+  if (cams6_all) std::memcpy(h->h_cams.p, cams6_all, sizeof(double) * 6 * NCn);
+  else {
+    std::memcpy(h->h_cams.p, cams_old.data() + (size_t)n_drop * 6, sizeof(double) * 6 * (NCo - n_drop));
+    if (n_new_cams) std::memcpy(h->h_cams.p + (size_t)(NCo - n_drop) * 6, new_cams6, sizeof(double) * 6 * n_new_cams);
+  }
+  // ---- 5. commit: the handle now describes the new window ------------------------------------------------------------
+  h->NC = NCn; h->NP = NPn; h->NO = NOn; h->nW = 1;
+  h->w_cam_off = {0, NCn}; h->w_pt_off = {0, NPn}; h->w_obs_off = {0, NOn};
+  h->tr_lo.swap(lo_n); h->tr_cnt.swap(cnt_n); h->tr_cid.swap(cid_n); h->rows_cur = nxt;
+  h->pt_order.swap(order);
+  h->pt_obs_off_int.assign(off_i.begin(), off_i.end());
+  h->pt_obs_off_caller.resize((size_t)NPn + 1);
+  for (int j = 0; j <= NPn; j++) h->pt_obs_off_caller[j] = off_n[j];
+  h->cam_seen.assign(NCn, 0);
+  {
+    std::vector<int32_t> diff((size_t)NCn + 1, 0);
+    for (int j = 0; j < NPn; j++) if (h->tr_cnt[j]) { diff[h->tr_lo[j]]++; diff[h->tr_lo[j] + h->tr_cnt[j]]--; }
+    int run = 0; h->local_cam_lo = NCn; h->local_cam_hi = -1;
+    for (int c = 0; c < NCn; c++) { run += diff[c]; if (run > 0) { h->cam_seen[c] = 1; h->local_cam_lo = std::min(h->local_cam_lo, c); h->local_cam_hi = c; } }
+  }
+  h->cam_win_h.assign(NCn, 0); h->pt_win_h.assign(NPn, 0);
+  h->host_obs_valid = false; h->prepared_fixed = -1; h->cov_h.clear();
+  CU(h, h->d_cams.reserve((size_t)NCn * 12)); CU(h, h->d_camR.reserve((size_t)NCn * kCamStride * 2));
+  CU(h, h->d_cam_s2.reserve((size_t)NCn * 6)); CU(h, h->d_cam_lam.reserve((size_t)NCn * 6)); CU(h, h->d_cam_y.reserve((size_t)NCn * 6));
+  CU(h, h->d_pt_s2.reserve((size_t)NPn * 3));
+  CU(h, h->d_feat.reserve((size_t)NOn * M)); CU(h, h->d_obs_cam.reserve((size_t)NOn)); CU(h, h->d_Zbuf.reserve((size_t)NOn * 18));
+  CU(h, h->d_cam_win.reserve(NCn)); CU(h, h->d_pt_obs_off.reserve((size_t)NPn + 1)); CU(h, h->d_pt_win.reserve(NPn)); CU(h, h->d_pt_order.reserve(NPn));
+  CU(h, h->d_recs.reserve((size_t)rec_stride));
+  if (!pts3_all) {
+    // the re-slotted points sit in the scratch: move them to parity 0 of the (possibly re-sized) point buffer, keep a host copy
+    DevBuf<double> fresh_pts;
+    if ((size_t)NPn * 6 > h->d_pts.cap) { CU(h, fresh_pts.reserve((size_t)NPn * 6)); std::swap(fresh_pts.p, h->d_pts.p); std::swap(fresh_pts.cap, h->d_pts.cap); fresh_pts.release(); }
+    CU(h, cudaMemcpyAsync(h->d_pts.p, h->d_pt_rec.p, sizeof(double) * 3 * NPn, cudaMemcpyDeviceToDevice, st));
+    CU(h, cudaMemcpyAsync(h->h_pts.p, h->d_pts.p, sizeof(double) * 3 * NPn, cudaMemcpyDeviceToHost, st));
+    h->host_iter_pending = true;
+  } else {
+    CU(h, h->d_pts.reserve((size_t)NPn * 6));
+    CU(h, cudaMemcpyAsync(h->d_pts.p, h->h_pts.p, sizeof(double) * 3 * NPn, cudaMemcpyHostToDevice, st));
+  }
+  CU(h, cudaMemcpyAsync(h->d_cams.p, h->h_cams.p, sizeof(double) * 6 * NCn, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_w_cam_off.p, h->w_cam_off.data(), sizeof(int32_t) * 2, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_w_pt_off.p, h->w_pt_off.data(), sizeof(int32_t) * 2, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemsetAsync(h->d_cam_win.p, 0, sizeof(int32_t) * NCn, st)); CU(h, cudaMemsetAsync(h->d_pt_win.p, 0, sizeof(int32_t) * NPn, st));
+  CU(h, cudaMemcpyAsync(h->d_pt_obs_off.p, T + t_offi, sizeof(int32_t) * ((size_t)NPn + 1), cudaMemcpyDeviceToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_pt_order.p, T + t_order, sizeof(int32_t) * NPn, cudaMemcpyDeviceToDevice, st));
+  h->timing.kernel_launches += launch_win_pack(h->d_rows[nxt].p, h->d_tr_off[nxt].p, T + t_lo, h->d_tr_cid.p, T + t_order, T + t_offi, NPn, NOn, M,
+                                               h->d_feat.p, h->d_obs_cam.p, st);
+  CU(h, cudaMemsetAsync(h->d_recs.p, 0, sizeof(IterRec) * (size_t)rec_stride, st));
+  fill_view_static(h);
+  h->V.rec_stride = rec_stride;
+  h->ws_h.assign(1, WinState{});
+  h->state = 1;
+  if (pt_id_map) std::memcpy(pt_id_map, id_map.data(), sizeof(int32_t) * NPo);
+  TT("advance: pack (enqueue)")
+  return UBA_OK;
+}
+
 int uba_get_sizes(const uba_handle* h, int* n_windows, int* n_cams, int* n_pts, int64_t* n_obs) {
   if (!h) return UBA_ERR_INVALID_ARGUMENT;
   if (n_windows) *n_windows = h->nW;
@@ -1395,6 +1647,7 @@ int uba_get_sizes(const uba_handle* h, int* n_windows, int* n_cams, int* n_pts, 
 int uba_get_tables(uba_handle* h, int fixed_frames, int32_t* obs_order, int64_t* pt_obs_off, int32_t* pt_order, int32_t* free_cam) {
   if (!h) return UBA_ERR_INVALID_ARGUMENT;
   if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  { const int rc = ensure_host_obs_tables(h); if (rc) return rc; }
   if (obs_order) std::memcpy(obs_order, h->obs_order.data(), sizeof(int32_t) * h->NO);
   if (pt_obs_off) std::memcpy(pt_obs_off, h->pt_obs_off_caller.data(), sizeof(int64_t) * ((size_t)h->NP + 1));
   if (pt_order) std::memcpy(pt_order, h->pt_order.data(), sizeof(int32_t) * h->NP);
@@ -1411,6 +1664,7 @@ int uba_linearize(uba_handle* h, int fixed_frames, double radius, uba_linearizat
   if (!h || !out) return UBA_ERR_INVALID_ARGUMENT;
   if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
   cudaSetDevice(h->device);
+  { const int rc0 = ensure_host_obs_tables(h); if (rc0) return rc0; }
   const double saved_radius = h->cfg.initial_radius;
   h->cfg.initial_radius = radius;
   // the device copy is about to be used as scratch: results of an earlier uba_optimise are gone, the getters fall back
@@ -1556,6 +1810,7 @@ int uba_get_cameras(uba_handle* h, double* cams6) {
   if (!h || !cams6) return UBA_ERR_INVALID_ARGUMENT;
   if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
   cudaSetDevice(h->device);
+  if (h->host_iter_pending) { CU(h, cudaStreamSynchronize(h->stream)); h->host_iter_pending = false; }
   if (h->state == 1) { std::memcpy(cams6, h->h_cams.p, sizeof(double) * 6 * h->NC); return UBA_OK; }
   std::vector<double> both((size_t)h->NC * 12);
   CU(h, cudaMemcpy(both.data(), h->d_cams.p, sizeof(double) * 12 * h->NC, cudaMemcpyDeviceToHost));
@@ -1572,6 +1827,7 @@ int uba_get_points(uba_handle* h, double* pts3) {
   if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
   cudaSetDevice(h->device);
   const int NP = h->NP;
+  if (h->host_iter_pending) { CU(h, cudaStreamSynchronize(h->stream)); h->host_iter_pending = false; }
   if (h->state == 1) {
     for (int s = 0; s < NP; s++) std::memcpy(pts3 + (size_t)h->pt_order[s] * 3, h->h_pts.p + (size_t)s * 3, sizeof(double) * 3);
     return UBA_OK;

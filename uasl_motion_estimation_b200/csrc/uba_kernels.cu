@@ -2747,6 +2747,60 @@ __global__ void k_ingest_feats(const TRaw* __restrict__ raw, const int32_t* __re
   }
 }
 
+// ---- sliding window (uba_window_advance): the canonical observation rows live on the device, [NO][M] doubles in the
+// caller's point order, tracks contiguous in the keyframe index, so that observation (point j, camera c) sits at row
+// off[j] + (c - lo[j]).  Advancing the window is then three small kernels instead of a host re-ingest + upload.
+// (1) surviving rows of the surviving points move to their new offsets
+__global__ void k_win_shift(const double* __restrict__ old_rows, const int32_t* __restrict__ old_off, const int32_t* __restrict__ dropped,
+                            const int32_t* __restrict__ id_map, const int32_t* __restrict__ new_off, int old_np, int M, double* __restrict__ new_rows) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= old_np) return;
+  const int nj = id_map[j];
+  if (nj < 0) return;
+  const int o0 = old_off[j] + dropped[j], o1 = old_off[j + 1];
+  double* dst = new_rows + (size_t)new_off[nj] * M;
+  const double* src = old_rows + (size_t)o0 * M;
+  for (int e = 0; e < (o1 - o0) * M; e++) dst[e] = src[e];
+}
+// (2) the new keyframes' observations drop into place
+__global__ void k_win_append(const double* __restrict__ feats, const int32_t* __restrict__ pt_idx, const int32_t* __restrict__ cam_idx,
+                             const int32_t* __restrict__ lo, const int32_t* __restrict__ off, int n, int M, double* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = pt_idx[i];
+  double* dst = rows + ((size_t)off[j] + (cam_idx[i] - lo[j])) * M;
+  for (int m = 0; m < M; m++) dst[m] = feats[(size_t)i * M + m];
+}
+// (3) canonical rows -> the lineariser's point-sorted SoA planes + camera words; thread per internal point slot
+__global__ void k_win_pack(const double* __restrict__ rows, const int32_t* __restrict__ off_c, const int32_t* __restrict__ lo_c,
+                           const unsigned char* __restrict__ cid_c, const int32_t* __restrict__ pt_order, const int32_t* __restrict__ off_i,
+                           int NP, int64_t NO, int M, double* __restrict__ feat, int32_t* __restrict__ obs_cam) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= NP) return;
+  const int j = pt_order[s];
+  const int o0 = off_i[s], k = off_i[s + 1] - o0;
+  const double* src = rows + (size_t)off_c[j] * M;
+  const int bit = cid_c[j] ? (1 << 30) : 0;
+  for (int q = 0; q < k; q++) {
+    for (int m = 0; m < M; m++) feat[(size_t)m * NO + o0 + q] = src[(size_t)q * M + m];
+    obs_cam[o0 + q] = (lo_c[j] + q) | bit;
+  }
+}
+// refined points of the previous window -> their slots in the new internal order; new points from the upload
+__global__ void k_win_points(const double* __restrict__ old_pts, const int32_t* __restrict__ src_slot, const double* __restrict__ fresh,
+                             int NP, double* __restrict__ out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= NP) return;
+  const int src = src_slot[s];
+  const double* p = src >= 0 ? old_pts + (size_t)src * 3 : fresh + (size_t)(-src - 1) * 3;
+  out[(size_t)s * 3] = p[0]; out[(size_t)s * 3 + 1] = p[1]; out[(size_t)s * 3 + 2] = p[2];
+}
+// raw rows as uploaded by uba_set_problem (float32 or double, caller order) -> canonical double rows
+template <typename TRaw>
+__global__ void k_win_rows(const TRaw* __restrict__ raw, double* __restrict__ rows, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) rows[i] = (double)raw[i];
+}
+
 // point-sharded runs: per-window gradient max-norm through a SUM allreduce — scatter (gather = 0): this rank's max into its
 // slot; gather (gather = 1, after the allreduce): max over the ranks' slots
 __global__ void k_rank_max(double* w_max, double* w_rmax, double* w_post, const double* stop_req, int nW, int rank, int n_ranks, int gather) {
@@ -3018,6 +3072,38 @@ int launch_ingest_feats(const void* raw, const int32_t* src, double* feat, int64
   const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
   if (raw_is_f32) UBA_LAUNCH(k_ingest_feats<float>, grid, 256, 0, st, (const float*)raw, src, feat, NO, M);
   else UBA_LAUNCH(k_ingest_feats<double>, grid, 256, 0, st, (const double*)raw, src, feat, NO, M);
+  return 1;
+}
+
+int launch_win_shift(const double* old_rows, const int32_t* old_off, const int32_t* dropped, const int32_t* id_map, const int32_t* new_off,
+                     int old_np, int M, double* new_rows, cudaStream_t st) {
+  if (old_np == 0) return 0;
+  UBA_LAUNCH(k_win_shift, (old_np + 127) / 128, 128, 0, st, old_rows, old_off, dropped, id_map, new_off, old_np, M, new_rows);
+  return 1;
+}
+int launch_win_append(const double* feats, const int32_t* pt_idx, const int32_t* cam_idx, const int32_t* lo, const int32_t* off, int n, int M,
+                      double* rows, cudaStream_t st) {
+  if (n == 0) return 0;
+  UBA_LAUNCH(k_win_append, (n + 127) / 128, 128, 0, st, feats, pt_idx, cam_idx, lo, off, n, M, rows);
+  return 1;
+}
+int launch_win_pack(const double* rows, const int32_t* off_c, const int32_t* lo_c, const unsigned char* cid_c, const int32_t* pt_order,
+                    const int32_t* off_i, int NP, int64_t NO, int M, double* feat, int32_t* obs_cam, cudaStream_t st) {
+  if (NP == 0) return 0;
+  UBA_LAUNCH(k_win_pack, (NP + 127) / 128, 128, 0, st, rows, off_c, lo_c, cid_c, pt_order, off_i, NP, NO, M, feat, obs_cam);
+  return 1;
+}
+int launch_win_points(const double* old_pts, const int32_t* src_slot, const double* fresh, int NP, double* out, cudaStream_t st) {
+  if (NP == 0) return 0;
+  UBA_LAUNCH(k_win_points, (NP + 127) / 128, 128, 0, st, old_pts, src_slot, fresh, NP, out);
+  return 1;
+}
+int launch_win_rows(const void* raw, int raw_is_f32, double* rows, int64_t n, cudaStream_t st) {
+  if (n == 0) return 0;
+  const int64_t blocks = (n + 255) / 256;
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  if (raw_is_f32) UBA_LAUNCH(k_win_rows<float>, grid, 256, 0, st, (const float*)raw, rows, n);
+  else UBA_LAUNCH(k_win_rows<double>, grid, 256, 0, st, (const double*)raw, rows, n);
   return 1;
 }
 

@@ -249,6 +249,7 @@ void uba_config_default(uba_config* c) {
   c->linearizer = 0;
   c->compute_covariance = 0;              // CalibrationParameters::compute_cov defaults to false (:42-43)
   c->solver = 0;
+  c->sliding_window = 0;
 }
 
 // log_map_Quat (rotation_utils.h:199-204) with acos clamped to [-1, 1].

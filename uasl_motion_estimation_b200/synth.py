@@ -140,3 +140,68 @@ def vo_quads(n_matches: int, outlier_fraction: float = 0.0, seed: int = BASE_SEE
     quads[out, 4] = rng.uniform(20, 1221, k); quads[out, 5] = rng.uniform(20, 356, k)
     quads[out, 6] = quads[out, 4] - rng.uniform(2, 90, k).astype(np.float32); quads[out, 7] = quads[out, 5]
     return quads, out
+
+
+class SlidingSequence:
+    """A long synthetic stereo sequence walked by a sliding window — BASELINE config c2: 200 keyframes,
+    a 20-keyframe window advanced one keyframe per BA call (181 calls).  It plays the caller's part around
+    ``uba_window_advance`` the way an application drives the reference (``BundleAdjuster.h:351-376`` over a container of
+    ``WBA_Point`` tracks, ``core/feature_types.h:121-191``): a track enters the container at its first keyframe, gains one
+    observation per keyframe while it is matched, and is erased once its last observation has left the window.
+
+    Tracks are cut at their first gap (a tracker loses the feature there), so every track is a run of consecutive
+    keyframes, which is what ``WBA_Point::addMatch`` asserts."""
+
+    def __init__(self, n_frames=200, window=20, n_pts=200_000, track_min=2, track_max=18, seed=BASE_SEED + 2000, lib=None):
+        self.W = window
+        self.n_frames = n_frames
+        seq = generate(n_frames, n_pts, track_min, track_max, 0, 0.0, seed=seed, lib=lib)
+        # keep the leading run of consecutive keyframes of every track
+        first = np.r_[True, seq.pt_idx[1:] != seq.pt_idx[:-1]]
+        brk = ~first & (seq.cam_idx != np.r_[0, seq.cam_idx[:-1]] + 1)
+        seg = np.cumsum(first) - 1
+        nbrk = np.cumsum(brk)
+        keep = nbrk == nbrk[np.flatnonzero(first)][seg]      # no gap yet inside this track
+        self.seq = seq
+        self.cam = seq.cam_idx[keep].astype(np.int64); self.pt = seq.pt_idx[keep].astype(np.int64)
+        self.feats = np.ascontiguousarray(seq.feats[keep])
+        self.lo = np.full(seq.n_pts, np.iinfo(np.int64).max); self.hi = np.full(seq.n_pts, -1)
+        np.minimum.at(self.lo, self.pt, self.cam); np.maximum.at(self.hi, self.pt, self.cam)
+        self.off = np.zeros(seq.n_pts + 1, np.int64); np.cumsum(np.bincount(self.pt, minlength=seq.n_pts), out=self.off[1:])
+        self.calib = seq.calib
+
+    @property
+    def n_calls(self):
+        return self.n_frames - self.W + 1
+
+    def initial_ids(self):
+        """Tracks alive in the first window, in container order."""
+        return np.flatnonzero((self.hi >= 0) & (self.lo < self.W))
+
+    def window(self, first, ids, cams=None, pts=None) -> Window:
+        """The window [first, first + W) over the tracks `ids` (container order) as the arrays initialiseObservations
+        would produce from them; initial values from `cams` / `pts` or the generator's perturbed ones."""
+        f1 = first + self.W
+        a = np.maximum(self.lo[ids], first); b = np.minimum(self.hi[ids], f1 - 1)
+        cnt = np.maximum(b - a + 1, 0)
+        n = int(cnt.sum())
+        pt_new = np.repeat(np.arange(len(ids)), cnt)
+        start = np.zeros(len(ids) + 1, np.int64); np.cumsum(cnt, out=start[1:])
+        q = np.arange(n) - start[pt_new]
+        src = self.off[ids][pt_new] + (a - self.lo[ids])[pt_new] + q
+        return Window(4, self.seq.cams_gt[first:f1], self.seq.cams_init[first:f1] if cams is None else cams,
+                      self.seq.pts_gt[ids], self.seq.pts_init[ids] if pts is None else pts, np.ascontiguousarray(self.feats[src]),
+                      (self.cam[src] - first).astype(np.int32), pt_new.astype(np.int32), np.zeros(n, np.int32), 2, self.calib)
+
+    def advance(self, first, ids):
+        """One step of the window, [first, first + W) -> [first + 1, first + 1 + W): the arguments of uba_window_advance and
+        the container afterwards.  Returns (kwargs, ids_new)."""
+        newf = first + self.W                      # the keyframe that enters
+        alive = self.hi[ids] >= first + 1
+        born = np.flatnonzero(self.lo == newf)
+        ids_new = np.concatenate([ids[alive], born])
+        seen = np.flatnonzero((self.lo[ids_new] <= newf) & (self.hi[ids_new] >= newf))   # tracks observed in the new keyframe
+        src = self.off[ids_new[seen]] + (newf - self.lo[ids_new[seen]])
+        kw = dict(n_drop=1, new_cams6=self.seq.cams_init[newf:newf + 1], new_pts3=self.seq.pts_init[born],
+                  feats=np.ascontiguousarray(self.feats[src]), cam_idx=np.full(len(seen), self.W - 1, np.int32), pt_idx=seen.astype(np.int32))
+        return kw, ids_new
