@@ -615,16 +615,17 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr int kT2MaxPc = 64;          // points per chunk are capped so that K = 3 Pc <= 192
 constexpr int kT2StageD = 8;          // per lane and buffer: point (3) + features (<= 4) doubles, 1 spare
 constexpr int kT2StageI = 4;          // ... and ints: next chunk's mask, its first-observation offset, obs_cam word, spare
+constexpr int kCamSm = 13;            // per-slot camera record in shared memory: R[9] t[3] small-angle flag; odd stride = slots in distinct banks
 // Zm capacity in doubles: the worst case over (T, nl) of 8 T * t2_ldz(Pc) is 96 x 84 (T = 12, Pc = 23) for
 // 256-thread CTAs and 32 x 196 (T = 4, Pc = 64) for 128-thread CTAs
 #ifndef UBA_T2_ZM128
 #define UBA_T2_ZM128 6400
 #endif
 __host__ __device__ constexpr int t2_zm_doubles(int nt) { return nt == 256 ? 8192 : UBA_T2_ZM128; }
-// doubles of the region {Zm | flush scratch} (the scratch aliases Zm): [points x slots][33] <= nt*33, or the
-// (8T) x (8T+1) K-group reduction tile (T <= 12 for 256-thread CTAs, <= 8 for 128-thread ones)
+// doubles of the region {Zm | flush scratch} (the scratch aliases Zm): [points x slots][33] + [slots][33] <= (nt + 21) * 33, or the
+// (8T) x (8T+1) reduction / transform tile of the Schur blocks (T <= 16 for 256-thread CTAs, <= 8 for 128-thread ones)
 __host__ __device__ constexpr int t2_main_doubles(int nt) {
-  return nt == 256 ? (96 * 97 > 8192 ? 96 * 97 : 8192) : (UBA_T2_ZM128 > 128 * 33 ? (UBA_T2_ZM128 > 64 * 65 ? UBA_T2_ZM128 : 64 * 65) : 128 * 33);
+  return nt == 256 ? 128 * 129 : (UBA_T2_ZM128 > 128 * 33 + 21 * 33 ? (UBA_T2_ZM128 > 64 * 65 ? UBA_T2_ZM128 : 64 * 65) : 128 * 33 + 21 * 33);
 }
 // ... followed by the two prefetch staging buffers
 __host__ __device__ constexpr int t2_stage_doubles(int nt) { return 2 * nt * (kT2StageD + kT2StageI / 2); }
@@ -635,9 +636,11 @@ __host__ __device__ inline int t2_ldz(int pc) {
   return k;
 }
 
+// index of entry (r, c), r <= c, in the packed upper triangle of a 6x6 block
+__host__ __device__ constexpr int ut6(int r, int c) { return r * 6 - r * (r - 1) / 2 + (c - r); }
+
 template <int M, int NT, int T, int TG>
 __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& part, double* sm) {
-  constexpr int NR = (M == 4) ? 3 : 2;
   constexpr int W = NT / 32;
   constexpr int KG = W / TG;                       // K-groups
   constexpr int NTILES = T * (T + 1) / 2;
@@ -649,6 +652,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   const int nl = part.n_local, nfx = part.n_fixed, nlf = nl - nfx;
   const int cur = st->cur;
   const double radius = st->radius;
+  const double inv_radius = radius > 0.0 ? 1.0 / radius : 0.0;
   const bool scale_ready = st->scale_ready != 0;
   const int cbase = V.w_cam_off[w];
   // phase-1 role, warp aligned: a point's nl slot lanes sit in ONE warp, so its 3x3 block is reduced with
@@ -663,16 +667,16 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   const int ldz = t2_ldz(Pc);
   const int ksteps = (3 * Pc + 3) / 4;
   // shared memory carve-up (doubles)
-  double* camS = sm;                                 // [kTileMaxLocal][kCamStride]
-  double* Zm = camS + kTileMaxLocal * kCamStride;    // [8 T][ldz]
+  double* camS = sm;                                 // [kTileMaxLocal][kCamSm]
+  double* Zm = camS + kTileMaxLocal * kCamSm;        // [8 T][ldz]
   double* scratch = Zm;                              // flush scratch aliases Zm
   __shared__ int s_free[kTileMaxLocal];
   __shared__ int s_gc[kTileMaxLocal];
 
-  for (int i = t; i < nl * kCamStride; i += NT) {
-    const int sl2 = i / kCamStride, k = i % kCamStride;
+  for (int i = t; i < nl * kCamSm; i += NT) {
+    const int sl2 = i / kCamSm, k = i - sl2 * kCamSm;
     const int gc = cbase + V.tile_cams[part.cam_list_off + sl2];
-    camS[i] = V.camR[cur][(size_t)gc * kCamStride + k];
+    camS[i] = V.camR[cur][(size_t)gc * kCamStride + (k < 12 ? k : 21)];   // R (9), t (3), small-angle flag
     if (k == 0) { s_gc[sl2] = gc; s_free[sl2] = V.free_cam[gc]; }
   }
   for (int i = t; i < 8 * T * ldz; i += NT) Zm[i] = 0.0;   // padding rows / columns stay zero for the whole part
@@ -689,21 +693,25 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
   double acc[TPW][2];
 #pragma unroll
   for (int i = 0; i < TPW; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
-  double Bq[21], vq[6], zq[6];
+  // Camera-side sums of my slot in the frame where the angle-axis part has NOT yet been multiplied by G = J_l(r):
+  //   F = d [I | -[u]x G]  =>  B = D B' D^T, v = D v', Z h = D (Z' h'),  D = diag(I, G^T)   (applied once per part, at the flush)
+  //   B'tt = sum Q,  B'tr = -sum Q [u]x =: -sum U,  B'rr = sum [u]x^T U     (Q = d^T d, Q01 = 0)
+  double Bt[5], Bu[9], Br[6], vq[6], zq[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) { vq[i] = 0.0; zq[i] = 0.0; }
+  for (int i = 0; i < 5; i++) Bt[i] = 0.0;
 #pragma unroll
-  for (int i = 0; i < 21; i++) Bq[i] = 0.0;
+  for (int i = 0; i < 9; i++) Bu[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { Br[i] = 0.0; vq[i] = 0.0; zq[i] = 0.0; }
   double cost = 0.0, gmax = 0.0, fail = 0.0;
   __syncthreads();
 
   // Prefetch pipeline over chunks, two implementations (chosen per tile variant by measurement on B200):
   //  * kAsyncPipe (the T = 4 variant: c4, c5): through shared memory with cp.async, no registers held across a chunk.  While
   //    chunk k is processed, the point and features of this lane's observation in chunk k+1 and the mask / first-observation
-  //    offset of its point in chunk k+2 are in flight into the lane's staging slot (two buffers, alternating).  The register
-  //    version made ptxas spill the prefetched values right after their loads, which stalls on cold data (-5 % on c4).
+  //    offset of its point in chunk k+2 are in flight into the lane's staging slot (two buffers, alternating).
   //  * otherwise (wider variants: c1, c2, c3) in registers: stage B holds the mask / offset of the chunk after next, stage A
-  //    the mask, point and features of the next chunk (the shared-memory version costs 8 % there).
+  //    the mask, point and features of the next chunk.
   constexpr bool kAsyncPipe = (T == 4);
   double* stageD = Zm + t2_main_doubles(NT);                       // [2][NT][kT2StageD]
   int* stageI = reinterpret_cast<int*>(stageD + 2 * NT * kT2StageD);   // [2][NT][kT2StageI]
@@ -806,40 +814,52 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
         }
       }
     }
-    double Wm[18];
+    double Pm[9], u[3] = {0, 0, 0};             // P = Q R: the translation rows of W' = F'^T E; W'rot = [u]x P
     double cg[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 9; i++) Pm[i] = 0.0;
     if (seen && (UBA_TILE_PHASES & 1)) {
-      double rraw[M], wgt, F[NR][6], E[NR][3], rh[NR];
-      const double rho0 = obs_linearize<M>(camS + sl * kCamStride, X, f, cid, V.calib, V.loss, rraw, wgt, F, E, rh);
+      const double* R = camS + sl * kCamSm;
+      double Q[5], m3[3];
+      const double rho0 = obs_linearize_q<M>(R, R + 9, R[12] != 0.0, X, f, cid, V.calib, V.loss, Q, m3, u);
       cost += 0.5 * rho0;
+      const double Q00 = Q[0], Q02 = Q[1], Q11 = Q[2], Q12 = Q[3], Q22 = Q[4];
+      // P = Q R (Q01 = 0)
 #pragma unroll
-      for (int a = 0; a < NR; a++) {
-        cg[0] = fma(E[a][0], E[a][0], cg[0]); cg[1] = fma(E[a][0], E[a][1], cg[1]); cg[2] = fma(E[a][0], E[a][2], cg[2]);
-        cg[3] = fma(E[a][1], E[a][1], cg[3]); cg[4] = fma(E[a][1], E[a][2], cg[4]); cg[5] = fma(E[a][2], E[a][2], cg[5]);
-        cg[6] = fma(E[a][0], rh[a], cg[6]); cg[7] = fma(E[a][1], rh[a], cg[7]); cg[8] = fma(E[a][2], rh[a], cg[8]);
+      for (int c = 0; c < 3; c++) {
+        Pm[c] = fma(Q00, R[c], Q02 * R[6 + c]);
+        Pm[3 + c] = fma(Q11, R[3 + c], Q12 * R[6 + c]);
+        Pm[6 + c] = fma(Q02, R[c], fma(Q12, R[3 + c], Q22 * R[6 + c]));
       }
+      // E^T E = R^T P (upper), E^T r = R^T m
+      cg[0] = fma(R[0], Pm[0], fma(R[3], Pm[3], R[6] * Pm[6]));
+      cg[1] = fma(R[0], Pm[1], fma(R[3], Pm[4], R[6] * Pm[7]));
+      cg[2] = fma(R[0], Pm[2], fma(R[3], Pm[5], R[6] * Pm[8]));
+      cg[3] = fma(R[1], Pm[1], fma(R[4], Pm[4], R[7] * Pm[7]));
+      cg[4] = fma(R[1], Pm[2], fma(R[4], Pm[5], R[7] * Pm[8]));
+      cg[5] = fma(R[2], Pm[2], fma(R[5], Pm[5], R[8] * Pm[8]));
+      cg[6] = fma(R[0], m3[0], fma(R[3], m3[1], R[6] * m3[2]));
+      cg[7] = fma(R[1], m3[0], fma(R[4], m3[1], R[7] * m3[2]));
+      cg[8] = fma(R[2], m3[0], fma(R[5], m3[1], R[8] * m3[2]));
       if (my_free) {
-        int q = 0;
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-#pragma unroll
-          for (int a = 0; a < NR; a++) vq[r] = fma(F[a][r], rh[a], vq[r]);
-#pragma unroll
-          for (int c = r; c < 6; c++) {
-#pragma unroll
-            for (int a = 0; a < NR; a++) Bq[q] = fma(F[a][r], F[a][c], Bq[q]);
-            q++;
-          }
-        }
-#pragma unroll
-        for (int r = 0; r < 6; r++)
-#pragma unroll
-          for (int c = 0; c < 3; c++) {
-            double sacc = 0.0;
-#pragma unroll
-            for (int a = 0; a < NR; a++) sacc = fma(F[a][r], E[a][c], sacc);
-            Wm[r * 3 + c] = sacc;
-          }
+        const double ux = u[0], uy = u[1], uz = u[2];
+        Bt[0] += Q00; Bt[1] += Q02; Bt[2] += Q11; Bt[3] += Q12; Bt[4] += Q22;
+        // U = Q [u]x
+        const double U00 = -Q02 * uy, U01 = fma(Q02, ux, -Q00 * uz), U02 = Q00 * uy;
+        const double U10 = fma(Q11, uz, -Q12 * uy), U11 = Q12 * ux, U12 = -Q11 * ux;
+        const double U20 = fma(Q12, uz, -Q22 * uy), U21 = fma(Q22, ux, -Q02 * uz), U22 = fma(Q02, uy, -Q12 * ux);
+        Bu[0] += U00; Bu[1] += U01; Bu[2] += U02; Bu[3] += U10; Bu[4] += U11; Bu[5] += U12; Bu[6] += U20; Bu[7] += U21; Bu[8] += U22;
+        // [u]x^T U, upper triangle
+        Br[0] = fma(uz, U10, fma(-uy, U20, Br[0]));
+        Br[1] = fma(uz, U11, fma(-uy, U21, Br[1]));
+        Br[2] = fma(uz, U12, fma(-uy, U22, Br[2]));
+        Br[3] = fma(ux, U21, fma(-uz, U01, Br[3]));
+        Br[4] = fma(ux, U22, fma(-uz, U02, Br[4]));
+        Br[5] = fma(uy, U02, fma(-ux, U12, Br[5]));
+        vq[0] += m3[0]; vq[1] += m3[1]; vq[2] += m3[2];
+        vq[3] = fma(uy, m3[2], fma(-uz, m3[1], vq[3]));
+        vq[4] = fma(uz, m3[0], fma(-ux, m3[2], vq[4]));
+        vq[5] = fma(ux, m3[1], fma(-uy, m3[0], vq[5]));
       }
     }
     // ---- phase 1b: sum E^T E / E^T r over the point's slot lanes (segmented shuffle tree + broadcast) ----
@@ -863,7 +883,8 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         s2[c] = scale_ready ? V.pt_s2[(size_t)p * 3 + c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
-        lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+        // lm_lambda() without its division: clamp(d s2) / (radius s2)
+        lam[c] = fmin(fmax(Cd[c] * s2[c], V.cfg.min_lm_diagonal), V.cfg.max_lm_diagonal) * (uba_rcp(s2[c]) * inv_radius);
       }
       const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
       const double gg[3] = {cg[6], cg[7], cg[8]};
@@ -894,22 +915,33 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
         if (!scale_ready) { V.pt_s2[(size_t)p * 3] = s2[0]; V.pt_s2[(size_t)p * 3 + 1] = s2[1]; V.pt_s2[(size_t)p * 3 + 2] = s2[2]; }
       }
     }
-    // ---- phase 1d: Z = W L^-T into the chunk matrix Zm (zeros where the point does not see my slot) ----
+    // ---- phase 1d: Z' = W' L^-T into the chunk matrix Zm (zeros where the point does not see my slot) ----
+    //      rows 0..2: P L^-T, rows 3..5: [u]x (P L^-T)
     if (p1_thread && my_free && (UBA_TILE_PHASES & 8)) {
       double* zc = Zm + (size_t)(6 * (sl - nfx)) * ldz + 3 * pl;
-      if (seen) {
+      double zt[3][3];
 #pragma unroll
-        for (int r = 0; r < 6; r++) {
-          const double z0 = Wm[r * 3] * Li[0];
-          const double z1 = fma(Wm[r * 3], Li[1], Wm[r * 3 + 1] * Li[2]);
-          const double z2 = fma(Wm[r * 3], Li[3], fma(Wm[r * 3 + 1], Li[4], Wm[r * 3 + 2] * Li[5]));
-          zc[(size_t)r * ldz] = z0; zc[(size_t)r * ldz + 1] = z1; zc[(size_t)r * ldz + 2] = z2;
-          zq[r] = fma(z0, h[0], fma(z1, h[1], fma(z2, h[2], zq[r])));
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 6; r++) { zc[(size_t)r * ldz] = 0.0; zc[(size_t)r * ldz + 1] = 0.0; zc[(size_t)r * ldz + 2] = 0.0; }
+      for (int r = 0; r < 3; r++) {
+        zt[r][0] = Pm[r * 3] * Li[0];
+        zt[r][1] = fma(Pm[r * 3], Li[1], Pm[r * 3 + 1] * Li[2]);
+        zt[r][2] = fma(Pm[r * 3], Li[3], fma(Pm[r * 3 + 1], Li[4], Pm[r * 3 + 2] * Li[5]));
       }
+      // (not seen: Pm = 0, u = 0 -> zeros, which is what the slot must hold)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        zc[c] = zt[0][c]; zc[(size_t)ldz + c] = zt[1][c]; zc[(size_t)2 * ldz + c] = zt[2][c];
+        zc[(size_t)3 * ldz + c] = fma(u[1], zt[2][c], -u[2] * zt[1][c]);
+        zc[(size_t)4 * ldz + c] = fma(u[2], zt[0][c], -u[0] * zt[2][c]);
+        zc[(size_t)5 * ldz + c] = fma(u[0], zt[1][c], -u[1] * zt[0][c]);
+      }
+      // Z' h: translation rows y = (P L^-T) h, rotation rows u x y
+      const double y0 = fma(zt[0][0], h[0], fma(zt[0][1], h[1], zt[0][2] * h[2]));
+      const double y1 = fma(zt[1][0], h[0], fma(zt[1][1], h[1], zt[1][2] * h[2]));
+      const double y2 = fma(zt[2][0], h[0], fma(zt[2][1], h[1], zt[2][2] * h[2]));
+      zq[0] += y0; zq[1] += y1; zq[2] += y2;
+      zq[3] = fma(u[1], y2, fma(-u[2], y1, zq[3]));
+      zq[4] = fma(u[2], y0, fma(-u[0], y2, zq[4]));
+      zq[5] = fma(u[0], y1, fma(-u[1], y0, zq[5]));
     }
     __syncthreads();
     // ---- phase 2: tensor-core SYRK over the chunk: acc(I,J) += Zm[8I.., k] Zm[8J.., k]^T ------------
@@ -941,82 +973,128 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
     __syncthreads();
   }
 
-  // ---- flush: Schur tiles.  K-groups are summed in shared memory, then one red.add per entry ---------
+  // ---- flush: Schur tiles.  K-groups are summed in shared memory, every 6x6 camera-pair block is brought from the
+  //      primed frame to the real one, S_ab = D_a S'_ab D_b^T, then one red.add per entry ------------------------------
   const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
   double* S = V.Sacc + V.w_red_off[w];
   const int sbeta = V.w_beta[w];
   const int nloc = 6 * nlf;
+  const double* camG = V.camR[cur];             // G of camera gc: camG[gc * kCamStride + 12 .. 20], row-major
   if (nlf > 0) {
     const int frow = lane >> 2, fc = (lane & 3) * 2;
-    if (KG == 1) {
-      // every tile has exactly one owner warp: straight to global memory
+    constexpr int LDS2 = 8 * T + 1;
+    double* Sl = scratch;                         // [8 T][LDS2]
+    for (int r = 0; r < KG; r++) {
+      if (kq == r) {
 #pragma unroll
-      for (int i = 0; i < TPW; i++) {
-        if (tI[i] >= 0) {
-          const int row = 8 * tI[i] + frow;
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            const int colx = 8 * tJ[i] + fc + e;
-            const double v = acc[i][e];
-            if (colx >= row && colx < nloc && v != 0.0) {
-              const int a = row / 6, b = colx / 6;
-              const int fa = s_free[nfx + a], fb = s_free[nfx + b];
-              atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + row - 6 * a, 6 * fb + (colx - 6 * b))], v);
-            }
+        for (int i = 0; i < TPW; i++) {
+          if (tI[i] >= 0) {
+            double* d = Sl + (size_t)(8 * tI[i] + frow) * LDS2 + 8 * tJ[i] + fc;
+            if (r == 0) { d[0] = acc[i][0]; d[1] = acc[i][1]; } else { d[0] += acc[i][0]; d[1] += acc[i][1]; }
           }
         }
       }
-    } else {
-      constexpr int LDS2 = 8 * T + 1;
-      double* Sl = scratch;                         // [8 T][LDS2]
-      for (int r = 0; r < KG; r++) {
-        if (kq == r) {
+      __syncthreads();
+    }
+    // thread (block pair a <= b, row r): row r of D_a X D_b^T; all rows are read before any is written back
+    const int nblk = nlf * (nlf + 1) / 2;
+    constexpr int PER = (NT / 6) * 6;             // a block's six rows never straddle two passes
+    for (int base = 0; base < nblk * 6; base += PER) {
+      const int idx = base + t;
+      const bool mine = t < PER && idx < nblk * 6;
+      double out[6] = {0, 0, 0, 0, 0, 0};
+      int a = 0, b = 0, r = 0;
+      if (mine) {
+        int blk = idx / 6; r = idx - blk * 6;
+        while (blk >= nlf - a) { blk -= nlf - a; a++; }
+        b = a + blk;
+        const double* Ga = camG + (size_t)s_gc[nfx + a] * kCamStride + 12;
+        const double* Gb = camG + (size_t)s_gc[nfx + b] * kCamStride + 12;
+        // X(i, j) of the block; diagonal blocks hold their upper triangle only
+        auto X = [&](int i, int j) -> double {
+          const int ri = 6 * a + i, cj = 6 * b + j;
+          return (a == b && j < i) ? Sl[(size_t)(6 * a + j) * LDS2 + 6 * a + i] : Sl[(size_t)ri * LDS2 + cj];
+        };
+        double row[6];
+        if (r < 3) {
 #pragma unroll
-          for (int i = 0; i < TPW; i++) {
-            if (tI[i] >= 0) {
-              double* d = Sl + (size_t)(8 * tI[i] + frow) * LDS2 + 8 * tJ[i] + fc;
-              if (r == 0) { d[0] = acc[i][0]; d[1] = acc[i][1]; } else { d[0] += acc[i][0]; d[1] += acc[i][1]; }
-            }
-          }
+          for (int j = 0; j < 6; j++) row[j] = X(r, j);
+        } else {
+          const double g0 = Ga[r - 3], g1 = Ga[3 + r - 3], g2 = Ga[6 + r - 3];     // column r-3 of G_a = row of G_a^T
+#pragma unroll
+          for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
         }
-        __syncthreads();
+        out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], Gb[j], fma(row[4], Gb[3 + j], row[5] * Gb[6 + j]));
       }
-      for (int idx = t; idx < nloc * nloc; idx += NT) {
-        const int row = idx / nloc, colx = idx - row * nloc;
-        if (colx < row) continue;
-        const double v = Sl[(size_t)row * LDS2 + colx];
-        if (v == 0.0) continue;
-        const int a = row / 6, b = colx / 6;
-        const int fa = s_free[nfx + a], fb = s_free[nfx + b];
-        atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + row - 6 * a, 6 * fb + (colx - 6 * b))], v);
+      __syncthreads();
+      if (mine) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) if (a != b || j >= r) Sl[(size_t)(6 * a + r) * LDS2 + 6 * b + j] = out[j];
       }
+      __syncthreads();
+    }
+    for (int idx = t; idx < nloc * nloc; idx += NT) {
+      const int row = idx / nloc, colx = idx - row * nloc;
+      if (colx < row) continue;
+      const double v = Sl[(size_t)row * LDS2 + colx];
+      if (v == 0.0) continue;
+      const int a = row / 6, b = colx / 6;
+      const int fa = s_free[nfx + a], fb = s_free[nfx + b];
+      atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + row - 6 * a, 6 * fb + (colx - 6 * b))], v);
     }
     __syncthreads();
   }
-  // ---- flush: camera blocks B, gradients v, rhs terms Z h: summed over a slot's lanes through shared memory
+  // ---- flush: camera blocks B', gradients v', rhs terms Z' h: summed over a slot's lanes through shared memory, brought
+  //      to the real frame (B = D B' D^T, v = D v', Z h = D Z' h) and added to the global sums -------------------------------
   if (p1_thread && my_free) {
     double* o = scratch + (size_t)(pl * nl + sl) * 33;
+    // packed upper triangle of B': (0,0) (0,1)=0 (0,2) | -U row 0 ; (1,1) (1,2) | -U row 1 ; (2,2) | -U row 2 ; B'rr
+    o[ut6(0, 0)] = Bt[0]; o[ut6(0, 1)] = 0.0; o[ut6(0, 2)] = Bt[1]; o[ut6(1, 1)] = Bt[2]; o[ut6(1, 2)] = Bt[3]; o[ut6(2, 2)] = Bt[4];
 #pragma unroll
-    for (int i = 0; i < 21; i++) o[i] = Bq[i];
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) o[ut6(r, 3 + c)] = -Bu[r * 3 + c];
+    o[ut6(3, 3)] = Br[0]; o[ut6(3, 4)] = Br[1]; o[ut6(3, 5)] = Br[2]; o[ut6(4, 4)] = Br[3]; o[ut6(4, 5)] = Br[4]; o[ut6(5, 5)] = Br[5];
 #pragma unroll
     for (int i = 0; i < 6; i++) { o[21 + i] = vq[i]; o[27 + i] = zq[i]; }
   }
   __syncthreads();
+  double* Bs = scratch + (size_t)NT * 33;       // [nlf][33] sums over the chunk's point slots
   for (int idx = t; idx < nlf * 33; idx += NT) {
     const int s2i = nfx + idx / 33, e = idx % 33;
     double sacc = 0.0;
     for (int q = 0; q < Pc; q++) sacc += scratch[(size_t)(q * nl + s2i) * 33 + e];
-    if (sacc == 0.0) continue;
-    const int gc = s_gc[s2i];
-    if (e < 21) {
-      int r = 0, k2 = e;
-      while (k2 >= 6 - r) { k2 -= 6 - r; r++; }
-      atomicAdd(&V.Bacc[(size_t)gc * 36 + r * 6 + r + k2], sacc);
-    } else if (e < 27) {
-      atomicAdd(&V.vacc[(size_t)gc * 6 + (e - 21)], sacc);
+    Bs[idx] = sacc;
+  }
+  __syncthreads();
+  for (int idx = t; idx < nlf * 6; idx += NT) {
+    const int a = idx / 6, r = idx - a * 6;
+    const int gc = s_gc[nfx + a];
+    const double* Bp = Bs + (size_t)a * 33;
+    const double* G = camG + (size_t)gc * kCamStride + 12;
+    auto X = [&](int i, int j) -> double { return i <= j ? Bp[ut6(i, j)] : Bp[ut6(j, i)]; };
+    double row[6], vr, zr;
+    if (r < 3) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) row[j] = X(r, j);
+      vr = Bp[21 + r]; zr = Bp[27 + r];
     } else {
-      atomicAdd(&V.zh[(size_t)gc * 6 + (e - 27)], sacc);
+      const double g0 = G[r - 3], g1 = G[3 + r - 3], g2 = G[6 + r - 3];
+#pragma unroll
+      for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
+      vr = fma(g0, Bp[24], fma(g1, Bp[25], g2 * Bp[26]));
+      zr = fma(g0, Bp[30], fma(g1, Bp[31], g2 * Bp[32]));
     }
+    double out[6];
+    out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
+#pragma unroll
+    for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], G[j], fma(row[4], G[3 + j], row[5] * G[6 + j]));
+#pragma unroll
+    for (int j = 0; j < 6; j++) if (j >= r && out[j] != 0.0) atomicAdd(&V.Bacc[(size_t)gc * 36 + r * 6 + j], out[j]);
+    if (vr != 0.0) atomicAdd(&V.vacc[(size_t)gc * 6 + r], vr);
+    if (zr != 0.0) atomicAdd(&V.zh[(size_t)gc * 6 + r], zr);
   }
   cost = warp_sum(cost); fail = warp_sum(fail); gmax = warp_max(gmax);
   if (warp_leader()) {
@@ -2901,7 +2979,7 @@ size_t lin_tile2_smem_bytes(int nt) {
 #else
   // camS | Zm (rows 8T <= 128, row stride t2_ldz(Pc)); the flush scratch ([points x slots][33] <= nt*33 doubles, or
   // the (8T) x (8T+1) K-group reduction tile, T <= 12 there) aliases Zm
-  return sizeof(double) * ((size_t)kTileMaxLocal * kCamStride + t2_main_doubles(nt) + t2_stage_doubles(nt));
+  return sizeof(double) * ((size_t)kTileMaxLocal * kCamSm + t2_main_doubles(nt) + t2_stage_doubles(nt));
 #endif
 }
 
