@@ -82,7 +82,7 @@ struct DevView {
   double* cam_y;              // [NC][6] camera solution y_c (step = -y), zeros for fixed cameras
   // points (internal order)
   double* pts[2];             // [NP][3]
-  double* pt_s2;              // [NP][3]
+  double* pt_is2;             // [NP][3] 1 / (Jacobi scale^2) of the point columns, captured at the first linearisation
   double* pt_rec;             // [NP][kPtRec]
   const int32_t* pt_obs_off;  // [NP+1]
   const int32_t* pt_win;      // [NP]
@@ -104,7 +104,7 @@ struct DevView {
   // tiled lineariser plan
   const TilePart* parts;      // [n_parts]
   int32_t n_parts;
-  int32_t tile_threads;       // 128 or 256 threads per CTA of k_lin_tile
+  int32_t tile_threads;       // 128 or 256 threads per CTA of k_lin_tile2
   const int32_t* tile_cams;   // local camera lists
   const uint32_t* pt_mask;    // [NP] bit s: the point observes slot s of its part's list (0: not a tile point)
   const int32_t* gen_pts;     // [n_gen] internal point slots handled by the generic lineariser
@@ -164,9 +164,10 @@ int launch_peer_barrier(const PeerView& P, cudaStream_t st);
 int launch_cam_prep(const DevView& V, int parity, cudaStream_t st);
 // only_listed: process V.gen_pts instead of every point
 int launch_lin_generic(const DevView& V, const DebugOut& dbg, bool only_listed, cudaStream_t st);
-int launch_lin_tile(const DevView& V, cudaStream_t st);
-int launch_lin_tile2(const DevView& V, const int* variant_off, cudaStream_t st);
-int lin_tile2_variant(int n_free_local);
+constexpr int kSlotMaxLocal = 10;  // widest part (local cameras) the slot-per-warp lineariser takes: 320-thread CTAs
+constexpr int kLinVariants = 8;    // launch classes of the tiled linearisers: 2 of k_lin_slot, 5 of k_lin_tile2, k_lin_wide
+int launch_lin_tiled(const DevView& V, const int* variant_off, cudaStream_t st);
+int lin_part_variant(int n_local, int n_free_local, bool slot_kernel);
 int launch_assemble(const DevView& V, int max_n, cudaStream_t st);
 // h_win_n: host array [nW] of reduced-system sizes (6 * free cameras); h_win_beta: [nW] banded half-bandwidth or 0
 int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st, bool keep_factor = false);

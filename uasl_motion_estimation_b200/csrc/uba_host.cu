@@ -136,9 +136,9 @@ struct uba_handle {
   std::vector<int64_t> w_red_off_h;
   int max_n = 0;
   bool use_tile = false;
-  bool use_tile2 = true;
+  bool use_slot = true;                       // the slot-per-warp lineariser takes the parts that are narrow enough
   int tile_threads = 256;
-  int variant_off[6] = {0, 0, 0, 0, 0, 0};
+  int variant_off[kLinVariants + 1] = {};
   std::vector<TilePart> parts_h;
   std::vector<int32_t> tile_cams_h, gen_pts_h;
   std::vector<uint32_t> pt_mask_h;
@@ -265,7 +265,7 @@ void fill_view_static(uba_handle* h) {
   V.camR[0] = h->d_camR.p; V.camR[1] = h->d_camR.p + (size_t)h->NC * kCamStride;
   V.cam_win = h->d_cam_win.p; V.cam_s2 = h->d_cam_s2.p; V.cam_lam = h->d_cam_lam.p; V.cam_y = h->d_cam_y.p;
   V.pts[0] = h->d_pts.p; V.pts[1] = h->d_pts.p + (size_t)h->NP * 3;
-  V.pt_s2 = h->d_pt_s2.p; V.pt_rec = h->d_pt_rec.p; V.pt_obs_off = h->d_pt_obs_off.p; V.pt_win = h->d_pt_win.p;
+  V.pt_is2 = h->d_pt_s2.p; V.pt_rec = h->d_pt_rec.p; V.pt_obs_off = h->d_pt_obs_off.p; V.pt_win = h->d_pt_win.p;
   V.feat = h->d_feat.p; V.obs_cam = h->d_obs_cam.p;
   V.Zbuf = h->d_Zbuf.p;
   V.ws = h->d_ws.p; V.recs = h->d_recs.p; V.n_active = h->d_n_active.p;
@@ -394,9 +394,15 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       h->pt_mask_h[s] = m;
     }
   }
-  // CTA size: 128 threads (two CTAs per SM) when every item's camera-pair blocks fit, else 256
-  int nt = 128;
-  if (const char* e = std::getenv("UBA_TILE_THREADS")) nt = std::atoi(e) == 256 ? 256 : 128;
+  // Which kernel takes an item: the slot-per-warp lineariser (k_lin_slot, chunks of 32 points) up to kSlotMaxLocal local
+  // cameras, k_lin_wide beyond; linearizer = 2 (or UBA_LIN_SLOT=0) sends everything to k_lin_tile2.
+  h->use_slot = h->cfg.linearizer != 2;
+  if (const char* e = std::getenv("UBA_LIN_SLOT")) h->use_slot = std::atoi(e) != 0 && h->cfg.linearizer != 2;
+  auto slot_item = [&](const Item& it) { return h->use_slot && it.nl <= kSlotMaxLocal; };
+  // CTA size of the other kernels: k_lin_wide always has 256 threads; k_lin_tile2 128 (two CTAs per SM) when every item is
+  // narrow, else 256
+  int nt = h->use_slot ? 256 : 128;
+  if (const char* e = std::getenv("UBA_TILE_THREADS")) nt = std::atoi(e) == 256 ? 256 : nt;
   for (const Item& it : items) {
     const int nlf = it.nl - it.nfx;
     if (nlf * (nlf + 1) / 2 > 128 || nlf > 10) nt = 256;
@@ -406,7 +412,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   size_t target_parts = 2 * 148 * (256 / nt);
   if (const char* e = std::getenv("UBA_TILE_PARTS")) target_parts = (size_t)std::max(1, std::atoi(e));
   for (const Item& it : items) {
-    const int Pc = nt / it.nl;
+    const int Pc = slot_item(it) ? 32 : nt / it.nl;
     int part_pts = std::max<size_t>(2 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
     part_pts = ((part_pts + Pc - 1) / Pc) * Pc;
     for (int b = it.begin; b < it.end; b += part_pts) {
@@ -415,18 +421,13 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       h->parts_h.push_back(p);
     }
   }
-  // second-generation kernel (tensor-core Schur products) when every item is narrow enough for 128-thread
-  // CTAs; wide items (> 10 free cameras) keep the first-generation kernel, whose chunks are larger there
-  h->use_tile2 = h->cfg.linearizer != 2 && nt == 128;
-  if (const char* e = std::getenv("UBA_TILE2")) h->use_tile2 = std::atoi(e) != 0 && h->cfg.linearizer != 2;
-  for (int v = 0; v < 6; v++) h->variant_off[v] = 0;
-  if (h->use_tile2) {
-    std::stable_sort(h->parts_h.begin(), h->parts_h.end(), [](const TilePart& a, const TilePart& b) {
-      return lin_tile2_variant(a.n_local - a.n_fixed) < lin_tile2_variant(b.n_local - b.n_fixed);
-    });
-    for (const TilePart& p : h->parts_h) h->variant_off[lin_tile2_variant(p.n_local - p.n_fixed) + 1]++;
-    for (int v = 0; v < 5; v++) h->variant_off[v + 1] += h->variant_off[v];
-  }
+  // one launch per kernel variant: parts grouped by variant
+  const bool slot = h->use_slot;
+  auto variant = [slot](const TilePart& a) { return lin_part_variant(a.n_local, a.n_local - a.n_fixed, slot); };
+  std::stable_sort(h->parts_h.begin(), h->parts_h.end(), [&](const TilePart& a, const TilePart& b) { return variant(a) < variant(b); });
+  for (int v = 0; v <= kLinVariants; v++) h->variant_off[v] = 0;
+  for (const TilePart& p : h->parts_h) h->variant_off[variant(p) + 1]++;
+  for (int v = 0; v < kLinVariants; v++) h->variant_off[v + 1] += h->variant_off[v];
 }
 
 // Tables that depend on fixed_frames: free cameras, reduced-system layout, accumulators.
@@ -618,7 +619,7 @@ int prepare(uba_handle* h, int fixed_frames) {
     std::vector<char> sig;
     auto put = [&](const void* ptr, size_t n) { const char* c = (const char*)ptr; sig.insert(sig.end(), c, c + n); };
     put(h->variant_off, sizeof(h->variant_off)); put(&h->max_n, sizeof(h->max_n));
-    put(&h->acc_total, sizeof(h->acc_total)); put(&h->use_tile, sizeof(h->use_tile)); put(&h->use_tile2, sizeof(h->use_tile2));
+    put(&h->acc_total, sizeof(h->acc_total)); put(&h->use_tile, sizeof(h->use_tile)); put(&h->use_slot, sizeof(h->use_slot));
     put(&h->peer_on, sizeof(h->peer_on));
     if (nW) { put(h->win_n.data(), sizeof(int) * nW); put(h->win_beta.data(), sizeof(int) * nW); }
     if (sig != h->graph_sig) { drop_graph(h); h->graph_sig.swap(sig); }
@@ -818,7 +819,7 @@ int launch_linearizers(uba_handle* h, const DebugOut& dbg) {
     n += launch_lin_generic(h->V, dbg, false, h->stream);
     cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream);
   }
-  n += h->use_tile2 ? launch_lin_tile2(h->V, h->variant_off, h->stream) : launch_lin_tile(h->V, h->stream);
+  n += launch_lin_tiled(h->V, h->variant_off, h->stream);
   DebugOut none{};
   n += launch_lin_generic(h->V, none, true, h->stream);
   return n;
@@ -1935,6 +1936,10 @@ int uba_time_linearize(uba_handle* h, int fixed_frames, double radius, int repea
   int rc = upload_state(h);
   if (!rc) rc = start_solve(h, fixed_frames);
   h->cfg.initial_radius = saved;
+  if (rc) return rc;
+  // one full LM iteration first: what is timed is the pass of a RUNNING solve (Jacobi scales captured, the iterate one
+  // accepted step in), not the very first linearisation with its extra square roots and stores
+  rc = run_iteration(h);
   if (rc) return rc;
   DebugOut none{};
   double total = 0.0;

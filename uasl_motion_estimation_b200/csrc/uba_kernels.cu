@@ -182,9 +182,9 @@ __global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D, int 
     const double Cd[3] = {C6[0], C6[3], C6[5]};
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      if (!st->scale_ready) { s2[c] = jacobi_s2(Cd[c], V.cfg.jacobi_scaling); V.pt_s2[(size_t)p * 3 + c] = s2[c]; }
-      else s2[c] = V.pt_s2[(size_t)p * 3 + c];
-      lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+      if (!st->scale_ready) { s2[c] = jacobi_is2(Cd[c], V.cfg.jacobi_scaling); V.pt_is2[(size_t)p * 3 + c] = s2[c]; }
+      else s2[c] = V.pt_is2[(size_t)p * 3 + c];
+      lam[c] = lm_lambda_inv(Cd[c], s2[c], radius > 0.0 ? 1.0 / radius : 0.0, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
     }
     if (D.C) {
       double* Cp = D.C + (size_t)p * 9;
@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D, int 
 
 
 // ---------------------------------------------------------------------------------------------
-// tiled lineariser (the fast path): one CTA per part (TilePart).  No global atomics in the loop:
+// tiled lineariser for WIDE parts (k_lin_wide: more than kSlotMaxLocal local cameras, e.g. the long tracks of c2):
+// one 256-thread CTA per part (TilePart), the first generation of the tiled design.  No global atomics in the loop:
 //   * every thread owns output tiles in REGISTERS for the whole part —
 //       phase 1 role: thread (point-in-chunk, camera slot) owns the 6x6 camera block B and the
 //                     gradient v of its slot;
@@ -301,14 +302,11 @@ __global__ void __launch_bounds__(128) k_lin_generic(DevView V, DebugOut D, int 
 constexpr int kZStride = 19;   // doubles per staged Z (18 + 1 pad: conflict-free 64-bit stores)
 constexpr int kFlushStride = 43;
 
-#ifndef UBA_TILE_PHASES
-#define UBA_TILE_PHASES 0xff
-#endif
 template <int M, int NT>
-__global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
+__global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_wide(DevView V, int first) {
   constexpr int NR = (M == 4) ? 3 : 2;
   extern __shared__ double sm[];
-  const TilePart part = V.parts[blockIdx.x];
+  const TilePart part = V.parts[first + blockIdx.x];
   const int w = part.window;
   const WinState* st = &V.ws[w];
   if (st->done) return;
@@ -376,7 +374,7 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
       seen = (mask >> sl) & 1u;
       if (mask) { X[0] = V.pts[cur][(size_t)p * 3]; X[1] = V.pts[cur][(size_t)p * 3 + 1]; X[2] = V.pts[cur][(size_t)p * 3 + 2]; }
     }
-    if (seen && (UBA_TILE_PHASES & 1)) {
+    if (seen && (0xff & 1)) {
       const int o = V.pt_obs_off[p] + __popc(mask & ((1u << sl) - 1u));
       double f[M];
 #pragma unroll
@@ -423,7 +421,7 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 1b: per-point sums of E^T E and E^T r over the point's observations ---------------
-    if (UBA_TILE_PHASES & 2)
+    if (0xff & 2)
     for (int idx = t; idx < np * 9; idx += NT) {
       const int q = idx / 9, e = idx - q * 9;
       unsigned m = maskS[q];
@@ -437,7 +435,7 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 1c: one thread per point: damping, 3x3 factor, h = L^-1 g, point record -----------
-    if (t < np && (UBA_TILE_PHASES & 4)) {
+    if (t < np && (0xff & 4)) {
       const unsigned pm = maskS[t];
       if (pm) {
         const int pp = c0 + t;
@@ -447,8 +445,8 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
         double s2[3], lam[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-          s2[c] = scale_ready ? V.pt_s2[(size_t)pp * 3 + c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
-          lam[c] = lm_lambda(Cd[c], s2[c], radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+          s2[c] = scale_ready ? V.pt_is2[(size_t)pp * 3 + c] : jacobi_is2(Cd[c], V.cfg.jacobi_scaling);
+          lam[c] = lm_lambda_inv(Cd[c], s2[c], radius > 0.0 ? 1.0 / radius : 0.0, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
         }
         const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
         const double g[3] = {cg[6], cg[7], cg[8]};
@@ -474,7 +472,7 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
             gmax = fmax(gmax, fabs(Xp[c] - proj));
           }
         }
-        if (!scale_ready) { V.pt_s2[(size_t)pp * 3] = s2[0]; V.pt_s2[(size_t)pp * 3 + 1] = s2[1]; V.pt_s2[(size_t)pp * 3 + 2] = s2[2]; }
+        if (!scale_ready) { V.pt_is2[(size_t)pp * 3] = s2[0]; V.pt_is2[(size_t)pp * 3 + 1] = s2[1]; V.pt_is2[(size_t)pp * 3 + 2] = s2[2]; }
 #pragma unroll
         for (int i = 0; i < 6; i++) LiS[t * 6 + i] = Li[i];
         hS[t * 3] = h[0]; hS[t * 3 + 1] = h[1]; hS[t * 3 + 2] = h[2];
@@ -482,7 +480,7 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 1d: Z = W L^-T for my observation (zero if the point block was not positive definite)
-    if (seen && my_free && (UBA_TILE_PHASES & 8)) {
+    if (seen && my_free && (0xff & 8)) {
       const double* Li = LiS + pl * 6;
       const double l0 = Li[0], l1 = Li[1], l2 = Li[2], l3 = Li[3], l4 = Li[4], l5 = Li[5];
       double* z = big + (size_t)(pl * nlf + (sl - nfx)) * kZStride;
@@ -496,7 +494,7 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
     }
     __syncthreads();
     // ---- phase 2: camera-pair blocks, acc += Z_a Z_b^T over my K-group's points ------------------
-    if (p2_thread && (UBA_TILE_PHASES & 16)) {
+    if (p2_thread && (0xff & 16)) {
       for (int q = kg; q < np; q += G) {
         const unsigned m = maskS[q] >> nfx;
         if (!((m >> ba) & 1u) || !((m >> bb) & 1u)) continue;
@@ -583,10 +581,10 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
 
 
 // ---------------------------------------------------------------------------------------------
-// tiled lineariser, second generation (k_lin_tile2).  Same plan and thread roles for phase 1 as
-// k_lin_tile, but
-//   * the per-point reduction + 3x3 factor is done by ONE thread per point in a single sub-phase
-//     (inputs prefetched), one barrier less;
+// tiled lineariser, second generation (k_lin_tile2): one CTA per part (TilePart), lane = one observation
+// (a point's slot lanes sit in one warp), no global atomics in the loop, one flush per part.
+//   * the per-point sums are reduced with a segmented shuffle tree and the 3x3 block is factored redundantly by
+//     every lane of the point;
 //   * the Schur products  sum_j Z_j Z_j^T  run on the FP64 tensor-core path
 //     (mma.sync.aligned.m8n8k4.f64, SASS DMMA.8x8x4): the chunk's Schur factors are staged as ONE
 //     matrix Zm[6 nlf (padded to 8 T)][3 Pc] in shared memory and every warp accumulates its
@@ -598,6 +596,10 @@ __global__ void __launch_bounds__(NT, kTileThreads / NT) k_lin_tile(DevView V) {
 // win is latency hiding, not a higher ceiling.
 // ---------------------------------------------------------------------------------------------
 #ifndef UBA_EMU
+// experiment hook (scripts/tile_phases.py): phases of k_lin_tile2 can be compiled out one by one
+#ifndef UBA_TILE_PHASES
+#define UBA_TILE_PHASES 0xff
+#endif
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -630,7 +632,7 @@ __host__ __device__ constexpr int t2_main_doubles(int nt) {
 // ... followed by the two prefetch staging buffers
 __host__ __device__ constexpr int t2_stage_doubles(int nt) { return 2 * nt * (kT2StageD + kT2StageI / 2); }
 
-__host__ __device__ inline int t2_ldz(int pc) {
+__host__ __device__ constexpr int t2_ldz(int pc) {
   int k = ((3 * pc + 3) / 4) * 4;     // K padded to the DMMA k = 4
   while ((k & 15) != 4) k += 4;       // row stride == 4 (mod 16) doubles: conflict-free fragment loads
   return k;
@@ -882,9 +884,8 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
       double s2[3], lam[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        s2[c] = scale_ready ? V.pt_s2[(size_t)p * 3 + c] : jacobi_s2(Cd[c], V.cfg.jacobi_scaling);
-        // lm_lambda() without its division: clamp(d s2) / (radius s2)
-        lam[c] = fmin(fmax(Cd[c] * s2[c], V.cfg.min_lm_diagonal), V.cfg.max_lm_diagonal) * (uba_rcp(s2[c]) * inv_radius);
+        s2[c] = scale_ready ? V.pt_is2[(size_t)p * 3 + c] : jacobi_is2(Cd[c], V.cfg.jacobi_scaling);
+        lam[c] = lm_lambda_inv(Cd[c], s2[c], inv_radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
       }
       const double Cdamp[6] = {cg[0] + lam[0], cg[1], cg[2], cg[3] + lam[1], cg[4], cg[5] + lam[2]};
       const double gg[3] = {cg[6], cg[7], cg[8]};
@@ -912,7 +913,7 @@ __device__ __forceinline__ void tile2_part(const DevView& V, const TilePart& par
             gmax = fmax(gmax, fabs(X[c] - proj));
           }
         }
-        if (!scale_ready) { V.pt_s2[(size_t)p * 3] = s2[0]; V.pt_s2[(size_t)p * 3 + 1] = s2[1]; V.pt_s2[(size_t)p * 3 + 2] = s2[2]; }
+        if (!scale_ready) { V.pt_is2[(size_t)p * 3] = s2[0]; V.pt_is2[(size_t)p * 3 + 1] = s2[1]; V.pt_is2[(size_t)p * 3 + 2] = s2[2]; }
       }
     }
     // ---- phase 1d: Z' = W' L^-T into the chunk matrix Zm (zeros where the point does not see my slot) ----
@@ -1115,6 +1116,487 @@ __global__ void __launch_bounds__(NT, NT == 128 ? UBA_T2_MINBLOCKS : 1) k_lin_ti
   const TilePart part = V.parts[first + blockIdx.x];
   if (V.ws[part.window].done) return;
   tile2_part<M, NT, T, TG>(V, part, sm);
+}
+#endif  // !UBA_EMU
+
+// ---------------------------------------------------------------------------------------------
+// tiled lineariser, third generation (k_lin_slot): WARP = CAMERA SLOT, LANE = POINT, plus one POINT WARP.
+//
+// Same plan (TilePart), same factored algebra and the same tensor-core Schur products as k_lin_tile2, but the
+// (point, slot) grid is laid out the other way round: warp s of the CTA owns local camera slot s and its 32 lanes
+// take 32 consecutive points of the part; one more warp (the point warp, lane = point) does everything that is per
+// POINT.  What that buys (ncu on c4: k_lin_tile2 issues ~170 warp instructions per point, two thirds of them overhead):
+//   * the camera record is warp-uniform: broadcast shared-memory loads, no bank conflicts;
+//   * the per-point sums  C = sum E^T E,  g = sum E^T r  cross WARPS through shared memory ([slot][value][lane],
+//     conflict-free) instead of a segmented shuffle tree per warp;
+//   * damping, 3x3 factor, the point record and the gradient norm are done ONCE per point, by the point warp — which
+//     holds none of the slot state, so its 36+ loads are all in flight at once — instead of redundantly by every slot
+//     lane of the point; meanwhile the slot warps run the tensor-core products of the PREVIOUS chunk;
+//   * every lane always holds an observation of its warp's slot: no lane padding (32 / nl), and Z' lands in the chunk
+//     matrix with a lane stride of 3 doubles (conflict-free);
+//   * each 8x8 output tile of the SYRK has ONE owner warp (tiles dealt round-robin over the slot warps): no K-group
+//     reduction at the flush and 4-8 accumulator registers instead of 40.
+// Per chunk of 32 points, slot warps:  linearise -> [A] -> SYRK of the previous chunk -> [B] -> stage Z';
+//                        point warp:   prefetch  -> [A] -> sum, damp, factor, record  -> [B].          Two barriers.
+// Features and points of the next chunk arrive through cp.async into per-lane staging slots ([value][thread]).
+// Handles parts with up to kSlotMaxLocal local cameras (c4, c5: 5; c1, c3: 10); wider parts go to k_lin_wide.
+// ---------------------------------------------------------------------------------------------
+#ifndef UBA_EMU
+constexpr int kSlotLdz = t2_ldz(32);              // 100: K = 96 columns per chunk of 32 points
+constexpr int kSlotStageD = 7;                    // staged doubles per lane and buffer: point (3) + features (<= 4)
+constexpr int kSlotStageI = 4;                    // ... and ints: next chunk's mask, its first-observation offset, obs_cam word, spare
+__host__ __device__ constexpr int slot_rows(int nl_max) { return ((6 * nl_max + 7) / 8) * 8; }
+// shared memory (doubles): camS | Zm [rows][kSlotLdz] | Cs [nl][9][32] | Ls [10][32] | staging; the flush scratch aliases Zm and Cs
+__host__ __device__ constexpr int slot_main_doubles(int nl_max) {
+  const int rows = slot_rows(nl_max), zc = rows * kSlotLdz + nl_max * 9 * 32, sl = rows * (rows + 1) + nl_max * 33;
+  return zc > sl ? zc : sl;
+}
+__host__ __device__ constexpr int slot_stage_doubles(int nl_max) { return 2 * 32 * nl_max * (kSlotStageD + kSlotStageI / 2); }
+__host__ __device__ constexpr size_t slot_smem_bytes(int nl_max) {
+  return sizeof(double) * ((size_t)nl_max * kCamSm + slot_main_doubles(nl_max) + 10 * 32 + slot_stage_doubles(nl_max));
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+template <int ID>
+__device__ __forceinline__ void named_bar(int nthreads) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory"); }
+
+template <int M, int NLMAX>
+__device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part, double* sm) {
+  const unsigned FULL = 0xffffffffu;
+  const int nl = part.n_local, nfx = part.n_fixed, nlf = nl - nfx;
+  const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;        // my point lane; my camera slot (sl == nl: the point warp)
+  if (sl > nl) return;                                            // the CTA is as wide as the widest part of its class
+  const bool pt_warp = sl == nl;
+  const int nslot = 32 * nl, nall = nslot + 32;                    // threads of the slot warps / of all live warps
+  const int t = threadIdx.x;
+  const int w = part.window;
+  const WinState* st = &V.ws[w];
+  const int cur = st->cur;
+  const int cbase = V.w_cam_off[w];
+  const int T = (6 * nlf + 7) / 8;                                 // 8-row tiles of the chunk matrix
+  constexpr int ROWS = slot_rows(NLMAX);
+  double* camS = sm;                                               // [nl][kCamSm]
+  double* Zm = camS + NLMAX * kCamSm;                              // [ROWS][kSlotLdz]
+  double* Cs = Zm + ROWS * kSlotLdz;                               // [nl][9][32]
+  double* Ls = Zm + slot_main_doubles(NLMAX);                      // [10][32]  L^-1 (6), h (3) of the chunk's points
+  double* stageD = Ls + 10 * 32;                                   // [2][kSlotStageD][32 NLMAX]
+  int* stageI = reinterpret_cast<int*>(stageD + 2 * kSlotStageD * 32 * NLMAX);   // [2][kSlotStageI][32 NLMAX]
+  double* scratch = Zm;
+  __shared__ int s_free[NLMAX];
+  __shared__ int s_gc[NLMAX];
+  for (int i = t; i < nl * kCamSm; i += nall) {
+    const int sl2 = i / kCamSm, k = i - sl2 * kCamSm;
+    const int gc = cbase + V.tile_cams[part.cam_list_off + sl2];
+    camS[i] = V.camR[cur][(size_t)gc * kCamStride + (k < 12 ? k : 21)];   // R (9), t (3), small-angle flag
+    if (k == 0) { s_gc[sl2] = gc; s_free[sl2] = V.free_cam[gc]; }
+  }
+  for (int i = t; i < 8 * T * kSlotLdz; i += nall) Zm[i] = 0.0;     // padding rows / columns stay zero for the whole part
+  named_bar<1>(nall);
+
+  if (pt_warp) {
+    // ================= the point warp: lane = point ===============================================================
+    const double radius = st->radius;
+    const double inv_radius = radius > 0.0 ? 1.0 / radius : 0.0;
+    const bool scale_ready = st->scale_ready != 0;
+    double gmax = 0.0, fail = 0.0;
+    for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += 32) {
+      const int p = c0 + lane;
+      // this chunk's per-point inputs: issued here, long before they are needed after [A]
+      unsigned mask = 0;
+      double X[3] = {0, 0, 0}, is2[3] = {1, 1, 1};
+      if (p < part.pt_end) mask = V.pt_mask[p];
+      if (mask) {
+        X[0] = V.pts[cur][(size_t)p * 3]; X[1] = V.pts[cur][(size_t)p * 3 + 1]; X[2] = V.pts[cur][(size_t)p * 3 + 2];
+        if (scale_ready) { is2[0] = V.pt_is2[(size_t)p * 3]; is2[1] = V.pt_is2[(size_t)p * 3 + 1]; is2[2] = V.pt_is2[(size_t)p * 3 + 2]; }
+      }
+      named_bar<1>(nall);                                           // [A] the slots' partial sums are in Cs
+      double Li[6] = {0, 0, 0, 0, 0, 0}, h[3] = {0, 0, 0}, lam[3] = {0, 0, 0}, gg[3] = {0, 0, 0};
+      bool ok = false;
+      if (mask) {
+        double c9[9];
+#pragma unroll
+        for (int e = 0; e < 9; e++) c9[e] = Cs[e * 32 + lane];
+        for (int s2 = 1; s2 < nl; s2++) {
+          const double* cs = Cs + (size_t)s2 * 9 * 32 + lane;
+#pragma unroll
+          for (int e = 0; e < 9; e++) c9[e] += cs[e * 32];
+        }
+        const double Cd[3] = {c9[0], c9[3], c9[5]};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if (!scale_ready) is2[c] = jacobi_is2(Cd[c], V.cfg.jacobi_scaling);
+          lam[c] = lm_lambda_inv(Cd[c], is2[c], inv_radius, V.cfg.min_lm_diagonal, V.cfg.max_lm_diagonal);
+        }
+        const double Cdamp[6] = {c9[0] + lam[0], c9[1], c9[2], c9[3] + lam[1], c9[4], c9[5] + lam[2]};
+        gg[0] = c9[6]; gg[1] = c9[7]; gg[2] = c9[8];
+        ok = point_factor(Cdamp, Li);
+        if (ok) linv_mul(Li, gg, h);
+        else {
+#pragma unroll
+          for (int i = 0; i < 6; i++) Li[i] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; i++) Ls[i * 32 + lane] = Li[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) Ls[(6 + i) * 32 + lane] = h[i];
+      named_bar<2>(nall);                                           // [B] (the record and the norms are off the slots' path)
+      if (mask) {
+        double2* rec = reinterpret_cast<double2*>(V.pt_rec + (size_t)p * kPtRec);   // 128-byte records: eight 16-byte stores
+        if (!ok) {
+          fail += 1.0;
+#pragma unroll
+          for (int i = 0; i < kPtRec / 2; i++) rec[i] = make_double2(0.0, 0.0);
+        } else {
+          rec[0] = make_double2(Li[0], Li[1]); rec[1] = make_double2(Li[2], Li[3]); rec[2] = make_double2(Li[4], Li[5]);
+          rec[3] = make_double2(h[0], h[1]); rec[4] = make_double2(h[2], gg[0]); rec[5] = make_double2(gg[1], gg[2]);
+          rec[6] = make_double2(lam[0], lam[1]); rec[7] = make_double2(lam[2], 0.0);
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            const double proj = V.cfg.use_bounds ? clampd(X[c] - gg[c], V.calib.lo[c], V.calib.hi[c]) : X[c] - gg[c];
+            gmax = fmax(gmax, fabs(X[c] - proj));
+          }
+        }
+        if (!scale_ready) { V.pt_is2[(size_t)p * 3] = is2[0]; V.pt_is2[(size_t)p * 3 + 1] = is2[1]; V.pt_is2[(size_t)p * 3 + 2] = is2[2]; }
+      }
+    }
+    named_bar<1>(nall);                                             // [A'] of the epilogue
+    fail = warp_sum(fail); gmax = warp_max(gmax);
+    if (lane == 0) {
+      if (fail != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_FAIL], fail);
+      if (gmax > 0.0) atomic_max_nonneg(&V.w_max[w], gmax);
+    }
+    return;
+  }
+
+  // ================= slot warps: warp = camera slot, lane = point ====================================================
+  const bool my_free = sl >= nfx;
+  const int ntiles = T * (T + 1) / 2;
+  // my SYRK tiles: idx = sl + i nl, enumerated (I <= J) row by row
+  constexpr int TPW = NLMAX <= 5 ? 2 : 4;                          // T (T + 1) / 2 <= TPW nl for every part of the class
+  int tI[TPW], tJ[TPW], nmine = 0;
+  unsigned pa[TPW], pb[TPW];                                       // shared-window byte addresses of my lane's fragment rows of tile i
+#pragma unroll
+  for (int i = 0; i < TPW; i++) {
+    int idx = sl + i * nl, I = 0;
+    const unsigned zm0 = (unsigned)__cvta_generic_to_shared(Zm);
+    if (idx >= ntiles) { tI[i] = -1; tJ[i] = 0; pa[i] = zm0; pb[i] = zm0; continue; }
+    while (idx >= T - I) { idx -= T - I; I++; }
+    tI[i] = I; tJ[i] = I + idx; nmine = i + 1;
+    pa[i] = zm0 + 8u * (unsigned)((8 * I + (lane >> 2)) * kSlotLdz + (lane & 3));
+    pb[i] = zm0 + 8u * (unsigned)((8 * tJ[i] + (lane >> 2)) * kSlotLdz + (lane & 3));
+  }
+  double acc[TPW][2];
+#pragma unroll
+  for (int i = 0; i < TPW; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+  // tensor-core SYRK over the chunk in Zm, every tile on its owner warp (K = 96: 24 steps of k = 4)
+  auto syrk = [&]() {
+    if (nmine > 0) {
+      auto syrk2 = [&](int i, int j) {        // two tiles side by side: independent accumulator chains
+#pragma unroll
+        for (int ks = 0; ks < 24; ks++) {
+          dmma884(acc[i][0], acc[i][1], lds_f64(pa[i] + 32 * ks), lds_f64(pb[i] + 32 * ks));
+          dmma884(acc[j][0], acc[j][1], lds_f64(pa[j] + 32 * ks), lds_f64(pb[j] + 32 * ks));
+        }
+      };
+      auto syrk1 = [&](int i) {
+#pragma unroll
+        for (int ks = 0; ks < 24; ks++) dmma884(acc[i][0], acc[i][1], lds_f64(pa[i] + 32 * ks), lds_f64(pb[i] + 32 * ks));
+      };
+      if (nmine >= 2) syrk2(0, 1); else syrk1(0);
+      if (TPW > 2) {
+        if (nmine >= 4) syrk2(TPW > 2 ? 2 : 0, TPW > 2 ? 3 : 0); else if (nmine == 3) syrk1(TPW > 2 ? 2 : 0);
+      }
+    }
+  };
+  // camera-side sums of my slot over my lane's points, in the frame where G = J_l(r) has not been applied (see k_lin_tile2)
+  double Bt[5], Bu[9], Br[6], vq[6], zq[6];
+#pragma unroll
+  for (int i = 0; i < 5; i++) Bt[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) Bu[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { Br[i] = 0.0; vq[i] = 0.0; zq[i] = 0.0; }
+  double cost = 0.0;
+
+  // prefetch pipeline (cp.async, no registers held): while chunk k is processed, the point and features of my observation in
+  // chunk k+1 and the mask / first-observation offset of my point in chunk k+2 are in flight into my staging column
+  constexpr int NS = 32 * NLMAX;
+  auto prefetch = [&](int b, int pa_, unsigned m, int off) {
+    double* sd = stageD + (size_t)b * kSlotStageD * NS + t;
+    int* si = stageI + (size_t)b * kSlotStageI * NS + t;
+    if ((m >> sl) & 1u) {
+      const double* px = V.pts[cur] + (size_t)pa_ * 3;
+      cp_async8(sd, px); cp_async8(sd + NS, px + 1); cp_async8(sd + 2 * NS, px + 2);
+      const int o = off + __popc(m & ((1u << sl) - 1u));
+#pragma unroll
+      for (int q = 0; q < M; q++) cp_async8(sd + (3 + q) * NS, V.feat + (size_t)q * V.NO + o);
+      if (M == 2) cp_async4(si + 2 * NS, V.obs_cam + o);
+    }
+    const int pb_ = pa_ + 32;
+    if (pb_ < part.pt_end) { cp_async4(si, V.pt_mask + pb_); cp_async4(si + NS, V.pt_obs_off + pb_); }
+    else si[0] = 0;
+    cp_async_commit();
+  };
+  unsigned mask_cur = 0;
+  {
+    const int pa_ = part.pt_begin + lane;
+    int off0 = 0;
+    if (pa_ < part.pt_end) { mask_cur = V.pt_mask[pa_]; off0 = V.pt_obs_off[pa_]; }
+    prefetch(0, pa_, mask_cur, off0);
+  }
+  const double* R = camS + sl * kCamSm;
+  int buf = 0;
+  bool have_prev = false;
+  for (int c0 = part.pt_begin; c0 < part.pt_end; c0 += 32, buf ^= 1) {
+    const int p = c0 + lane;
+    const unsigned mask = mask_cur;
+    const bool seen = (mask >> sl) & 1u;
+    double X[3] = {0, 0, 0}, f[M];
+#pragma unroll
+    for (int q = 0; q < M; q++) f[q] = 0.0;
+    int cid = 0;
+    {
+      cp_async_wait_all();
+      const double* sd = stageD + (size_t)buf * kSlotStageD * NS + t;
+      const int* si = stageI + (size_t)buf * kSlotStageI * NS + t;
+      if (seen) {
+        X[0] = sd[0]; X[1] = sd[NS]; X[2] = sd[2 * NS];
+#pragma unroll
+        for (int q = 0; q < M; q++) f[q] = sd[(3 + q) * NS];
+        if (M == 2) cid = (si[2 * NS] >> 30) & 1;
+      }
+      const unsigned mask_next = (unsigned)si[0];
+      const int off_next = si[NS];
+      prefetch(buf ^ 1, p + 32, mask_next, off_next);
+      mask_cur = mask_next;
+    }
+    // ---- linearise my observation; partial sums of the point block to shared memory ---------------------------------
+    double Pm[9], u[3] = {0, 0, 0}, cg[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { Pm[i] = 0.0; cg[i] = 0.0; }
+    if (seen) {
+      double Q[5], m3[3];
+      const double rho0 = obs_linearize_q<M>(R, R + 9, R[12] != 0.0, X, f, cid, V.calib, V.loss, Q, m3, u);
+      cost += 0.5 * rho0;
+      const double Q00 = Q[0], Q02 = Q[1], Q11 = Q[2], Q12 = Q[3], Q22 = Q[4];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        Pm[c] = fma(Q00, R[c], Q02 * R[6 + c]);
+        Pm[3 + c] = fma(Q11, R[3 + c], Q12 * R[6 + c]);
+        Pm[6 + c] = fma(Q02, R[c], fma(Q12, R[3 + c], Q22 * R[6 + c]));
+      }
+      cg[0] = fma(R[0], Pm[0], fma(R[3], Pm[3], R[6] * Pm[6]));
+      cg[1] = fma(R[0], Pm[1], fma(R[3], Pm[4], R[6] * Pm[7]));
+      cg[2] = fma(R[0], Pm[2], fma(R[3], Pm[5], R[6] * Pm[8]));
+      cg[3] = fma(R[1], Pm[1], fma(R[4], Pm[4], R[7] * Pm[7]));
+      cg[4] = fma(R[1], Pm[2], fma(R[4], Pm[5], R[7] * Pm[8]));
+      cg[5] = fma(R[2], Pm[2], fma(R[5], Pm[5], R[8] * Pm[8]));
+      cg[6] = fma(R[0], m3[0], fma(R[3], m3[1], R[6] * m3[2]));
+      cg[7] = fma(R[1], m3[0], fma(R[4], m3[1], R[7] * m3[2]));
+      cg[8] = fma(R[2], m3[0], fma(R[5], m3[1], R[8] * m3[2]));
+      if (my_free) {
+        const double ux = u[0], uy = u[1], uz = u[2];
+        Bt[0] += Q00; Bt[1] += Q02; Bt[2] += Q11; Bt[3] += Q12; Bt[4] += Q22;
+        const double U00 = -Q02 * uy, U01 = fma(Q02, ux, -Q00 * uz), U02 = Q00 * uy;
+        const double U10 = fma(Q11, uz, -Q12 * uy), U11 = Q12 * ux, U12 = -Q11 * ux;
+        const double U20 = fma(Q12, uz, -Q22 * uy), U21 = fma(Q22, ux, -Q02 * uz), U22 = fma(Q02, uy, -Q12 * ux);
+        Bu[0] += U00; Bu[1] += U01; Bu[2] += U02; Bu[3] += U10; Bu[4] += U11; Bu[5] += U12; Bu[6] += U20; Bu[7] += U21; Bu[8] += U22;
+        Br[0] = fma(uz, U10, fma(-uy, U20, Br[0]));
+        Br[1] = fma(uz, U11, fma(-uy, U21, Br[1]));
+        Br[2] = fma(uz, U12, fma(-uy, U22, Br[2]));
+        Br[3] = fma(ux, U21, fma(-uz, U01, Br[3]));
+        Br[4] = fma(ux, U22, fma(-uz, U02, Br[4]));
+        Br[5] = fma(uy, U02, fma(-ux, U12, Br[5]));
+        vq[0] += m3[0]; vq[1] += m3[1]; vq[2] += m3[2];
+        vq[3] = fma(uy, m3[2], fma(-uz, m3[1], vq[3]));
+        vq[4] = fma(uz, m3[0], fma(-ux, m3[2], vq[4]));
+        vq[5] = fma(ux, m3[1], fma(-uy, m3[0], vq[5]));
+      }
+    }
+    {
+      double* cs = Cs + (size_t)sl * 9 * 32 + lane;
+#pragma unroll
+      for (int e = 0; e < 9; e++) cs[e * 32] = cg[e];
+    }
+    named_bar<1>(nall);                       // [A] partial sums visible to the point warp; Z' of the previous chunk complete
+    // ---- while the point warp factors this chunk's points: Schur products of the PREVIOUS chunk ---------------------
+    if (have_prev) syrk();
+    have_prev = true;
+    named_bar<2>(nall);                       // [B] L^-1, h of this chunk in Ls; every warp is done reading the old Zm
+    // ---- (free slots) Z' = W' L^-T into the chunk matrix: rows 0..2 P L^-T, rows 3..5 [u]x (P L^-T) ------------------
+    if (my_free) {
+      double Li[6], h[3];
+#pragma unroll
+      for (int i = 0; i < 6; i++) Li[i] = Ls[i * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < 3; i++) h[i] = Ls[(6 + i) * 32 + lane];
+      double zt[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        zt[r][0] = Pm[r * 3] * Li[0];
+        zt[r][1] = fma(Pm[r * 3], Li[1], Pm[r * 3 + 1] * Li[2]);
+        zt[r][2] = fma(Pm[r * 3], Li[3], fma(Pm[r * 3 + 1], Li[4], Pm[r * 3 + 2] * Li[5]));
+      }
+      double* zc = Zm + (size_t)(6 * (sl - nfx)) * kSlotLdz + 3 * lane;     // (not seen: P = 0, u = 0 -> zeros)
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        zc[c] = zt[0][c]; zc[kSlotLdz + c] = zt[1][c]; zc[2 * kSlotLdz + c] = zt[2][c];
+        zc[3 * kSlotLdz + c] = fma(u[1], zt[2][c], -u[2] * zt[1][c]);
+        zc[4 * kSlotLdz + c] = fma(u[2], zt[0][c], -u[0] * zt[2][c]);
+        zc[5 * kSlotLdz + c] = fma(u[0], zt[1][c], -u[1] * zt[0][c]);
+      }
+      const double y0 = fma(zt[0][0], h[0], fma(zt[0][1], h[1], zt[0][2] * h[2]));
+      const double y1 = fma(zt[1][0], h[0], fma(zt[1][1], h[1], zt[1][2] * h[2]));
+      const double y2 = fma(zt[2][0], h[0], fma(zt[2][1], h[1], zt[2][2] * h[2]));
+      zq[0] += y0; zq[1] += y1; zq[2] += y2;
+      zq[3] = fma(u[1], y2, fma(-u[2], y1, zq[3]));
+      zq[4] = fma(u[2], y0, fma(-u[0], y2, zq[4]));
+      zq[5] = fma(u[0], y1, fma(-u[1], y0, zq[5]));
+    }
+  }
+  named_bar<1>(nall);                         // [A'] the last chunk's Z' is staged
+  syrk();
+  named_bar<3>(nslot);                        // from here on only the slot warps
+
+  // ---- flush: Schur tiles -> shared memory, S_ab = D_a S'_ab D_b^T per camera-pair block, one red.add per entry ------
+  const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
+  double* S = V.Sacc + V.w_red_off[w];
+  const int sbeta = V.w_beta[w];
+  const int nloc = 6 * nlf;
+  const double* camG = V.camR[cur];
+  if (nlf > 0) {
+    const int frow = lane >> 2, fc = (lane & 3) * 2;
+    const int LDS2 = 8 * T + 1;
+    double* Sl = scratch;                         // [8 T][LDS2]
+#pragma unroll
+    for (int i = 0; i < TPW; i++) {
+      if (tI[i] >= 0) {
+        double* d = Sl + (size_t)(8 * tI[i] + frow) * LDS2 + 8 * tJ[i] + fc;
+        d[0] = acc[i][0]; d[1] = acc[i][1];
+      }
+    }
+    named_bar<3>(nslot);
+    const int nblk = nlf * (nlf + 1) / 2;
+    const int per = (nslot / 6) * 6;              // a block's six rows never straddle two passes
+    for (int base = 0; base < nblk * 6; base += per) {
+      const int idx = base + t;
+      const bool mine = t < per && idx < nblk * 6;
+      double out[6] = {0, 0, 0, 0, 0, 0};
+      int a = 0, b = 0, r = 0;
+      if (mine) {
+        int blk = idx / 6; r = idx - blk * 6;
+        while (blk >= nlf - a) { blk -= nlf - a; a++; }
+        b = a + blk;
+        const double* Ga = camG + (size_t)s_gc[nfx + a] * kCamStride + 12;
+        const double* Gb = camG + (size_t)s_gc[nfx + b] * kCamStride + 12;
+        auto X = [&](int i, int j) -> double {
+          return (a == b && j < i) ? Sl[(size_t)(6 * a + j) * LDS2 + 6 * a + i] : Sl[(size_t)(6 * a + i) * LDS2 + 6 * b + j];
+        };
+        double row[6];
+        if (r < 3) {
+#pragma unroll
+          for (int j = 0; j < 6; j++) row[j] = X(r, j);
+        } else {
+          const double g0 = Ga[r - 3], g1 = Ga[3 + r - 3], g2 = Ga[6 + r - 3];
+#pragma unroll
+          for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
+        }
+        out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], Gb[j], fma(row[4], Gb[3 + j], row[5] * Gb[6 + j]));
+      }
+      named_bar<3>(nslot);
+      if (mine) {
+#pragma unroll
+        for (int j = 0; j < 6; j++) if (a != b || j >= r) Sl[(size_t)(6 * a + r) * LDS2 + 6 * b + j] = out[j];
+      }
+      named_bar<3>(nslot);
+    }
+    for (int idx = t; idx < nloc * nloc; idx += nslot) {
+      const int row = idx / nloc, colx = idx - row * nloc;
+      if (colx < row) continue;
+      const double v = Sl[(size_t)row * LDS2 + colx];
+      if (v == 0.0) continue;
+      const int a = row / 6, b = colx / 6;
+      const int fa = s_free[nfx + a], fb = s_free[nfx + b];
+      atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + row - 6 * a, 6 * fb + (colx - 6 * b))], v);
+    }
+    named_bar<3>(nslot);
+  }
+  // ---- flush: B', v', Z' h of my slot summed over the lanes (butterfly), packed, brought to the real frame ------------
+  double* Bs = scratch;                           // [nlf][33]: packed upper triangle of B', v', Z' h
+  if (my_free) {
+    double val[33];
+    val[ut6(0, 0)] = Bt[0]; val[ut6(0, 1)] = 0.0; val[ut6(0, 2)] = Bt[1]; val[ut6(1, 1)] = Bt[2]; val[ut6(1, 2)] = Bt[3]; val[ut6(2, 2)] = Bt[4];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) val[ut6(r, 3 + c)] = -Bu[r * 3 + c];
+    val[ut6(3, 3)] = Br[0]; val[ut6(3, 4)] = Br[1]; val[ut6(3, 5)] = Br[2]; val[ut6(4, 4)] = Br[3]; val[ut6(4, 5)] = Br[4]; val[ut6(5, 5)] = Br[5];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { val[21 + i] = vq[i]; val[27 + i] = zq[i]; }
+#pragma unroll
+    for (int e = 0; e < 33; e++) {
+      if (e == ut6(0, 1)) continue;
+      double v = val[e];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      val[e] = v;
+    }
+    if (lane == 0) {
+      double* o = Bs + (size_t)(sl - nfx) * 33;
+#pragma unroll
+      for (int e = 0; e < 33; e++) o[e] = val[e];
+    }
+  }
+  named_bar<3>(nslot);
+  for (int idx = t; idx < nlf * 6; idx += nslot) {
+    const int a = idx / 6, r = idx - a * 6;
+    const int gc = s_gc[nfx + a];
+    const double* Bp = Bs + (size_t)a * 33;
+    const double* G = camG + (size_t)gc * kCamStride + 12;
+    auto X = [&](int i, int j) -> double { return i <= j ? Bp[ut6(i, j)] : Bp[ut6(j, i)]; };
+    double row[6], vr, zr;
+    if (r < 3) {
+#pragma unroll
+      for (int j = 0; j < 6; j++) row[j] = X(r, j);
+      vr = Bp[21 + r]; zr = Bp[27 + r];
+    } else {
+      const double g0 = G[r - 3], g1 = G[3 + r - 3], g2 = G[6 + r - 3];
+#pragma unroll
+      for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
+      vr = fma(g0, Bp[24], fma(g1, Bp[25], g2 * Bp[26]));
+      zr = fma(g0, Bp[30], fma(g1, Bp[31], g2 * Bp[32]));
+    }
+    double out[6];
+    out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
+#pragma unroll
+    for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], G[j], fma(row[4], G[3 + j], row[5] * G[6 + j]));
+#pragma unroll
+    for (int j = 0; j < 6; j++) if (j >= r && out[j] != 0.0) atomicAdd(&V.Bacc[(size_t)gc * 36 + r * 6 + j], out[j]);
+    if (vr != 0.0) atomicAdd(&V.vacc[(size_t)gc * 6 + r], vr);
+    if (zr != 0.0) atomicAdd(&V.zh[(size_t)gc * 6 + r], zr);
+  }
+  cost = warp_sum(cost);
+  if (lane == 0 && cost != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_COST], cost);
+}
+
+// One kernel per slot-count class (blockDim = 32 (NLMAX + 1)); parts are grouped by class on the host.  168 registers:
+// twelve warps per SM (two 192-thread CTAs) put three warps on each of the four register-file partitions of 16 K
+// registers, so 170 per thread is the most that can launch.
+#ifndef UBA_SLOT_MAXNREG
+#define UBA_SLOT_MAXNREG 168
+#endif
+template <int M, int NLMAX>
+__global__ void __maxnreg__(UBA_SLOT_MAXNREG) k_lin_slot(DevView V, int first) {
+  extern __shared__ double sm[];
+  const TilePart part = V.parts[first + blockIdx.x];
+  if (V.ws[part.window].done) return;
+  slot_part<M, NLMAX>(V, part, sm);
 }
 #endif  // !UBA_EMU
 
@@ -2935,43 +3417,6 @@ int launch_lin_generic(const DevView& V, const DebugOut& dbg, bool only_listed, 
 }
 
 
-size_t lin_tile_smem_bytes(int nt) {
-#ifdef UBA_EMU
-  (void)nt;
-  return 0;
-#else
-  return sizeof(double) * (kTileMaxLocal * kCamStride + nt * 9 + nt * 3 + nt * 6 + nt / 2 + nt * kFlushStride);
-#endif
-}
-
-int launch_lin_tile(const DevView& V, cudaStream_t st) {
-  if (V.n_parts == 0) return 0;
-#ifdef UBA_EMU
-  (void)st;
-  return 0;
-#else
-  // 128-thread CTAs (two per SM, in different phases) when every part fits 128 threads, else 256
-  const int nt = V.tile_threads;
-  const size_t smem = lin_tile_smem_bytes(nt);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_lin_tile<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(256));
-    cudaFuncSetAttribute(k_lin_tile<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(256));
-    cudaFuncSetAttribute(k_lin_tile<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(128));
-    cudaFuncSetAttribute(k_lin_tile<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin_tile_smem_bytes(128));
-    configured = true;
-  }
-  if (nt == 128) {
-    if (V.M == 4) UBA_LAUNCH((k_lin_tile<4, 128>), V.n_parts, 128, smem, st, V);
-    else UBA_LAUNCH((k_lin_tile<2, 128>), V.n_parts, 128, smem, st, V);
-  } else {
-    if (V.M == 4) UBA_LAUNCH((k_lin_tile<4, 256>), V.n_parts, 256, smem, st, V);
-    else UBA_LAUNCH((k_lin_tile<2, 256>), V.n_parts, 256, smem, st, V);
-  }
-  return 1;
-#endif
-}
-
 size_t lin_tile2_smem_bytes(int nt) {
 #ifdef UBA_EMU
   (void)nt;
@@ -2996,14 +3441,37 @@ static int launch_t2_variant(const DevView& V, int first, int count, cudaStream_
 
 #endif
 
-// variant of a part: row tiles of 8 over 6 * (free local cameras) rows
-int lin_tile2_variant(int n_free_local) {
+// variant of a part: the slot kernel's two width classes and k_lin_wide beyond them (default), or, with
+// uba_config.linearizer = 2, k_lin_tile2's row-tile classes (8-row tiles over 6 * (free local cameras) rows)
+int lin_part_variant(int n_local, int n_free_local, bool slot_kernel) {
+  if (slot_kernel) return n_local <= 5 ? 0 : n_local <= kSlotMaxLocal ? 1 : 7;   // 7: k_lin_wide
   const int rows = 6 * n_free_local;
-  return rows <= 32 ? 0 : rows <= 48 ? 1 : rows <= 64 ? 2 : rows <= 96 ? 3 : 4;
+  return 2 + (rows <= 32 ? 0 : rows <= 48 ? 1 : rows <= 64 ? 2 : rows <= 96 ? 3 : 4);
 }
 
-// variant_off[6]: parts are sorted by variant; variant v covers [variant_off[v], variant_off[v+1])
-int launch_lin_tile2(const DevView& V, const int* variant_off, cudaStream_t st) {
+#ifndef UBA_EMU
+template <int M, int NLMAX>
+static int launch_slot_variant(const DevView& V, int first, int count, cudaStream_t st) {
+  if (count == 0) return 0;
+  const size_t smem = slot_smem_bytes(NLMAX);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(k_lin_slot<M, NLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+  UBA_LAUNCH((k_lin_slot<M, NLMAX>), count, 32 * (NLMAX + 1), smem, st, V, first);
+  return 1;
+}
+#endif
+
+size_t lin_wide_smem_bytes(int nt) {
+#ifdef UBA_EMU
+  (void)nt;
+  return 0;
+#else
+  return sizeof(double) * (kTileMaxLocal * kCamStride + nt * 9 + nt * 3 + nt * 6 + nt / 2 + nt * kFlushStride);
+#endif
+}
+
+// variant_off[kLinVariants + 1]: parts are sorted by variant; variant v covers [variant_off[v], variant_off[v+1])
+int launch_lin_tiled(const DevView& V, const int* variant_off, cudaStream_t st) {
   if (V.n_parts == 0) return 0;
 #ifdef UBA_EMU
   (void)st; (void)variant_off;
@@ -3011,6 +3479,9 @@ int launch_lin_tile2(const DevView& V, const int* variant_off, cudaStream_t st) 
 #else
   int n = 0;
   const int* o = variant_off;
+  if (V.M == 4) { n += launch_slot_variant<4, 5>(V, o[0], o[1] - o[0], st); n += launch_slot_variant<4, 10>(V, o[1], o[2] - o[1], st); }
+  else { n += launch_slot_variant<2, 5>(V, o[0], o[1] - o[0], st); n += launch_slot_variant<2, 10>(V, o[1], o[2] - o[1], st); }
+  o += 2;
 #define T2_ALL(MM, NN)                                                              \
   n += launch_t2_variant<MM, NN, 4, 1>(V, o[0], o[1] - o[0], st);                     \
   n += launch_t2_variant<MM, NN, 6, 2>(V, o[1], o[2] - o[1], st);                     \
@@ -3023,6 +3494,19 @@ int launch_lin_tile2(const DevView& V, const int* variant_off, cudaStream_t st) 
     else { T2_ALL(2, 256) n += launch_t2_variant<2, 256, 16, 8>(V, o[4], o[5] - o[4], st); }
   }
 #undef T2_ALL
+  o += 5;
+  if (o[1] > o[0]) {     // wide parts
+    const size_t smem = lin_wide_smem_bytes(256);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(k_lin_wide<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_lin_wide<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = true;
+    }
+    if (V.M == 4) UBA_LAUNCH((k_lin_wide<4, 256>), o[1] - o[0], 256, smem, st, V, o[0]);
+    else UBA_LAUNCH((k_lin_wide<2, 256>), o[1] - o[0], 256, smem, st, V, o[0]);
+    n++;
+  }
   return n;
 #endif
 }
