@@ -2913,6 +2913,285 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   }
   if (t == 0 && half == 0 && failed) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
 }
+// ---------------------------------------------------------------------------------------------
+// Block cyclic reduction of a banded reduced camera system on ONE CLUSTER of CTAs (k_chol_bcr).
+//
+// With camera spread bw (half-bandwidth beta = 6 bw + 5) the matrix is block TRIDIAGONAL in super-blocks of m = 6 bw rows
+// (c4, c5: m = 24, N = 50 / 25 super-blocks).  Cholesky in the nested-dissection order of that path graph: level l
+// eliminates every super-block j = s (2 q + 1), s = 2^l, whose two neighbours j - s and j + s stay — all of them
+// INDEPENDENT, so a level is one round of parallel eliminations over the cluster and the sequential depth is
+// log2(N) + 1 eliminations of a 24-row panel instead of N / 2 block steps of the two-sided sweep (k_chol_banded_c2).
+// One elimination (one CTA, panel in shared memory; P = [D_j | A_ja | A_jb | r_j], m x (3 m + 1)):
+//   LDL^T by rows with the pivot reciprocal computed one step ahead, rows scaled to the Cholesky factor at the end:
+//       R = L^T,  W_a = L^-1 A_ja,  W_b = L^-1 A_jb,  z = L^-1 r_j;
+//   Schur updates on the FP64 MMA path:  D_a -= W_a^T W_a,  D_b -= W_b^T W_b  (fp64 red.add: a surviving block has two
+//   eliminated neighbours),  new coupling A_ba = -W_b^T W_a  (single writer),  r_a -= W_a^T z,  r_b -= W_b^T z.
+// The panel STAYS in the CTA's shared memory (a CTA eliminates ~N / cluster size blocks), so the backward pass
+//       x_j = R^-1 (z - W_a x_a - W_b x_b)
+// reads nothing but the neighbours' solutions from global memory.  One cluster barrier per level in each direction.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int bcr_ldp(int mp) { return ((3 * mp + 1 + 15) / 16) * 16 + 8; }   // == 8 (mod 16): conflict-free MMA fragments
+// doubles of scratch per super-block in global memory: D, C (MP x MP each), r, x (MP each)
+__host__ __device__ constexpr size_t bcr_block_doubles(int mp) { return (size_t)2 * mp * mp + 2 * mp; }
+// how many eliminations CTA `rank` of `ncta` performs (eliminations are dealt round-robin in level order); also the
+// number of panels it keeps
+__host__ __device__ inline int bcr_slots(int N, int ncta) { return (N + ncta - 1) / ncta; }
+
+template <int MP>
+__global__ void __launch_bounds__(256) k_chol_bcr(DevView V, int w, int beta) {
+  extern __shared__ double sm[];
+  const WinState* st = &V.ws[w];
+  if (st->done) return;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank(), ncta = (int)cluster.num_blocks();
+  constexpr int LDP = bcr_ldp(MP);
+  constexpr int TT = MP / 8;
+  const int f0 = V.w_free_off[w];
+  const int n = 6 * (V.w_free_off[w + 1] - f0);
+  const int bw1 = beta + 1;
+  const int m = beta - 5;                       // 6 * camera spread
+  const int N = (n + m - 1) / m;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  double* rhs = V.rhs + (size_t)6 * f0;
+  double* Lt = V.A + V.w_red_off[w];
+  const double* Ab = Lt + (size_t)2 * n * bw1;  // assembled band: Ab[i][c] = A[i][i - beta + c]
+  double* G = Lt + (size_t)3 * n * bw1;         // scratch: per super-block D | C | r | x, then the failure flag
+  const size_t BS = bcr_block_doubles(MP);
+  auto Dg = [&](int j) { return G + (size_t)j * BS; };
+  auto Cg = [&](int j) { return G + (size_t)j * BS + MP * MP; };
+  auto rg = [&](int j) { return G + (size_t)j * BS + 2 * MP * MP; };
+  auto xg = [&](int j) { return G + (size_t)j * BS + 2 * MP * MP + MP; };
+  double* gfail = G + (size_t)N * BS;
+  __shared__ double s_rd[MP + 1];               // pivot reciprocals of the panel being eliminated
+  __shared__ double s_x[2 * MP];                // neighbours' solutions (backward)
+  __shared__ int s_fail;
+#ifdef UBA_BAND_TIMING
+  long long tmark[24]; int nmark = 0;
+#define BCR_MARK() { if (t == 0 && nmark < 24) { long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); tmark[nmark++] = c_; } }
+#else
+#define BCR_MARK()
+#endif
+  BCR_MARK()
+  if (t == 0) s_fail = 0;
+  auto Aband = [&](int i, int k) -> double {     // A[i][k] of the assembled matrix, any (i, k) inside [0, n)
+    if (k > i) { const int q = i; i = k; k = q; }
+    return i - k <= beta ? Ab[(size_t)i * bw1 + (k - i + beta)] : 0.0;
+  };
+
+  // ---- phase 0: band -> block tridiagonal form in global scratch (identity on the padded tail) ---------------------------
+  for (int j = rank; j < N; j += ncta) {
+    const int i0 = j * m;
+    for (int e = t; e < MP * MP; e += 256) {
+      const int a = e / MP, b = e - a * MP;
+      const int ia = i0 + a, ib = i0 + b;
+      double d = 0.0, c = 0.0;
+      if (a < m && b < m) {
+        if (ia < n && ib < n) d = Aband(ia, ib); else d = a == b ? 1.0 : 0.0;
+        const int ic = i0 + m + a;              // coupling with the next super-block: A[(j+1) m + a][j m + b]
+        if (ic < n && ib < n) c = Aband(ic, ib);
+      }
+      Dg(j)[e] = d; Cg(j)[e] = c;
+    }
+    for (int a = t; a < MP; a += 256) { rg(j)[a] = (a < m && i0 + a < n) ? rhs[i0 + a] : 0.0; xg(j)[a] = 0.0; }
+  }
+  if (rank == 0 && t == 0) *gfail = 0.0;
+  BCR_MARK()
+  __threadfence();
+  cluster.sync();
+  BCR_MARK()
+
+  // my panels, in the order I eliminate them
+  constexpr int kMaxSlots = 16;
+  int sj[kMaxSlots], ss[kMaxSlots];             // super-block and stride of each of my eliminations
+  int nslot = 0;
+
+  // ---- one elimination -----------------------------------------------------------------------------------------------------
+  // The LDL^T runs on a REGISTER-resident panel: thread (row group rg, column c) keeps rows 8 rg .. 8 rg + 7 of column c of
+  // [D_j | A_ja | A_jb | r_j]; per step it needs the pivot row's entry of its column, the eight multipliers of its rows
+  // (both from the row the owners published in shared memory when it became final) and eight FMAs.  One barrier per step;
+  // the owner of the next pivot publishes its reciprocal together with the row.
+  constexpr int NCOL = 3 * MP + 1, NG = MP / 8;
+  static_assert(NG * NCOL <= 256, "k_chol_bcr: panel does not fit 256 threads");
+  __shared__ double s_row[2][NCOL + 3];         // published pivot rows (double-buffered by step parity)
+  __shared__ double s_d[MP];                    // pivots
+  const int pc = t % NCOL, prg = t / NCOL;      // my column, my row group (prg >= NG: no panel entries)
+  auto eliminate = [&](double* P, int j, int s) {
+    const int a = j - s, b = j + s;
+    const bool has_a = a >= 0 && s > 0, has_b = b < N && s > 0;
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = 0.0;
+    if (prg < NG) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int i = 8 * prg + q;
+        if (pc < MP) v[q] = Dg(j)[i * MP + pc];
+        else if (pc < 2 * MP) v[q] = has_a ? Cg(a)[i * MP + (pc - MP)] : 0.0;               // A_ja = C_a
+        else if (pc < 3 * MP) v[q] = has_b ? Cg(j)[(pc - 2 * MP) * MP + i] : 0.0;           // A_jb = C_j^T
+        else v[q] = rg(j)[i];
+      }
+      if (prg == 0) {
+        s_row[0][pc] = v[0];
+        if (pc == 0) {
+          const double d0 = v[0];
+          if (!(d0 >= 2.2250738585072014e-308 && d0 <= 1.7976931348623157e308)) s_fail = 1;
+          s_d[0] = d0; s_rd[0] = uba_rcp(d0);
+        }
+      }
+    }
+    __syncthreads();
+    BCR_MARK()
+#pragma unroll
+    for (int k = 0; k < MP; k++) {
+      if (k < m) {
+        if (prg < NG) {
+          const double* row = s_row[k & 1];
+          const double pk = row[pc], rd = s_rd[k];
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const int i = 8 * prg + q;
+            if (i > k) v[q] = fma(-(row[i] * rd), pk, v[q]);
+          }
+          if (k + 1 < m && prg == (k + 1) / 8) {
+            const double nv = v[(k + 1) % 8];
+            s_row[(k + 1) & 1][pc] = nv;
+            if (pc == k + 1) {
+              if (!(nv >= 2.2250738585072014e-308 && nv <= 1.7976931348623157e308)) s_fail = 1;
+              s_d[k + 1] = nv; s_rd[k + 1] = uba_rcp(nv);
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // rows -> Cholesky factor in the shared-memory panel: R[i][c] = v / sqrt(d_i); the strict lower triangle of the D part
+    // receives R^T (row k = column k of R, contiguous: the backward substitution reads it without bank conflicts), the
+    // diagonal slot 1 / R[i][i]; rows >= m stay zero
+    BCR_MARK()
+    if (t < MP) s_rd[t] = t < m ? uba_rsqrt(s_d[t]) : 0.0;
+    __syncthreads();
+    if (prg < NG) {
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int i = 8 * prg + q;
+        const double r = i < m ? v[q] * s_rd[i] : 0.0;
+        if (pc >= MP) P[i * LDP + pc] = r;
+        else if (pc > i) { P[i * LDP + pc] = pc < m ? r : 0.0; if (pc < m) P[pc * LDP + i] = r; }
+        else if (pc == i) P[i * LDP + i] = s_rd[i];
+      }
+    }
+    __syncthreads();
+    BCR_MARK()
+    // Schur updates of the neighbours (FP64 MMA): tiles of W_a^T W_a, W_b^T W_b, W_b^T W_a over K = rows of the panel
+    if (has_a || has_b) {
+      const int frow = lane >> 2, fk = lane & 3;
+      for (int tile = warp; tile < 3 * TT * TT; tile += 8) {
+        const int which = tile / (TT * TT), ij = tile - which * TT * TT, I = ij / TT, J = ij - I * TT;
+        if ((which == 0 && !has_a) || (which == 1 && !has_b) || (which == 2 && !(has_a && has_b))) continue;
+        const int cx = (which == 0 ? MP : 2 * MP) + 8 * I, cy = (which == 1 ? 2 * MP : MP) + 8 * J;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < MP / 4; ks++) {
+          const double av = P[(4 * ks + fk) * LDP + cx + frow];
+          const double bv = P[(4 * ks + fk) * LDP + cy + frow];
+          dmma884(c0, c1, av, bv);
+        }
+        const int oi = 8 * I + frow, oj = 8 * J + 2 * fk;
+        if (which == 0) { atomicAdd(&Dg(a)[oi * MP + oj], -c0); atomicAdd(&Dg(a)[oi * MP + oj + 1], -c1); }
+        else if (which == 1) { atomicAdd(&Dg(b)[oi * MP + oj], -c0); atomicAdd(&Dg(b)[oi * MP + oj + 1], -c1); }
+        else { Cg(a)[oi * MP + oj] = -c0; Cg(a)[oi * MP + oj + 1] = -c1; }       // A_ba: rows of b, columns of a
+      }
+      if (t < 2 * MP) {
+        const int side = t / MP, i = t - side * MP;
+        if ((side == 0 && has_a) || (side == 1 && has_b)) {
+          double acc = 0.0;
+          for (int k = 0; k < m; k++) acc = fma(P[k * LDP + (1 + side) * MP + i], P[k * LDP + 3 * MP], acc);
+          atomicAdd(&rg(side == 0 ? a : b)[i], -acc);
+        }
+      }
+    }
+    __syncthreads();
+    BCR_MARK()
+  };
+
+  // ---- forward: levels of independent eliminations -------------------------------------------------------------------------
+  int g = 0;                                    // running index of the elimination (level order)
+  for (int s = 1; s < N; s <<= 1) {
+    for (int j = s; j < N; j += 2 * s, g++) {
+      if (g % ncta != rank) continue;
+      if (nslot < kMaxSlots) { sj[nslot] = j; ss[nslot] = s; eliminate(sm + (size_t)nslot * MP * LDP, j, s); nslot++; }
+    }
+    BCR_MARK()
+    __threadfence();
+    cluster.sync();
+    BCR_MARK()
+  }
+  // the root (super-block 0, no neighbours left) and its solution
+  const bool root_mine = g % ncta == rank;
+  auto solve_block = [&](const double* P, int j, int s) {
+    // y = z - W_a x_a - W_b x_b (eight partial sums per row, shuffle-reduced), then R x = y on warp 0
+    const int a = j - s, b = j + s;
+    const bool has_a = a >= 0 && s > 0, has_b = b < N && s > 0;
+    if (t < 2 * MP) { const int side = t / MP, i = t - side * MP; s_x[t] = (side == 0 ? has_a : has_b) ? xg(side == 0 ? a : b)[i] : 0.0; }
+    __syncthreads();
+    {
+      const int i = t >> 3, q = t & 7;
+      double acc = 0.0;
+      if (i < m) {
+        for (int c = q; c < 2 * MP; c += 8) acc = fma(P[i * LDP + MP + c], s_x[c], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (q == 0 && i < MP) s_rd[i] = i < m ? P[i * LDP + 3 * MP] - acc : 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double y = lane < MP ? s_rd[lane] : 0.0;
+      for (int k = m - 1; k >= 0; k--) {
+        const double xk = __shfl_sync(0xffffffffu, y, k) * P[k * LDP + k];      // diagonal slot = 1 / R[k][k]
+        if (lane == k) y = xk;
+        else if (lane < k) y = fma(-P[k * LDP + lane], xk, y);                  // row k of the lower triangle = column k of R
+      }
+      if (lane < MP) {
+        xg(j)[lane] = y;
+        const int i = j * m + lane;
+        if (lane < m && i < n) rhs[i] = y;
+      }
+    }
+    __syncthreads();
+  };
+  if (root_mine) {
+    double* P = sm + (size_t)nslot * MP * LDP;
+    eliminate(P, 0, 0);
+    solve_block(P, 0, 0);
+  }
+  __threadfence();
+  cluster.sync();
+  // ---- backward: the levels in reverse -------------------------------------------------------------------------------------
+  int top = 1;
+  while (top < N) top <<= 1;
+  int slot = nslot - 1;
+  for (int s = top >> 1; s >= 1; s >>= 1) {
+    while (slot >= 0 && ss[slot] == s) {
+      solve_block(sm + (size_t)slot * MP * LDP, sj[slot], s);
+      slot--;
+    }
+    __threadfence();
+    cluster.sync();
+  }
+  BCR_MARK()
+#ifdef UBA_BAND_TIMING
+  if (t == 0 && rank < 2) { for (int i = 0; i < 24; i++) V.Zbuf[rank * 24 + i] = i < nmark ? (double)(tmark[i] - tmark[0]) : 0.0; }
+#endif
+  // ---- failure: a bad pivot anywhere poisons the solve: report zeros and count the failure ---------------------------------
+  if (t == 0 && s_fail) atomicAdd(gfail, 1.0);
+  __threadfence();
+  cluster.sync();
+  if (*((volatile double*)gfail) != 0.0) {
+    for (int i = rank * 256 + t; i < n; i += ncta * 256) rhs[i] = 0.0;
+    if (rank == 0 && t == 0) atomicAdd(&V.w_loc[(size_t)w * WC_COUNT + WC_FAIL], 1.0);
+  }
+}
+
 #endif  // UBA_EMU
 
 // blocked forward + backward substitution with the factor in global memory; one CTA
@@ -3470,30 +3749,48 @@ size_t lin_wide_smem_bytes(int nt) {
 #endif
 }
 
-// variant_off[kLinVariants + 1]: parts are sorted by variant; variant v covers [variant_off[v], variant_off[v+1])
+// variant_off[kLinVariants + 1]: parts are sorted by variant; variant v covers [variant_off[v], variant_off[v+1]).
+// When parts of several variants exist (ragged windows such as c2: short tracks on k_lin_slot, long ones on k_lin_wide),
+// their kernels run SIDE BY SIDE: every variant after the first is launched on a side stream forked from `st` and joined
+// back (inside a stream capture this becomes a fork / join in the graph).  They only meet in the fp64 atomics.
 int launch_lin_tiled(const DevView& V, const int* variant_off, cudaStream_t st) {
   if (V.n_parts == 0) return 0;
 #ifdef UBA_EMU
   (void)st; (void)variant_off;
   return 0;
 #else
-  int n = 0;
+  constexpr int kSide = 3;
+  static thread_local cudaStream_t side[kSide] = {};
+  static thread_local cudaEvent_t ev_fork = nullptr, ev_join[kSide] = {};
+  if (!ev_fork) {
+    cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < kSide; i++) { cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming); }
+  }
+  int n = 0, used = 0;
+  bool forked = false;
+  // the stream for the next non-empty variant: the caller's for the first, a side stream for the following ones
+  auto next_stream = [&](int count) -> cudaStream_t {
+    if (count <= 0 || n == 0) return st;
+    if (!forked) { cudaEventRecord(ev_fork, st); forked = true; }
+    cudaStream_t s2 = side[used % kSide];
+    if (used < kSide) cudaStreamWaitEvent(s2, ev_fork, 0);
+    used++;
+    return s2;
+  };
   const int* o = variant_off;
-  if (V.M == 4) { n += launch_slot_variant<4, 5>(V, o[0], o[1] - o[0], st); n += launch_slot_variant<4, 10>(V, o[1], o[2] - o[1], st); }
-  else { n += launch_slot_variant<2, 5>(V, o[0], o[1] - o[0], st); n += launch_slot_variant<2, 10>(V, o[1], o[2] - o[1], st); }
+  { const int c0 = o[1] - o[0]; cudaStream_t s2 = next_stream(c0); n += V.M == 4 ? launch_slot_variant<4, 5>(V, o[0], c0, s2) : launch_slot_variant<2, 5>(V, o[0], c0, s2); }
+  { const int c1 = o[2] - o[1]; cudaStream_t s2 = next_stream(c1); n += V.M == 4 ? launch_slot_variant<4, 10>(V, o[1], c1, s2) : launch_slot_variant<2, 10>(V, o[1], c1, s2); }
   o += 2;
-#define T2_ALL(MM, NN)                                                              \
-  n += launch_t2_variant<MM, NN, 4, 1>(V, o[0], o[1] - o[0], st);                     \
-  n += launch_t2_variant<MM, NN, 6, 2>(V, o[1], o[2] - o[1], st);                     \
-  n += launch_t2_variant<MM, NN, 8, 2>(V, o[2], o[3] - o[2], st);                     \
-  n += launch_t2_variant<MM, NN, 12, 4>(V, o[3], o[4] - o[3], st);
+#define T2_ONE(MM, NN, TT, GG, k) { const int cc = o[k + 1] - o[k]; cudaStream_t s2 = next_stream(cc); n += launch_t2_variant<MM, NN, TT, GG>(V, o[k], cc, s2); }
+#define T2_ALL(MM, NN) T2_ONE(MM, NN, 4, 1, 0) T2_ONE(MM, NN, 6, 2, 1) T2_ONE(MM, NN, 8, 2, 2) T2_ONE(MM, NN, 12, 4, 3)
   if (V.tile_threads == 128) {
     if (V.M == 4) { T2_ALL(4, 128) } else { T2_ALL(2, 128) }
   } else {
-    if (V.M == 4) { T2_ALL(4, 256) n += launch_t2_variant<4, 256, 16, 8>(V, o[4], o[5] - o[4], st); }
-    else { T2_ALL(2, 256) n += launch_t2_variant<2, 256, 16, 8>(V, o[4], o[5] - o[4], st); }
+    if (V.M == 4) { T2_ALL(4, 256) T2_ONE(4, 256, 16, 8, 4) }
+    else { T2_ALL(2, 256) T2_ONE(2, 256, 16, 8, 4) }
   }
 #undef T2_ALL
+#undef T2_ONE
   o += 5;
   if (o[1] > o[0]) {     // wide parts
     const size_t smem = lin_wide_smem_bytes(256);
@@ -3503,10 +3800,13 @@ int launch_lin_tiled(const DevView& V, const int* variant_off, cudaStream_t st) 
       cudaFuncSetAttribute(k_lin_wide<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       configured = true;
     }
-    if (V.M == 4) UBA_LAUNCH((k_lin_wide<4, 256>), o[1] - o[0], 256, smem, st, V, o[0]);
-    else UBA_LAUNCH((k_lin_wide<2, 256>), o[1] - o[0], 256, smem, st, V, o[0]);
+    cudaStream_t s2 = next_stream(o[1] - o[0]);
+    if (V.M == 4) UBA_LAUNCH((k_lin_wide<4, 256>), o[1] - o[0], 256, smem, s2, V, o[0]);
+    else UBA_LAUNCH((k_lin_wide<2, 256>), o[1] - o[0], 256, smem, s2, V, o[0]);
     n++;
   }
+  // join the side streams back
+  for (int i = 0; i < used && i < kSide; i++) { cudaEventRecord(ev_join[i], side[i]); cudaStreamWaitEvent(st, ev_join[i], 0); }
   return n;
 #endif
 }
@@ -3562,6 +3862,31 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
       if (h_win_beta[w] > 0) {
         const int beta = h_win_beta[w];
 #ifndef UBA_EMU
+        // UBA_BAND_BCR=<cluster size>: block cyclic reduction on one cluster of CTAs.  Correct (tested), log-depth, but its
+        // per-elimination constant is not there yet: c4 0.149 ms on 16 CTAs against 0.116 ms for the two-sided sweep below
+        // (scripts/bcr_timing.py gives the phase split), so it is off by default.
+        static const int bcr_ctas = [] { const char* e = getenv("UBA_BAND_BCR"); return e ? atoi(e) : 0; }();
+        if (bcr_ctas > 0 && beta >= 11 && beta <= 35 && (beta - 5) % 6 == 0 && n >= 12 * (beta + 1)) {
+          const int m = beta - 5, mp = ((m + 7) / 8) * 8, N = (n + m - 1) / m;
+          int ncta = bcr_ctas > 16 ? 16 : bcr_ctas;
+          if (ncta > N) ncta = N;
+          const size_t smem = (size_t)bcr_slots(N, ncta) * mp * bcr_ldp(mp) * sizeof(double);
+          const size_t scratch = (size_t)3 * n * (beta + 1) + (size_t)N * bcr_block_doubles(mp) + 1;
+          if (mp <= 24 && smem <= 200 * 1024 && bcr_slots(N, ncta) <= 16 && scratch <= (size_t)n * n) {
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(ncta); lc.blockDim = dim3(256); lc.dynamicSmemBytes = smem; lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+#define UBA_BCR_LAUNCH(MPV) { cudaFuncSetAttribute(k_chol_bcr<MPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (ncta > 8) cudaFuncSetAttribute(k_chol_bcr<MPV>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); \
+            cudaLaunchKernelEx(&lc, k_chol_bcr<MPV>, V, w, beta); }
+            if (mp == 8) UBA_BCR_LAUNCH(8) else if (mp == 16) UBA_BCR_LAUNCH(16) else UBA_BCR_LAUNCH(24)
+#undef UBA_BCR_LAUNCH
+            launches++;
+            continue;
+          }
+        }
         // default for long bands: the two halves of the band on a cluster of two CTAs
         static const bool use_c2 = [] { const char* e = getenv("UBA_BAND_C2"); return !(e && e[0] == '0'); }();
         if (use_c2 && beta >= 11 && beta <= 35 && n >= 12 * (beta + 1)) {
