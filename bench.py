@@ -204,13 +204,125 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_c2seq(args, rank, local):
+    """BASELINE config c2 as it is defined: a 200-keyframe stereo sequence, a 20-keyframe window advanced one keyframe per
+    BA call (181 calls), every call warm-started from the previous one's solution, K = 4 LM iterations per call.
+
+    ours: the window SLIDES on the device (uba_window_advance: only the new keyframe's observations travel) and, beside it,
+    the same sequence with every window re-submitted through uba_set_problem; `e2e` is the sliding path, host buffers in and
+    out, every call.  --impl reference: the oracle's LM on every 20th window of the same sequence, same start, same K.
+    One GPU (a per-frame loop does not shard); other ranks exit."""
+    if rank != 0:
+        return
+    import oracle_binding as ob
+    from uasl_motion_estimation_b200 import capi, synth
+    K = 4
+    fixed = 2
+    seq = synth.SlidingSequence()
+    ids0 = seq.initial_ids()
+    cfgkw = dict(loss_kind=capi.LOSS_HUBER, fixed_iterations=K)
+    config = {"workload": "c2seq", "n_keyframes": seq.n_frames, "window": seq.W, "calls": seq.n_calls, "lm_iterations_per_call": K,
+              "fixed_frames": fixed, "loss": "huber", "parallelism": "single GPU", "scale": 1.0}
+    if args.impl == "reference":
+        ob.build()
+        ob.lib().uba_ref_set_threads(os.cpu_count() or 1)
+        cfg = capi.default_config(**cfgkw)
+        # the windows the GPU arm would hand over: replayed from the generator's initial values (no GPU in this arm)
+        ids = ids0; t = 0.0; nobs = 0; n = 0
+        for first in range(seq.n_calls):
+            if first % 20 == 0 and n < max(1, args.steps // 2):
+                win = seq.window(first, ids)
+                t0 = time.perf_counter(); ob.optimise(win, cfg, fixed); t += time.perf_counter() - t0
+                nobs += win.n_obs; n += 1
+            if first + 1 < seq.n_calls:
+                _, ids = seq.advance(first, ids)
+        value = nobs * K / t
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t / (n * K) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": ob.lib().uba_ref_max_threads(), "kind": "port",
+                                 "sample": f"{n} of the {seq.n_calls} per-frame calls (every 20th window), {K} LM iterations each, through the oracle"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_call": t / n * 1e3}}
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    torch.cuda.set_device(local)
+
+    def run_sequence(sliding):
+        """Returns (per-call ms, observation count per call, h2d bytes, d2h bytes, kernel launches)."""
+        cfg = capi.default_config(device=local, sliding_window=1 if sliding else 0, **cfgkw)
+        h = capi.Handle(cfg)
+        ids = ids0
+        w = seq.window(0, ids)
+        ms = []; nobs = []; h2d = d2h = 0
+        t0 = time.perf_counter()
+        h.set_problem(4, w.cams_init, w.pts_init, w.feats, w.cam_idx, w.pt_idx, w.cam_id, w.calib)
+        h.optimise(fixed); cams = h.cameras(); pts = h.points()
+        ms.append((time.perf_counter() - t0) * 1e3); nobs.append(w.n_obs)
+        for first in range(seq.n_calls - 1):
+            kw, ids_new = seq.advance(first, ids)
+            if not sliding:
+                # what a caller without the sliding entry point does: carry the solution over on the host, re-submit everything
+                alive = seq.hi[ids] >= first + 1
+                cams0 = np.concatenate([cams[1:], kw["new_cams6"]]); pts0 = np.concatenate([pts[alive], kw["new_pts3"]])
+                w = seq.window(first + 1, ids_new, cams=cams0, pts=pts0)
+            t0 = time.perf_counter()
+            if sliding:
+                h.window_advance(**kw)
+                h2d += kw["feats"].nbytes + kw["cam_idx"].nbytes + kw["pt_idx"].nbytes + kw["new_cams6"].nbytes + kw["new_pts3"].nbytes
+            else:
+                h.set_problem(4, w.cams_init, w.pts_init, w.feats, w.cam_idx, w.pt_idx, w.cam_id, w.calib)
+                h2d += w.feats.nbytes + w.cam_idx.nbytes + w.pt_idx.nbytes + w.cam_id.nbytes + w.cams_init.nbytes + w.pts_init.nbytes
+            rc, sums = h.optimise(fixed)
+            cams = h.cameras(); pts = h.points()
+            ms.append((time.perf_counter() - t0) * 1e3); nobs.append(h.n_obs)
+            d2h += cams.nbytes + pts.nbytes
+            ids = ids_new
+        launches = h.timing()["kernel_launches"]
+        # device-resident iteration time on the last (steady-state) window
+        ms_iter = h.time_iteration(fixed, iterations=max(args.steps, 5), flush_l2=True)
+        ms_lin = h.time_linearize(fixed, 1e4, repeats=max(args.steps, 5), flush_l2=True)
+        n_last = h.n_obs
+        h.close()
+        return np.array(ms), np.array(nobs), h2d, d2h, launches, ms_iter, ms_lin, n_last
+
+    run_sequence(True)                                        # warm-up: allocations, graph capture, clocks
+    sampler = ClockSampler(local); sampler.start()
+    ms_s, nobs, h2d, d2h, launches, ms_iter, ms_lin, n_last = run_sequence(True)
+    ms_r, _, h2d_r, _, _, _, _, _ = run_sequence(False)
+    clocks = sampler.stop()
+    calls = len(ms_s)
+    e2e = float(nobs[1:].sum()) * K / (ms_s[1:].sum() * 1e-3)        # the first call is the cold start (uba_set_problem)
+    hbm_peak, peak_src = measured_peaks()
+    line = {"metric": METRIC, "value": n_last / (ms_iter * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_iter, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config, n_obs_last_window=int(n_last), n_obs_per_call_mean=float(nobs.mean())),
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d / (calls - 1) / K), "d2h_bytes_per_step": int(d2h / (calls - 1) / K),
+                    "ms_per_call": float(np.median(ms_s[1:])), "ms_per_call_p95": float(np.percentile(ms_s[1:], 95)),
+                    "lm_iterations_per_call": K, "calls": calls,
+                    "resubmit_ms_per_call": float(np.median(ms_r[1:])), "resubmit_h2d_bytes_per_call": int(h2d_r / (calls - 1)),
+                    "sliding_h2d_bytes_per_call": int(h2d / (calls - 1))},
+            "lm_iters_per_s": 1e3 / ms_iter, "linearize_obs_per_s": n_last / (ms_lin * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                         "kernel": "linearise+Schur pass", "kernel_ms": ms_lin, "note": "see the c4 / c3 lines for the roofline of this kernel"}}
+    if not args.no_cpu_baseline:
+        ob.build()
+        cfg = capi.default_config(**cfgkw)
+        win = seq.window(0, ids0)
+        t0 = time.perf_counter(); ob.optimise(win, cfg, fixed); tt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": win.n_obs * K / tt, "unit": UNIT, "cores": ob.lib().uba_ref_max_threads(), "kind": "port",
+                                "sample": f"the first window ({win.n_obs} observations), {K} LM iterations through the oracle", "ms_per_call": tt * 1e3}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c2seq", "c3", "c4", "c5"])
     ap.add_argument("--windows", type=int, default=0, help="c3: windows per GPU (default 512)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the point count (debugging only; 1.0 = BASELINE size)")
     ap.add_argument("--linearizer", type=int, default=0)
@@ -219,6 +331,9 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "c2seq":
+        run_c2seq(args, rank, local)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -150,3 +150,30 @@ def test_oracle_infeasible_start_fails(oracle, emu_lib):
     o = oracle.optimise(win, capi.default_config(emu_lib), 2)
     assert o["rc"] == capi.UBA_ERR_INFEASIBLE and o["summary"]["usable"] == 0
     np.testing.assert_array_equal(o["pts"], before)
+
+
+# ---- boundary maths of the product library (libuba_host.so: same sources as libuba.so) against the oracle's copy -----------
+def test_library_log_exp_maps_match_the_oracle_and_clamp():
+    """uba_log_map_quat / uba_exp_map_quat (core/rotation_utils.h:190-204) of the PRODUCT library: equal to the oracle's
+    restatement on random rotations, inverse of each other, and clamped where the reference's acos(w > 1) gives NaN."""
+    import oracle_binding as ob
+    from uasl_motion_estimation_b200 import capi
+    lib = capi.load_host()
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        if q[0] < 0: q = -q
+        r_lib = np.zeros(3); r_ref = np.zeros(3)
+        lib.uba_log_map_quat(capi.dptr(q), capi.dptr(r_lib)); ob.lib().uba_ref_log_map_quat(capi.dptr(q), capi.dptr(r_ref))
+        assert np.array_equal(r_lib, r_ref)
+        q_lib = np.zeros(4); q_ref = np.zeros(4)
+        lib.uba_exp_map_quat(capi.dptr(r_lib), capi.dptr(q_lib)); ob.lib().uba_ref_exp_map_quat(capi.dptr(r_lib), capi.dptr(q_ref))
+        assert np.array_equal(q_lib, q_ref)
+        assert np.abs(q_lib - q).max() < 1e-12
+    # identity and the w a hair above one case (rotation_utils.h:203 has no clamp: NaN in the reference)
+    for w in (1.0, 1.0 + 2.3e-16):
+        q = np.array([w, 0.0, 0.0, 0.0]); r = np.ones(3)
+        lib.uba_log_map_quat(capi.dptr(q), capi.dptr(r))
+        assert np.array_equal(r, np.zeros(3))
+    q = np.zeros(4); lib.uba_exp_map_quat(capi.dptr(np.zeros(3)), capi.dptr(q))
+    assert np.array_equal(q, np.array([1.0, 0.0, 0.0, 0.0]))

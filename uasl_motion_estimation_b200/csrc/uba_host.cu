@@ -72,12 +72,17 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;
+  // grows with a quarter of headroom: a sliding window's sizes creep up and down from call to call, and every
+  // cudaFree / cudaMalloc pair costs milliseconds
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) cap = n;
+    p = nullptr;
+    const size_t want = cap ? n + n / 4 + 256 : std::max<size_t>(n, 1);
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess && want > n) { cudaGetLastError(); e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess) cap = n; return e; }
+    if (e == cudaSuccess) cap = want;
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -89,9 +94,12 @@ struct PinBuf {
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
     if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) cap = n;
+    p = nullptr;
+    const size_t want = cap ? n + n / 4 + 256 : std::max<size_t>(n, 1);
+    cap = 0;
+    cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess && want > n) { cudaGetLastError(); e = cudaMallocHost((void**)&p, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess) cap = n; return e; }
+    if (e == cudaSuccess) cap = want;
     return e;
   }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
@@ -1610,7 +1618,7 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
   if (!pts3_all) {
     // the re-slotted points sit in the scratch: move them to parity 0 of the (possibly re-sized) point buffer, keep a host copy
     DevBuf<double> fresh_pts;
-    if ((size_t)NPn * 6 > h->d_pts.cap) { CU(h, fresh_pts.reserve((size_t)NPn * 6)); std::swap(fresh_pts.p, h->d_pts.p); std::swap(fresh_pts.cap, h->d_pts.cap); fresh_pts.release(); }
+    if ((size_t)NPn * 6 > h->d_pts.cap) { CU(h, fresh_pts.reserve((size_t)NPn * 6 + (size_t)NPn * 6 / 4)); std::swap(fresh_pts.p, h->d_pts.p); std::swap(fresh_pts.cap, h->d_pts.cap); fresh_pts.release(); }
     CU(h, cudaMemcpyAsync(h->d_pts.p, h->d_pt_rec.p, sizeof(double) * 3 * NPn, cudaMemcpyDeviceToDevice, st));
     CU(h, cudaMemcpyAsync(h->h_pts.p, h->d_pts.p, sizeof(double) * 3 * NPn, cudaMemcpyDeviceToHost, st));
     h->host_iter_pending = true;
