@@ -2978,20 +2978,27 @@ __global__ void __launch_bounds__(256) k_chol_bcr(DevView V, int w, int beta) {
     return i - k <= beta ? Ab[(size_t)i * bw1 + (k - i + beta)] : 0.0;
   };
 
-  // ---- phase 0: band -> block tridiagonal form in global scratch (identity on the padded tail) ---------------------------
+  // ---- phase 0: band -> block tridiagonal form in global scratch (identity on the padded tail).  Loads in batches of
+  //      independent registers: a plain load / store loop is compiled as one memory round trip per element ----------------------
   for (int j = rank; j < N; j += ncta) {
     const int i0 = j * m;
-    for (int e = t; e < MP * MP; e += 256) {
+    constexpr int U = (MP * MP + 255) / 256;
+    double dv[U], cv[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int e = t + u * 256;
       const int a = e / MP, b = e - a * MP;
       const int ia = i0 + a, ib = i0 + b;
       double d = 0.0, c = 0.0;
-      if (a < m && b < m) {
+      if (e < MP * MP && a < m && b < m) {
         if (ia < n && ib < n) d = Aband(ia, ib); else d = a == b ? 1.0 : 0.0;
         const int ic = i0 + m + a;              // coupling with the next super-block: A[(j+1) m + a][j m + b]
         if (ic < n && ib < n) c = Aband(ic, ib);
       }
-      Dg(j)[e] = d; Cg(j)[e] = c;
+      dv[u] = d; cv[u] = c;
     }
+#pragma unroll
+    for (int u = 0; u < U; u++) { const int e = t + u * 256; if (e < MP * MP) { Dg(j)[e] = dv[u]; Cg(j)[e] = cv[u]; } }
     for (int a = t; a < MP; a += 256) { rg(j)[a] = (a < m && i0 + a < n) ? rhs[i0 + a] : 0.0; xg(j)[a] = 0.0; }
   }
   if (rank == 0 && t == 0) *gfail = 0.0;
@@ -3006,78 +3013,80 @@ __global__ void __launch_bounds__(256) k_chol_bcr(DevView V, int w, int beta) {
   int nslot = 0;
 
   // ---- one elimination -----------------------------------------------------------------------------------------------------
-  // The LDL^T runs on a REGISTER-resident panel: thread (row group rg, column c) keeps rows 8 rg .. 8 rg + 7 of column c of
-  // [D_j | A_ja | A_jb | r_j]; per step it needs the pivot row's entry of its column, the eight multipliers of its rows
-  // (both from the row the owners published in shared memory when it became final) and eight FMAs.  One barrier per step;
-  // the owner of the next pivot publishes its reciprocal together with the row.
-  constexpr int NCOL = 3 * MP + 1, NG = MP / 8;
-  static_assert(NG * NCOL <= 256, "k_chol_bcr: panel does not fit 256 threads");
-  __shared__ double s_row[2][NCOL + 3];         // published pivot rows (double-buffered by step parity)
+  // The LDL^T runs on a REGISTER-resident panel, one thread per COLUMN of [D_j | A_ja | A_jb | r_j] (3 MP + 1 threads, three
+  // warps; the other warps wait at the CTA barrier behind the loop): the thread keeps its column's MP rows.  Step k needs
+  // its own row-k entry (a register), the pivot reciprocal and the row-k entries of the columns below the pivot — the
+  // multipliers — which every column thread published in shared memory when its row k became final:
+  //     v[i] -= row_k[i] * (v[k] / d_k)        for the rows i > k,
+  // one load and one FMA per entry, all indices static.  One named barrier (three warps) per step; the owner of the next
+  // pivot publishes its reciprocal together with its row entry.
+  constexpr int NCOL = 3 * MP + 1;
+  constexpr int NLD = ((NCOL + 31) / 32) * 32;  // threads in the LDL^T loop (whole warps)
+  static_assert(NLD <= 256, "k_chol_bcr: panel does not fit 256 threads");
+  __shared__ double s_row[2][NCOL + 3];         // published rows (double-buffered by step parity); NCOL >= 2 MP: reads past a row's end stay inside
   __shared__ double s_d[MP];                    // pivots
-  const int pc = t % NCOL, prg = t / NCOL;      // my column, my row group (prg >= NG: no panel entries)
+  const int pc = t;                             // my column (t < NCOL)
   auto eliminate = [&](double* P, int j, int s) {
     const int a = j - s, b = j + s;
     const bool has_a = a >= 0 && s > 0, has_b = b < N && s > 0;
-    double v[8];
+    if (t < NLD) {
+      double v[MP];
 #pragma unroll
-    for (int q = 0; q < 8; q++) v[q] = 0.0;
-    if (prg < NG) {
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int i = 8 * prg + q;
-        if (pc < MP) v[q] = Dg(j)[i * MP + pc];
-        else if (pc < 2 * MP) v[q] = has_a ? Cg(a)[i * MP + (pc - MP)] : 0.0;               // A_ja = C_a
-        else if (pc < 3 * MP) v[q] = has_b ? Cg(j)[(pc - 2 * MP) * MP + i] : 0.0;           // A_jb = C_j^T
-        else v[q] = rg(j)[i];
+      for (int i = 0; i < MP; i++) {
+        double x = 0.0;
+        if (pc < MP) x = Dg(j)[i * MP + pc];
+        else if (pc < 2 * MP) x = has_a ? Cg(a)[i * MP + (pc - MP)] : 0.0;               // A_ja = C_a
+        else if (pc < 3 * MP) x = has_b ? Cg(j)[(pc - 2 * MP) * MP + i] : 0.0;           // A_jb = C_j^T
+        else if (pc == 3 * MP) x = rg(j)[i];
+        v[i] = x;
       }
-      if (prg == 0) {
-        s_row[0][pc] = v[0];
-        if (pc == 0) {
-          const double d0 = v[0];
-          if (!(d0 >= 2.2250738585072014e-308 && d0 <= 1.7976931348623157e308)) s_fail = 1;
-          s_d[0] = d0; s_rd[0] = uba_rcp(d0);
-        }
+      if (pc < NCOL) s_row[0][pc] = v[0];
+      if (pc == 0) {
+        const double d0 = v[0];
+        if (!(d0 >= 2.2250738585072014e-308 && d0 <= 1.7976931348623157e308)) s_fail = 1;
+        s_d[0] = d0; s_rd[0] = uba_rcp(d0);
       }
-    }
-    __syncthreads();
-    BCR_MARK()
+      asm volatile("bar.sync 2, %0;" ::"n"(NLD) : "memory");
+      BCR_MARK()
+      // A ROLLED loop over the pivots with a compact body: straight-line code that runs once per elimination is fetched
+      // at ~6.5 cycles per instruction (measured: 450 cycles per step for 70 instructions, barriers and the reciprocal
+      // chain not counting), a loop body that stays in the instruction cache is not.  The register column SHIFTS by one row
+      // per step (the shift rides on the FMA's destination), so that the pivot row is always v[0] and every index is static;
+      // a row's final value goes to the shared-memory panel when it leaves.
+      const unsigned srow = (unsigned)__cvta_generic_to_shared(&s_row[0][0]);
+#pragma unroll 1
+      for (int kk = 0; kk < m; kk++) {
+        const unsigned row = srow + (unsigned)(((kk & 1) * (NCOL + 3) + kk) * 8);   // &s_row[kk & 1][kk]
+        const double f = v[0] * s_rd[kk];
+        if (pc < NCOL) P[kk * LDP + pc] = v[0];                                     // row kk, unscaled
 #pragma unroll
-    for (int k = 0; k < MP; k++) {
-      if (k < m) {
-        if (prg < NG) {
-          const double* row = s_row[k & 1];
-          const double pk = row[pc], rd = s_rd[k];
-#pragma unroll
-          for (int q = 0; q < 8; q++) {
-            const int i = 8 * prg + q;
-            if (i > k) v[q] = fma(-(row[i] * rd), pk, v[q]);
-          }
-          if (k + 1 < m && prg == (k + 1) / 8) {
-            const double nv = v[(k + 1) % 8];
-            s_row[(k + 1) & 1][pc] = nv;
-            if (pc == k + 1) {
-              if (!(nv >= 2.2250738585072014e-308 && nv <= 1.7976931348623157e308)) s_fail = 1;
-              s_d[k + 1] = nv; s_rd[k + 1] = uba_rcp(nv);
-            }
+        for (int j = 1; j < MP; j++) v[j - 1] = fma(-lds_f64(row + 8 * j), f, v[j]);   // entries past the last row: unused
+        v[MP - 1] = 0.0;
+        if (kk + 1 < m) {
+          if (pc < NCOL) s_row[(kk + 1) & 1][pc] = v[0];
+          if (pc == kk + 1) {
+            const double nv = v[0];
+            if (!(nv >= 2.2250738585072014e-308 && nv <= 1.7976931348623157e308)) s_fail = 1;
+            s_d[kk + 1] = nv; s_rd[kk + 1] = uba_rcp(nv);
           }
         }
-        __syncthreads();
+        asm volatile("bar.sync 2, %0;" ::"n"(NLD) : "memory");
       }
-    }
-    // rows -> Cholesky factor in the shared-memory panel: R[i][c] = v / sqrt(d_i); the strict lower triangle of the D part
-    // receives R^T (row k = column k of R, contiguous: the backward substitution reads it without bank conflicts), the
-    // diagonal slot 1 / R[i][i]; rows >= m stay zero
-    BCR_MARK()
-    if (t < MP) s_rd[t] = t < m ? uba_rsqrt(s_d[t]) : 0.0;
-    __syncthreads();
-    if (prg < NG) {
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int i = 8 * prg + q;
-        const double r = i < m ? v[q] * s_rd[i] : 0.0;
-        if (pc >= MP) P[i * LDP + pc] = r;
-        else if (pc > i) { P[i * LDP + pc] = pc < m ? r : 0.0; if (pc < m) P[pc * LDP + i] = r; }
-        else if (pc == i) P[i * LDP + i] = s_rd[i];
+      BCR_MARK()
+      // rows -> Cholesky factor in the shared-memory panel: R[i][c] = P[i][c] / sqrt(d_i); the strict lower triangle of the D
+      // part receives R^T (row k = column k of R, contiguous: the backward substitution reads it without bank conflicts),
+      // the diagonal slot 1 / R[i][i]; rows >= m stay zero
+      if (t < MP) s_rd[t] = t < m ? uba_rsqrt(s_d[t]) : 0.0;
+      asm volatile("bar.sync 2, %0;" ::"n"(NLD) : "memory");
+      if (pc < NCOL) {
+#pragma unroll 1
+        for (int i = 0; i < MP; i++) {
+          const double isd = s_rd[i];
+          const double r = i < m ? P[i * LDP + pc] * isd : 0.0;
+          if (pc >= MP) P[i * LDP + pc] = r;
+          else if (pc > i) { P[i * LDP + pc] = pc < m ? r : 0.0; if (pc < m) P[pc * LDP + i] = r; }
+          else if (pc == i) P[i * LDP + i] = isd;
+        }
       }
     }
     __syncthreads();
@@ -3085,29 +3094,44 @@ __global__ void __launch_bounds__(256) k_chol_bcr(DevView V, int w, int beta) {
     // Schur updates of the neighbours (FP64 MMA): tiles of W_a^T W_a, W_b^T W_b, W_b^T W_a over K = rows of the panel
     if (has_a || has_b) {
       const int frow = lane >> 2, fk = lane & 3;
-      for (int tile = warp; tile < 3 * TT * TT; tile += 8) {
-        const int which = tile / (TT * TT), ij = tile - which * TT * TT, I = ij / TT, J = ij - I * TT;
-        if ((which == 0 && !has_a) || (which == 1 && !has_b) || (which == 2 && !(has_a && has_b))) continue;
-        const int cx = (which == 0 ? MP : 2 * MP) + 8 * I, cy = (which == 1 ? 2 * MP : MP) + 8 * J;
-        double c0 = 0.0, c1 = 0.0;
+      constexpr int NTILE = 3 * TT * TT, TPWB = (NTILE + 7) / 8;
+      int cx[TPWB], cy[TPWB], wh[TPWB];
+      double c0[TPWB], c1[TPWB];
 #pragma unroll
-        for (int ks = 0; ks < MP / 4; ks++) {
-          const double av = P[(4 * ks + fk) * LDP + cx + frow];
-          const double bv = P[(4 * ks + fk) * LDP + cy + frow];
-          dmma884(c0, c1, av, bv);
-        }
-        const int oi = 8 * I + frow, oj = 8 * J + 2 * fk;
-        if (which == 0) { atomicAdd(&Dg(a)[oi * MP + oj], -c0); atomicAdd(&Dg(a)[oi * MP + oj + 1], -c1); }
-        else if (which == 1) { atomicAdd(&Dg(b)[oi * MP + oj], -c0); atomicAdd(&Dg(b)[oi * MP + oj + 1], -c1); }
-        else { Cg(a)[oi * MP + oj] = -c0; Cg(a)[oi * MP + oj + 1] = -c1; }       // A_ba: rows of b, columns of a
+      for (int q = 0; q < TPWB; q++) {
+        const int tile = warp + 8 * q;
+        const int which = tile / (TT * TT), ij = tile - which * TT * TT, I = ij / TT, J = ij - I * TT;
+        const bool on = tile < NTILE && !((which == 0 && !has_a) || (which == 1 && !has_b) || (which == 2 && !(has_a && has_b)));
+        wh[q] = on ? which : -1;
+        cx[q] = (which == 0 ? MP : 2 * MP) + 8 * I + frow; cy[q] = (which == 1 ? 2 * MP : MP) + 8 * J + frow;
+        if (!on) { cx[q] = MP + frow; cy[q] = MP + frow; }
+        c0[q] = 0.0; c1[q] = 0.0;
       }
-      if (t < 2 * MP) {
-        const int side = t / MP, i = t - side * MP;
-        if ((side == 0 && has_a) || (side == 1 && has_b)) {
-          double acc = 0.0;
-          for (int k = 0; k < m; k++) acc = fma(P[k * LDP + (1 + side) * MP + i], P[k * LDP + 3 * MP], acc);
-          atomicAdd(&rg(side == 0 ? a : b)[i], -acc);
+#pragma unroll 1
+      for (int ks = 0; ks < MP / 4; ks++) {
+        const double* Pk = P + (4 * ks + fk) * LDP;
+#pragma unroll
+        for (int q = 0; q < TPWB; q++) dmma884(c0[q], c1[q], Pk[cx[q]], Pk[cy[q]]);
+      }
+#pragma unroll
+      for (int q = 0; q < TPWB; q++) {
+        if (wh[q] < 0) continue;
+        const int oi = cx[q] - (wh[q] == 0 ? MP : 2 * MP), oj = cy[q] - frow - (wh[q] == 1 ? 2 * MP : MP) + 2 * fk;
+        if (wh[q] == 0) { atomicAdd(&Dg(a)[oi * MP + oj], -c0[q]); atomicAdd(&Dg(a)[oi * MP + oj + 1], -c1[q]); }
+        else if (wh[q] == 1) { atomicAdd(&Dg(b)[oi * MP + oj], -c0[q]); atomicAdd(&Dg(b)[oi * MP + oj + 1], -c1[q]); }
+        else { Cg(a)[oi * MP + oj] = -c0[q]; Cg(a)[oi * MP + oj + 1] = -c1[q]; }   // A_ba: rows of b, columns of a
+      }
+      // r_a -= W_a^T z, r_b -= W_b^T z: four partial sums per entry
+      {
+        const int e = t >> 2, part = t & 3;       // entry e of [r_a | r_b], quarter of the rows
+        const int side = e / MP, i = e - side * MP;
+        double acc = 0.0;
+        if (e < 2 * MP) {
+#pragma unroll
+          for (int kk = 0; kk < MP / 4; kk++) { const int kr = part + 4 * kk; acc = fma(P[kr * LDP + (1 + side) * MP + i], P[kr * LDP + 3 * MP], acc); }
         }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (part == 0 && e < 2 * MP && ((side == 0 && has_a) || (side == 1 && has_b))) atomicAdd(&rg(side == 0 ? a : b)[i], -acc);
       }
     }
     __syncthreads();
@@ -3146,10 +3170,11 @@ __global__ void __launch_bounds__(256) k_chol_bcr(DevView V, int w, int beta) {
     __syncthreads();
     if (warp == 0) {
       double y = lane < MP ? s_rd[lane] : 0.0;
+#pragma unroll 1
       for (int k = m - 1; k >= 0; k--) {
-        const double xk = __shfl_sync(0xffffffffu, y, k) * P[k * LDP + k];      // diagonal slot = 1 / R[k][k]
-        if (lane == k) y = xk;
-        else if (lane < k) y = fma(-P[k * LDP + lane], xk, y);                  // row k of the lower triangle = column k of R
+        const double l = lane < k ? P[k * LDP + lane] : 0.0;                      // row k of the lower triangle = column k of R
+        const double xk = __shfl_sync(0xffffffffu, y, k) * P[k * LDP + k];        // diagonal slot = 1 / R[k][k]
+        y = lane == k ? xk : fma(-l, xk, y);
       }
       if (lane < MP) {
         xg(j)[lane] = y;
