@@ -4,21 +4,28 @@
 // and bench.py's cpu_baseline / --impl reference legs may load it.  The product
 // (libuba) never links, loads or calls anything in this directory.
 //
-// PARITY UNPINNED: the reference (abeauvisage/uasl_motion_estimation) ships no tests,
-// fixtures or golden vectors for this path, and its arithmetic lives in Ceres Solver,
-// an un-vendored and un-versioned third-party dependency ("Ceres 1.12 minimum",
-// reference README.md:8; find_package(Ceres QUIET ...), CMakeLists.txt:12) that is not
-// installed here, as are OpenCV-C++ and glog, so the reference's own code cannot be
-// compiled in this container either.  This file therefore RESTATES:
-//   * the reference's residual functors, evaluated like the reference does — through
-//     forward-mode dual numbers (the role ceres::Jet<double,9> plays for
-//     AutoDiffCostFunction<.,M,6,3>, BundleAdjuster.h:97-102,:133-138,:174-179);
-//   * the published Ceres algorithms those functors and ceres::Solve rely on
-//     ([CERES-UPSTREAM], recalled, not verifiable here): AngleAxisRotatePoint, the
-//     Huber/Cauchy loss + corrector, Jacobi column scaling, the Levenberg–Marquardt
-//     trust-region strategy, Schur elimination of the point blocks, the monotonic
-//     trust-region minimiser's accept/reject/termination rules, bound projection.
-// It is anchored on the reference's own call sites (cited per function below).
+// PINNING.  The reference (abeauvisage/uasl_motion_estimation) ships no tests, fixtures or golden vectors for this
+// path, and its solver arithmetic lives in Ceres Solver, an un-vendored and un-versioned third-party dependency
+// ("Ceres 1.12 minimum", reference README.md:8; find_package(Ceres QUIET ...), CMakeLists.txt:12) that is not installed
+// here (nor are OpenCV-C++ and glog).  What pins this file all the same:
+//   * PINNED BY THE REFERENCE'S OWN TEXT: oracle/_ref/libuba_ref.so is the reference's BundleAdjuster.h,
+//     rotation_utils.cpp and StereoVisualOdometry.cpp compiled where they lie (oracle/Makefile, oracle/ref_shim.cpp)
+//     against the minimal Ceres / OpenCV stand-ins of oracle/refstub.  tests/test_ref_pin.py holds this file to it:
+//     residual rows and autodiff Jacobians of the three functors bit for bit, log / exp map, the observation table of
+//     initialiseObservations, parameter packing, bounds / fixed cameras / options / Status of optimise() with the reference
+//     class run end to end (its ceres::Solve being refstub's independent dense restatement) to 1e-12; the committed
+//     fixture tests/golden/ref_golden.json carries the same outputs to the GPU box.
+//   * STILL RECALLED, NOT PINNED ([CERES-UPSTREAM]): the published Ceres algorithms behind ceres::Solve — the Huber /
+//     Cauchy corrector, Jacobi column scaling, the Levenberg-Marquardt trust-region strategy and its accept / reject /
+//     termination rules, bound projection.  Real Ceres cannot run here; two independent restatements (this file: per
+//     point through the Schur complement; refstub: dense normal equations) agreeing to 1e-12 guard against slips, not
+//     against a shared misreading of Ceres.  DESIGN.md section 5 says so.
+// This file RESTATES
+//   * the reference's residual functors, evaluated like the reference does — through forward-mode dual numbers (the role
+//     ceres::Jet<double,9> plays for AutoDiffCostFunction<.,M,6,3>, BundleAdjuster.h:97-102,:133-138,:174-179);
+//   * AngleAxisRotatePoint, the loss functions + corrector, Jacobi scaling, the LM strategy, Schur elimination of the
+//     point blocks, the monotonic trust-region minimiser's rules, bound projection;
+// anchored on the reference's own call sites (cited per function below).
 //
 // Plain C++17, fp64 only, no dependencies.  Optional OpenMP (compile with -fopenmp).
 

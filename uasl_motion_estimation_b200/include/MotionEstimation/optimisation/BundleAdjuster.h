@@ -17,6 +17,9 @@
  *     window, :370-371); an offending window ends in Status::FAILED;
  *   - log_map_Quat's acos argument is clamped to [-1, 1] (rotation_utils.h:203 yields NaN for w > 1);
  *   - glog is not initialised (nothing logs through it any more);
+ *   - every point carries bounds (:455-460), so Ceres runs a projected Armijo line search after each trust-region step;
+ *     libuba clamps the full step to the box and accepts or rejects it: results differ from a Ceres run only on steps
+ *     whose clamped full step fails sufficient decrease (none on the benchmark windows);
  *   - getPosesCovariance() (CalibrationParameters::compute_cov) returns the 6x6 blocks of the inverse
  *     undamped reduced camera matrix, i.e. the camera blocks of (J^T J)^-1 that ceres::Covariance
  *     computes (:502-512); fixed cameras get a zero 6x6 block instead of Ceres' refusal; on failure the
