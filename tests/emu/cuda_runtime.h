@@ -49,6 +49,11 @@ inline cudaError_t cudaStreamQuery(cudaStream_t) { return 0; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
+constexpr int cudaEventDisableTiming = 2;
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = 0; return 0; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, int, int) { *s = nullptr; return 0; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = nullptr; return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return 0; }

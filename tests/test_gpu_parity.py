@@ -75,6 +75,7 @@ def test_reference_termination_rules(gpu_lib, oracle):
 _SOLVER_ENVS = {
     "cluster2": {},                                          # default: two-sided band Cholesky on a 2-CTA cluster
     "lookahead": {"UBA_BAND_C2": "0"},                       # one CTA, panel-warp lookahead
+    "pipelined": {"UBA_PIPE_SOLVE": "1"},                    # the cluster solver running under the lineariser (experimental)
     "bcr8": {"UBA_BAND_BCR": "8"},                           # block cyclic reduction on a cluster of 8 CTAs (experimental)
     "bcr16": {"UBA_BAND_BCR": "16"},                         # ... of 16 CTAs (non-portable cluster size)
     "bcr3": {"UBA_BAND_BCR": "3"},                           # ... of 3 (uneven deal of the eliminations)

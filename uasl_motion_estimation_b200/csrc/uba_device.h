@@ -109,6 +109,13 @@ struct DevView {
   const uint32_t* pt_mask;    // [NP] bit s: the point observes slot s of its part's list (0: not a tile point)
   const int32_t* gen_pts;     // [n_gen] internal point slots handled by the generic lineariser
   int32_t n_gen;
+  // pipelined solve (single banded window on one GPU): the band solver runs UNDER the lineariser.  A part's CTA counts itself
+  // done for each of its cameras; whoever completes a camera assembles that camera's rows of the reduced system and raises
+  // its flag; the solver waits on the flags of the rows it loads.
+  int32_t pipe_on;
+  const int32_t* cam_expect;  // [NC] parts whose camera list holds the camera
+  int32_t* cam_done;          // [NC] parts that have flushed (zeroed per iteration)
+  int32_t* row_ready;         // [free cameras] rows 6 f .. 6 f + 5 of the band and the rhs are assembled (zeroed per iteration)
   WinState* ws;               // [nW]
   IterRec* recs;              // [nW][rec_stride]
   int32_t rec_stride;
@@ -170,7 +177,8 @@ int launch_lin_tiled(const DevView& V, const int* variant_off, cudaStream_t st);
 int lin_part_variant(int n_local, int n_free_local, bool slot_kernel);
 int launch_assemble(const DevView& V, int max_n, cudaStream_t st);
 // h_win_n: host array [nW] of reduced-system sizes (6 * free cameras); h_win_beta: [nW] banded half-bandwidth or 0
-int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st, bool keep_factor = false);
+// parts: 3 = factorisation + epilogue (default), 1 = factorisation only, 2 = epilogue only
+int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st, bool keep_factor = false, int parts = 3);
 constexpr int kBandMaxBeta = 63;
 int solve_small_limit();
 int launch_backsub(const DevView& V, cudaStream_t st);

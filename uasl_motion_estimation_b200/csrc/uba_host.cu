@@ -210,6 +210,12 @@ struct uba_handle {
   DevBuf<int32_t> d_tr_tmp;                   // per-advance index tables
   DevBuf<unsigned char> d_tr_cid;
   DevBuf<double> d_fresh;                     // new rows / new points of an advance
+  // pipelined solve: the band solver of a single large window runs under the lineariser (see DevView::pipe_on)
+  bool pipe_on = false;
+  cudaStream_t stream2 = nullptr;             // the solver's branch of the iteration
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<int32_t> cam_expect_h;
+  DevBuf<int32_t> d_cam_expect, d_pipe;       // d_pipe: [cam_done NC | row_ready n_free], zeroed per iteration
   bool host_obs_valid = true;                 // obs_order / h_obs_internal / h_obs_cam describe the resident window
   bool host_iter_pending = false;             // a device -> host copy into h_pts is still in flight on the stream
   // timing
@@ -429,10 +435,24 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
       h->parts_h.push_back(p);
     }
   }
-  // one launch per kernel variant: parts grouped by variant
+  // one launch per kernel variant: parts grouped by variant; inside a variant the parts of a single window go from BOTH ENDS
+  // of the window towards its middle (CTAs are dispatched in this order), which is the order in which the two-sided band
+  // solver consumes the rows of the reduced system when it runs under the lineariser
   const bool slot = h->use_slot;
   auto variant = [slot](const TilePart& a) { return lin_part_variant(a.n_local, a.n_local - a.n_fixed, slot); };
-  std::stable_sort(h->parts_h.begin(), h->parts_h.end(), [&](const TilePart& a, const TilePart& b) { return variant(a) < variant(b); });
+  const int ncw = h->nW == 1 ? h->NC : 0;
+  auto end_dist = [&](const TilePart& a) {
+    if (!ncw) return 0;
+    const int first = h->tile_cams_h[a.cam_list_off], last = h->tile_cams_h[a.cam_list_off + a.n_local - 1];
+    return std::min(first, ncw - 1 - last);
+  };
+  std::stable_sort(h->parts_h.begin(), h->parts_h.end(), [&](const TilePart& a, const TilePart& b) {
+    const int va = variant(a), vb = variant(b);
+    return va != vb ? va < vb : end_dist(a) < end_dist(b);
+  });
+  h->cam_expect_h.assign(h->NC, 0);
+  for (const TilePart& p : h->parts_h)
+    for (int q = 0; q < p.n_local; q++) h->cam_expect_h[h->w_cam_off[p.window] + h->tile_cams_h[p.cam_list_off + q]]++;
   for (int v = 0; v <= kLinVariants; v++) h->variant_off[v] = 0;
   for (const TilePart& p : h->parts_h) h->variant_off[variant(p) + 1]++;
   for (int v = 0; v < kLinVariants; v++) h->variant_off[v + 1] += h->variant_off[v];
@@ -604,9 +624,35 @@ int prepare(uba_handle* h, int fixed_frames) {
     if (h->NP) CU(h, cudaMemcpyAsync(h->d_pt_mask.p, h->pt_mask_h.data(), sizeof(uint32_t) * h->NP, cudaMemcpyHostToDevice, h->stream));
     if (!h->gen_pts_h.empty()) CU(h, cudaMemcpyAsync(h->d_gen_pts.p, h->gen_pts_h.data(), sizeof(int32_t) * h->gen_pts_h.size(), cudaMemcpyHostToDevice, h->stream));
   }
+  // pipelined solve (UBA_PIPE_SOLVE=1, experimental): one banded window on this GPU alone, every observed point in a slot part,
+  // the two-sided cluster solver.  Correct (the parity suite passes with it) but not a win as the lineariser is scheduled
+  // today: its first wave of ~300 parts runs for ~100 us and ends almost at once, so the rows at the two ends of the window —
+  // the first ones the solver needs — are complete only 20-30 us before the whole pass is (scripts/pipe_timing.py), while the
+  // completion hooks cost the lineariser 20 us: c4 0.42 ms per iteration against 0.32 ms.  It needs parts that complete
+  // progressively from the ends (much smaller parts, hence a much cheaper flush) to pay.
+  {
+    static const bool want = [] { const char* e = getenv("UBA_PIPE_SOLVE"); return e && e[0] == '1'; }();
+    static const bool c2_on = [] { const char* e = getenv("UBA_BAND_C2"); const char* b = getenv("UBA_BAND_BCR"); return !(e && e[0] == '0') && !(b && atoi(b) > 0); }();
+    bool ok = want && c2_on && nW == 1 && !h->comm && h->use_tile && h->use_slot && h->gen_pts_h.empty() && !h->parts_h.empty() &&
+              h->variant_off[2] == h->variant_off[kLinVariants];      // slot parts only
+    if (ok) {
+      const int beta = h->win_beta[0], n = h->win_n[0];
+      ok = beta >= 11 && beta <= 35 && n >= 12 * (beta + 1);
+    }
+#ifdef UBA_EMU
+    ok = false;
+#endif
+    h->pipe_on = ok;
+    if (ok) {
+      CU(h, h->d_cam_expect.reserve(NC)); CU(h, h->d_pipe.reserve((size_t)NC + nfree + 1));
+      CU(h, cudaMemcpyAsync(h->d_cam_expect.p, h->cam_expect_h.data(), sizeof(int32_t) * NC, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
   CU(h, cudaStreamSynchronize(h->stream));
   TT("prepare: h2d + sync")
   DevView& V = h->V;
+  V.pipe_on = 0;                               // switched on in the copies the pipelined launches get (run_iteration)
+  V.cam_expect = h->d_cam_expect.p; V.cam_done = h->d_pipe.p; V.row_ready = h->d_pipe.p ? h->d_pipe.p + NC : nullptr;
   V.tile_threads = h->tile_threads;
   V.parts = h->d_parts.p; V.n_parts = h->use_tile ? (int)h->parts_h.size() : 0; V.tile_cams = h->d_tile_cams.p; V.pt_mask = h->d_pt_mask.p;
   V.gen_pts = h->d_gen_pts.p; V.n_gen = h->use_tile ? (int)h->gen_pts_h.size() : 0;
@@ -628,7 +674,7 @@ int prepare(uba_handle* h, int fixed_frames) {
     auto put = [&](const void* ptr, size_t n) { const char* c = (const char*)ptr; sig.insert(sig.end(), c, c + n); };
     put(h->variant_off, sizeof(h->variant_off)); put(&h->max_n, sizeof(h->max_n));
     put(&h->acc_total, sizeof(h->acc_total)); put(&h->use_tile, sizeof(h->use_tile)); put(&h->use_slot, sizeof(h->use_slot));
-    put(&h->peer_on, sizeof(h->peer_on));
+    put(&h->peer_on, sizeof(h->peer_on)); put(&h->pipe_on, sizeof(h->pipe_on));
     if (nW) { put(h->win_n.data(), sizeof(int) * nW); put(h->win_beta.data(), sizeof(int) * nW); }
     if (sig != h->graph_sig) { drop_graph(h); h->graph_sig.swap(sig); }
   }
@@ -834,13 +880,10 @@ int launch_linearizers(uba_handle* h, const DebugOut& dbg) {
 }
 
 // the linearise + Schur pass (the roofline kernel of the hot path)
+int zero_accumulators(uba_handle* h);
+
 int run_linearize(uba_handle* h, const DebugOut& dbg) {
-  // zero what this pass accumulates into: for banded windows only the band of the Schur accumulator is ever touched
-  if (!h->dense_override && h->zero_ranges.size() <= 4) {
-    for (const auto& r : h->zero_ranges) CU(h, cudaMemsetAsync(h->d_acc.p + r.first, 0, r.second * sizeof(double), h->stream));
-  } else {
-    CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
-  }
+  { const int rcz = zero_accumulators(h); if (rcz) return rcz; }
   PhaseTimer t(h, 0);
   h->timing.kernel_launches += launch_linearizers(h, dbg);
   h->timing.linearize_launches++;
@@ -867,11 +910,42 @@ int run_linearize(uba_handle* h, const DebugOut& dbg) {
   return UBA_OK;
 }
 
+// the zeroing every linearisation starts with
+int zero_accumulators(uba_handle* h) {
+  // for banded windows only the band of the Schur accumulator is ever touched
+  if (!h->dense_override && h->zero_ranges.size() <= 4) {
+    for (const auto& r : h->zero_ranges) CU(h, cudaMemsetAsync(h->d_acc.p + r.first, 0, r.second * sizeof(double), h->stream));
+  } else {
+    CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
+  }
+  return UBA_OK;
+}
+
 int run_iteration(uba_handle* h) {
   DebugOut none{};
-  int rc = run_linearize(h, none);
-  if (rc) return rc;
+  int rc;
+#ifndef UBA_EMU
+  if (h->pipe_on && !h->profiling && !h->dense_override) {
+    // Pipelined: [zero] -> { band solver (launched FIRST, so that its two CTAs are resident) | lineariser, whose CTAs
+    // assemble the reduced system camera by camera and raise the row flags the solver waits on } -> epilogue ...
+    rc = zero_accumulators(h);
+    if (rc) return rc;
+    CU(h, cudaMemsetAsync(h->d_pipe.p, 0, sizeof(int32_t) * ((size_t)h->NC + h->free_list_h.size()), h->stream));
+    DevView Vp = h->V; Vp.pipe_on = 1;
+    DevView Vcp = h->Vc; Vcp.pipe_on = 1;
+    CU(h, cudaEventRecord(h->ev_fork, h->stream));
+    CU(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    h->timing.kernel_launches += launch_solve(Vcp, h->win_n.data(), h->win_beta.data(), solve_small_limit(), h->stream2, false, 1);
+    h->timing.kernel_launches += launch_lin_tiled(Vp, h->variant_off, h->stream);
+    h->timing.linearize_launches++;
+    CU(h, cudaEventRecord(h->ev_join, h->stream2));
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    h->timing.kernel_launches += launch_solve(h->Vc, h->win_n.data(), h->win_beta.data(), solve_small_limit(), h->stream, false, 2);
+  } else
+#endif
   {
+    rc = run_linearize(h, none);
+    if (rc) return rc;
     PhaseTimer t(h, 1);
     h->timing.kernel_launches += launch_assemble(h->Vc, h->max_n, h->stream);
     h->timing.kernel_launches += launch_solve(h->Vc, h->win_n.data(), h->win_beta.data(), solve_small_limit(), h->stream);
@@ -1405,6 +1479,14 @@ int uba_create(const uba_config* cfg, uba_handle** out) {
   h->cfg = c; h->device = c.device;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(nullptr, UBA_ERR_CUDA, "cudaStreamCreate failed"); }
   for (auto& ev : h->ev) cudaEventCreate(&ev);
+  {
+    // the solver's branch gets the highest priority: its two CTAs must become resident while the lineariser's grid is
+    // still queueing for the same SMs
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+  }
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
   *out = h;
   return UBA_OK;
 }
@@ -1428,6 +1510,10 @@ void uba_destroy(uba_handle* h) {
   h->d_cam_win.release(); h->d_pt_obs_off.release(); h->d_pt_win.release(); h->d_obs_cam.release(); h->d_obs_src.release(); h->d_n_active.release();
   h->d_pt_order.release(); h->d_w_red_off.release(); h->d_ws.release(); h->d_recs.release();
   for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  h->d_cam_expect.release(); h->d_pipe.release();
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1954,8 +2040,11 @@ int uba_time_linearize(uba_handle* h, int fixed_frames, double radius, int repea
   for (int r = 0; r < repeats; r++) {
     if (do_flush) { rc = flush_l2(h); if (rc) return rc; }
     CU(h, cudaMemsetAsync(h->d_acc.p, 0, h->acc_total * sizeof(double), h->stream));
+    const bool pipe = h->pipe_on && !h->dense_override;    // the pass as the pipelined iteration runs it: with its assembly hooks
+    if (pipe) CU(h, cudaMemsetAsync(h->d_pipe.p, 0, sizeof(int32_t) * ((size_t)h->NC + h->free_list_h.size()), h->stream));
     cudaEventRecord(h->ev[4], h->stream);
-    h->timing.kernel_launches += launch_linearizers(h, none);
+    if (pipe) { DevView Vp = h->V; Vp.pipe_on = 1; h->timing.kernel_launches += launch_lin_tiled(Vp, h->variant_off, h->stream); }
+    else h->timing.kernel_launches += launch_linearizers(h, none);
     h->timing.linearize_launches++;
     cudaEventRecord(h->ev[5], h->stream);
     CU(h, cudaEventSynchronize(h->ev[5]));

@@ -1141,6 +1141,7 @@ __global__ void __launch_bounds__(NT, NT == 128 ? UBA_T2_MINBLOCKS : 1) k_lin_ti
 // Features and points of the next chunk arrive through cp.async into per-lane staging slots ([value][thread]).
 // Handles parts with up to kSlotMaxLocal local cameras (c4, c5: 5; c1, c3: 10); wider parts go to k_lin_wide.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cam_damping(const DevView& V, const WinState* st, int gc, int r, double d, bool store);
 #ifndef UBA_EMU
 constexpr int kSlotLdz = t2_ldz(32);              // 100: K = 96 columns per chunk of 32 points
 constexpr int kSlotStageD = 7;                    // staged doubles per lane and buffer: point (3) + features (<= 4)
@@ -1583,6 +1584,55 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
   }
   cost = warp_sum(cost);
   if (lane == 0 && cost != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_COST], cost);
+  // ---- pipelined solve: count this part done for each of its cameras; the part that completes a camera assembles the
+  //      camera's six rows of the damped band  A = B + Lambda - S  and of  rhs = v - Z h  (what k_assemble does for the whole
+  //      matrix when the solve is not pipelined) and raises the rows' flag for the band solver, which is already running ------
+  if (V.pipe_on) {
+    __shared__ int s_last[NLMAX];
+    __threadfence();                            // my atomics are performed before the counters move
+    named_bar<3>(nslot);
+    if (t < nl) {
+      const int gc = s_gc[t];
+      const int old = atomicAdd(&V.cam_done[gc], 1);
+      s_last[t] = (old + 1 == V.cam_expect[gc] && s_free[t] >= 0) ? 1 : 0;
+    }
+    named_bar<3>(nslot);
+    const int bw1 = sbeta + 1;
+    double* Ab = V.A + V.w_red_off[w] + (size_t)2 * n * bw1;
+    double* rhs = V.rhs + (size_t)6 * V.w_free_off[w];
+    for (int a = 0; a < nl; a++) {
+      if (!s_last[a]) continue;                 // (uniform over the CTA)
+      __threadfence();                          // acquire side: everybody else's sums for this camera are in L2
+      const int gc = s_gc[a], f = s_free[a];
+      double gm = 0.0;
+      for (int e = t; e < 6 * bw1; e += nslot) {
+        const int r = e / bw1, c = e - r * bw1;
+        const int i = 6 * f + r, k = i - sbeta + c;
+        double val = 0.0;
+        if (k >= 0) {
+          const int fk = k / 6, ck = k - 6 * fk;
+          if (fk == f) {
+            const int rr = ck < r ? ck : r, cc = ck < r ? r : ck;
+            const double b = __ldcg(&V.Bacc[(size_t)gc * 36 + rr * 6 + cc]);
+            val = b - __ldcg(&S[sacc_index(n, sbeta, 6 * f + rr, 6 * f + cc)]);
+            if (rr == cc) val += cam_damping(V, st, gc, r, b, true);
+          } else {
+            val = -__ldcg(&S[sacc_index(n, sbeta, k, i)]);
+          }
+        }
+        Ab[(size_t)i * bw1 + c] = val;
+      }
+      if (t < 6) {
+        const double v = __ldcg(&V.vacc[(size_t)gc * 6 + t]);
+        rhs[6 * f + t] = v - __ldcg(&V.zh[(size_t)gc * 6 + t]);
+        gm = fabs(v);
+      }
+      if (t < 32) { gm = warp_max(gm); if (t == 0 && gm > 0.0) atomic_max_nonneg(&V.w_max[w], gm); }
+      __threadfence();
+      named_bar<3>(nslot);
+      if (t == 0) *(volatile int32_t*)&V.row_ready[f] = 1;
+    }
+  }
 }
 
 // One kernel per slot-count class (blockDim = 32 (NLMAX + 1)); parts are grouped by class on the host.  168 registers:
@@ -1596,7 +1646,13 @@ __global__ void __maxnreg__(UBA_SLOT_MAXNREG) k_lin_slot(DevView V, int first) {
   extern __shared__ double sm[];
   const TilePart part = V.parts[first + blockIdx.x];
   if (V.ws[part.window].done) return;
+#ifdef UBA_BAND_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < 1000) { long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); V.Zbuf[100 + blockIdx.x] = (double)(g_ % 1000000000ll); }
+#endif
   slot_part<M, NLMAX>(V, part, sm);
+#ifdef UBA_BAND_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < 1000) { long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); V.Zbuf[1100 + blockIdx.x] = (double)(g_ % 1000000000ll); }
+#endif
 }
 #endif  // !UBA_EMU
 
@@ -2458,12 +2514,13 @@ __host__ __device__ constexpr size_t c2_backward_doubles(int beta) {
   return (size_t)(kC2ChunkBlocks + (beta + 6) / 6 + 1) * 6 * (beta + 1) + (size_t)kC2ChunkBlocks * ((beta + 6) / 6 + 1) * 36;
 }
 
-template <int PER>
+template <int PER, bool PIPE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c2(DevView V, int w, int beta) {
   extern __shared__ double sm[];
   const WinState* st = &V.ws[w];
   if (st->done) return;
   constexpr int NH = 256, NWORKH = 224;
+  constexpr int kPollThread = 200;              // a worker without side duties (pipelined solve: polls the row flags)
   const int half = (int)(blockIdx.x & 1);
   const int f0 = V.w_free_off[w];
   const int n = 6 * (V.w_free_off[w + 1] - f0);
@@ -2488,19 +2545,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   const bool panel = t >= NWORKH;
   const int pl = t - NWORKH;
 #ifdef UBA_BAND_TIMING
-  long long tph[8]; int nph = 0; long long busy = 0; long long bseg[3] = {0, 0, 0}; long long brole = 0; long long seg[6] = {0, 0, 0, 0, 0, 0}; long long tq = 0;
+  long long tph[8]; long long tgl[8]; int nph = 0; long long busy = 0; long long bseg[3] = {0, 0, 0}; long long brole = 0; long long seg[6] = {0, 0, 0, 0, 0, 0}; long long tq = 0;
 #define SG(i) { const long long now_ = clock64(); seg[i] += now_ - tq; tq = now_; }
-#define PH() { if (t == 0) tph[nph++] = clock64(); }
+#define PH() { if (t == 0) { tph[nph] = clock64(); long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); tgl[nph] = g_; nph++; } }
 #else
 #define PH()
 #endif
   PH()
   if (t == 0) s_fail = 0;
+  // Pipelined solve (V.pipe_on): the lineariser is still running; every row of the band (and of the rhs) is assembled by the
+  // lineariser CTA that completed its camera, which then raises row_ready[camera].  Whoever loads a row waits for its flag
+  // (bounded: a flag that never comes fails the solve instead of hanging the device) and reads through L2.
+  constexpr bool pipe = PIPE;                  // (a separate instantiation: the plain solve keeps its cached loads and up-front rhs)
+  auto wait_row = [&](int io) {
+    if (!pipe) return;
+    const volatile int32_t* fl = &V.row_ready[io / 6];
+    if (*fl == 0) {
+      long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      while (*fl == 0) {
+        __nanosleep(100);
+        long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ll) { s_fail = 1; break; }
+      }
+    }
+    __threadfence();
+  };
+  auto ab_load = [&](int io, int c) -> double { wait_row(io); return pipe ? __ldcg(&Ab[(size_t)io * bw1 + c]) : Ab[(size_t)io * bw1 + c]; };
+  auto rhs_load = [&](int io) -> double { wait_row(io); return pipe ? __ldcg(&rhs[io]) : rhs[io]; };
   auto band_entry = [&](int i, int c) -> double {
     if (i >= H.nh || i - beta + c < 0) return 0.0;
-    return H.dir == 0 ? Ab[(size_t)i * bw1 + c] : Ab[(size_t)(n - 1 - i + beta - c) * bw1 + c];
+    return H.dir == 0 ? ab_load(i, c) : ab_load(n - 1 - i + beta - c, c);
   };
-  for (int i = t; i < ylen; i += NH) y[i] = i < H.nh ? rhs[H.dir == 0 ? i : n - 1 - i] : 0.0;
+  // the rhs rows travel with the band rows: the first kBandRing now, six more with every ring refill
+  for (int i = t; i < ylen; i += NH) y[i] = (i < H.nh && (!pipe || i < kBandRing)) ? rhs_load(H.dir == 0 ? i : n - 1 - i) : 0.0;
   // global -> shared staging in batches of 8 independent loads per thread: a plain `dst[e] = src[e]` loop is compiled as one
   // load-store pair after the other (shared stores may alias generic loads), i.e. one memory round trip per element
   {
@@ -2514,6 +2591,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
     }
   }
   for (int i = t; i < 40 * XS; i += NH) Xbuf[i] = 0.0;
+  if (pipe && t == kPollThread && kBandRing < H.nh) wait_row(H.dir == 0 ? kBandRing : n - 1 - (kBandRing + 5));   // rows entering at step 0
   // trailing update W -= X X^T on the FP64 tensor-core path: 8x8 tiles (I >= J) of the beta x beta window, dealt to
   // the 7 worker warps; the X fragments of a tile are 4 shared-memory loads per lane instead of 12 per scalar pair
   constexpr int kTW = 3;                      // tiles per worker warp (15 tiles for beta = 35, 10 for beta = 29)
@@ -2606,10 +2684,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
       // Ring refill, every step: the 6 rows of the block that was eliminated in the previous step are dead; the rows 126
       // further down take their slots.  One entry per thread (6 (beta+1) <= 216), row / column of the entry fixed per
       // thread (no index arithmetic in the loop), loaded here and stored at the end of the step.
-      double pre = 0.0;
+      double pre = 0.0, prey = 0.0;
       if (rf_on) {
         const int i = c0 + kBandRing + rf_row;
-        if (i < H.nh) pre = H.dir == 0 ? Ab[(size_t)i * bw1 + rf_col] : Ab[(size_t)(n - 1 - i + beta - rf_col) * bw1 + rf_col];
+        if (i < H.nh) {                          // (pipelined: the previous step's poll made sure these rows are assembled)
+          const double* src = &Ab[(size_t)(H.dir == 0 ? i : n - 1 - i + beta - rf_col) * bw1 + rf_col];
+          pre = pipe ? __ldcg(src) : *src;
+          if (pipe && rf_col == 0) prey = __ldcg(&rhs[H.dir == 0 ? i : n - 1 - i]);
+        }
+      }
+      // pipelined: one worker polls the flag of the camera whose rows enter the ring at the NEXT step; the load is issued here
+      // and looked at only at the end of the step, so a flag that is already up costs nothing
+      int nxt_flag = 1;
+      const volatile int32_t* nxt_ptr = nullptr;
+      if (pipe && t == kPollThread) {
+        const int i1 = c0 + 6 + kBandRing + 5;   // last row entering at the next step
+        if (i1 - 5 < H.nh) {
+          const int cam = H.dir == 0 ? (i1 - 5) / 6 : (n - 1 - i1) / 6;
+          if (cam >= 0 && cam < n / 6) { nxt_ptr = &V.row_ready[cam]; nxt_flag = *nxt_ptr; }
+        }
       }
 #ifdef UBA_BAND_TIMING
       SG(0)
@@ -2691,7 +2784,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
 #ifdef UBA_BAND_TIMING
       SG(4)
 #endif
-      if (rf_on) ring[o0 + rf_row * bw1 + rf_col] = pre;   // slot of row c0 + rf_row, dead since the previous step
+      if (rf_on) {
+        ring[o0 + rf_row * bw1 + rf_col] = pre;   // slot of row c0 + rf_row, dead since the previous step
+        if (pipe && rf_col == 0 && c0 + kBandRing + rf_row < H.nh) y[c0 + kBandRing + rf_row] = prey;
+      }
+      if (nxt_ptr && nxt_flag == 0) {           // the lineariser has not finished that camera yet: wait here (bounded)
+        long long t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*nxt_ptr == 0) {
+          __nanosleep(200);
+          long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 2000000000ll) { s_fail = 1; break; }
+        }
+      }
+      if (nxt_ptr) __threadfence();
     }
 #ifdef UBA_BAND_TIMING
     if (!panel) SG(5)
@@ -2718,9 +2823,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
       if (b > a || a - b > beta) continue;
       const int it = ne0 + a, kt = ne0 + b;                          // top: local = original numbering
       const int ib = ne1 + (sw - 1 - b), kbm = ne1 + (sw - 1 - a);   // bottom (reversed): row >= col
-      ring[(it % kBandRing) * bw1 + (kt - it + beta)] += ring1[(ib % kBandRing) * bw1 + (kbm - ib + beta)] - Ab[(size_t)(m + a) * bw1 + (b - a + beta)];
+      ring[(it % kBandRing) * bw1 + (kt - it + beta)] += ring1[(ib % kBandRing) * bw1 + (kbm - ib + beta)] - ab_load(m + a, b - a + beta);
     }
-    for (int a = t; a < sw; a += NH) y[ne0 + a] += y1[ne1 + (sw - 1 - a)] - rhs[m + a];
+    for (int a = t; a < sw; a += NH) y[ne0 + a] += y1[ne1 + (sw - 1 - a)] - rhs_load(m + a);
     __syncthreads();
     if (t == NWORKH) {                        // factor of the first separator block
       const int ob = (ne0 % kBandRing) * bw1;
@@ -2899,7 +3004,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256) k_chol_banded_c
   __syncthreads();
   PH()
 #ifdef UBA_BAND_TIMING
-  if (t == 0) for (int q = 0; q < nph; q++) V.Zbuf[half * 8 + q] = (double)(tph[q] - tph[0]);
+  if (t == 0) for (int q = 0; q < nph; q++) { V.Zbuf[half * 8 + q] = (double)(tph[q] - tph[0]); V.Zbuf[64 + half * 8 + q] = (double)(tgl[q] % 1000000000ll); }
   if (half == 0 && (t & 31) == 0) V.Zbuf[16 + (t >> 5)] = (double)busy;
   if (half == 0 && t == 0) for (int q = 0; q < 3; q++) V.Zbuf[56 + q] = (double)bseg[q];
   if (half == 0 && (t == 0 || t == NWORKH - 32 || t == NWORKH)) V.Zbuf[59 + (t == 0 ? 0 : t == NWORKH ? 2 : 1)] = (double)brole;
@@ -3848,8 +3953,9 @@ int launch_assemble(const DevView& V, int max_n, cudaStream_t st) {
 
 int solve_small_limit() { return 160; }
 
-int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st, bool keep_factor) {
+int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, int max_small_n, cudaStream_t st, bool keep_factor, int parts) {
   int launches = 0;
+  if (parts & 1) {
   int small_max = 0, n_large = 0;
   for (int w = 0; w < V.nW; w++) {
     if (h_win_beta[w] > 0) n_large++;
@@ -3918,8 +4024,9 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
           const int sw = ((beta + 1 + 5) / 6) * 6, mm = (((n - sw) / 2) / 6) * 6;
           const size_t smem = ((size_t)kBandRing * (beta + 1) + (n - mm) + beta + 8 + (size_t)40 * 9 + 8 + c2_backward_doubles(beta) + 8) * sizeof(double);
           const int per = (beta * (beta + 1) / 2 + 223) / 224;
-#define UBA_C2_LAUNCH(PP) { cudaFuncSetAttribute(k_chol_banded_c2<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH(k_chol_banded_c2<PP>, 2, 256, smem, st, V, w, beta); }
-          if (per <= 2) UBA_C2_LAUNCH(2) else UBA_C2_LAUNCH(3)
+#define UBA_C2_LAUNCH(PP, PI) { cudaFuncSetAttribute(k_chol_banded_c2<PP, PI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); UBA_LAUNCH((k_chol_banded_c2<PP, PI>), 2, 256, smem, st, V, w, beta); }
+          if (V.pipe_on) { if (per <= 2) UBA_C2_LAUNCH(2, true) else UBA_C2_LAUNCH(3, true) }
+          else { if (per <= 2) UBA_C2_LAUNCH(2, false) else UBA_C2_LAUNCH(3, false) }
 #undef UBA_C2_LAUNCH
           launches++;
           continue;
@@ -3956,13 +4063,15 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
     }
   }
 #endif
-  {
+  }
+  if (parts & 2) {
     const int avg = (V.NC + V.nW - 1) / V.nW;          // any split is correct (grid-stride loop); this one suits uniform windows
     const int bs = avg <= 32 ? 32 : 64;
     int slices = (avg + bs - 1) / bs; if (slices > 16) slices = 16;
     UBA_LAUNCH(k_solve_epilogue, dim3(V.nW, slices), bs, 0, st, V);
+    launches++;
   }
-  return launches + 1;
+  return launches;
 }
 
 int launch_backsub(const DevView& V, cudaStream_t st) {
