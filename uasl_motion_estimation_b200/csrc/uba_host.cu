@@ -412,7 +412,13 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   // cameras, k_lin_wide beyond; linearizer = 2 (or UBA_LIN_SLOT=0) sends everything to k_lin_tile2.
   h->use_slot = h->cfg.linearizer != 2;
   if (const char* e = std::getenv("UBA_LIN_SLOT")) h->use_slot = std::atoi(e) != 0 && h->cfg.linearizer != 2;
-  auto slot_item = [&](const Item& it) { return h->use_slot && it.nl <= kSlotMaxLocal; };
+  // A window that needs k_lin_wide for some of its parts keeps it for all of them: the two kernels' CTAs (352 threads x 168
+  // registers, 256 x 255) cannot share an SM, so side by side they take turns with one CTA per SM each and two tails
+  // (measured on c2: 0.110 ms split against 0.089 ms all wide).
+  std::vector<char> win_wide(h->nW, 0);
+  for (const Item& it : items) if (it.nl > kSlotMaxLocal) win_wide[it.w] = 1;
+  if (const char* e = std::getenv("UBA_LIN_SPLIT")) { if (std::atoi(e) != 0) std::fill(win_wide.begin(), win_wide.end(), 0); }
+  auto slot_item = [&](const Item& it) { return h->use_slot && it.nl <= kSlotMaxLocal && !win_wide[it.w]; };
   // CTA size of the other kernels: k_lin_wide always has 256 threads; k_lin_tile2 128 (two CTAs per SM) when every item is
   // narrow, else 256
   int nt = h->use_slot ? 256 : 128;
@@ -432,6 +438,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     for (int b = it.begin; b < it.end; b += part_pts) {
       TilePart p{};
       p.window = it.w; p.pt_begin = b; p.pt_end = std::min(it.end, b + part_pts); p.cam_list_off = it.cam_off; p.n_local = it.nl; p.n_fixed = it.nfx;
+      p.pad_[0] = slot_item(it) ? 1 : 0;       // host-side note: this part goes to k_lin_slot
       h->parts_h.push_back(p);
     }
   }
@@ -439,7 +446,10 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   // of the window towards its middle (CTAs are dispatched in this order), which is the order in which the two-sided band
   // solver consumes the rows of the reduced system when it runs under the lineariser
   const bool slot = h->use_slot;
-  auto variant = [slot](const TilePart& a) { return lin_part_variant(a.n_local, a.n_local - a.n_fixed, slot); };
+  auto variant = [slot](const TilePart& a) {
+    const int v = lin_part_variant(a.n_local, a.n_local - a.n_fixed, slot);
+    return slot && v < 2 && !a.pad_[0] ? 7 : v;     // a narrow part of a window that stays with k_lin_wide
+  };
   const int ncw = h->nW == 1 ? h->NC : 0;
   auto end_dist = [&](const TilePart& a) {
     if (!ncw) return 0;
