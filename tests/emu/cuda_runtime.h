@@ -21,6 +21,8 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
+struct alignas(16) double2 { double x, y; };
+template <typename T> inline T __ldcs(const T* p) { return *p; }
 namespace uba_emu { extern thread_local dim3 t_threadIdx, t_blockIdx, t_blockDim, t_gridDim; }
 #define threadIdx uba_emu::t_threadIdx
 #define blockIdx uba_emu::t_blockIdx

@@ -1164,7 +1164,7 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 template <int ID>
 __device__ __forceinline__ void named_bar(int nthreads) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory"); }
 
-template <int M, int NLMAX>
+template <int M, int NLMAX, bool PIPE>
 __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part, double* sm) {
   const unsigned FULL = 0xffffffffu;
   const int nl = part.n_local, nfx = part.n_fixed, nlf = nl - nfx;
@@ -1587,7 +1587,7 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
   // ---- pipelined solve: count this part done for each of its cameras; the part that completes a camera assembles the
   //      camera's six rows of the damped band  A = B + Lambda - S  and of  rhs = v - Z h  (what k_assemble does for the whole
   //      matrix when the solve is not pipelined) and raises the rows' flag for the band solver, which is already running ------
-  if (V.pipe_on) {
+  if constexpr (PIPE) {                         // (its own instantiation: the hooks cost registers the plain pass needs)
     __shared__ int s_last[NLMAX];
     __threadfence();                            // my atomics are performed before the counters move
     named_bar<3>(nslot);
@@ -1641,7 +1641,7 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
 #ifndef UBA_SLOT_MAXNREG
 #define UBA_SLOT_MAXNREG 168
 #endif
-template <int M, int NLMAX>
+template <int M, int NLMAX, bool PIPE>
 __global__ void __maxnreg__(UBA_SLOT_MAXNREG) k_lin_slot(DevView V, int first) {
   extern __shared__ double sm[];
   const TilePart part = V.parts[first + blockIdx.x];
@@ -1649,7 +1649,7 @@ __global__ void __maxnreg__(UBA_SLOT_MAXNREG) k_lin_slot(DevView V, int first) {
 #ifdef UBA_BAND_TIMING
   if (threadIdx.x == 0 && blockIdx.x < 1000) { long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); V.Zbuf[100 + blockIdx.x] = (double)(g_ % 1000000000ll); }
 #endif
-  slot_part<M, NLMAX>(V, part, sm);
+  slot_part<M, NLMAX, PIPE>(V, part, sm);
 #ifdef UBA_BAND_TIMING
   if (threadIdx.x == 0 && blockIdx.x < 1000) { long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); V.Zbuf[1100 + blockIdx.x] = (double)(g_ % 1000000000ll); }
 #endif
@@ -3870,8 +3870,13 @@ static int launch_slot_variant(const DevView& V, int first, int count, cudaStrea
   if (count == 0) return 0;
   const size_t smem = slot_smem_bytes(NLMAX);
   static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(k_lin_slot<M, NLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-  UBA_LAUNCH((k_lin_slot<M, NLMAX>), count, 32 * (NLMAX + 1), smem, st, V, first);
+  if (!configured) {
+    cudaFuncSetAttribute(k_lin_slot<M, NLMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_lin_slot<M, NLMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  if (V.pipe_on) UBA_LAUNCH((k_lin_slot<M, NLMAX, true>), count, 32 * (NLMAX + 1), smem, st, V, first);
+  else UBA_LAUNCH((k_lin_slot<M, NLMAX, false>), count, 32 * (NLMAX + 1), smem, st, V, first);
   return 1;
 }
 #endif
