@@ -371,12 +371,15 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         h.comm_init(uid[0], rank, world)
 
+    # a batch caller owns its windows as one set of concatenated host arrays (what uba_set_batch takes): built once, here
+    batch = synth.concat_windows(wins) if len(wins) > 1 else None
+
     def set_problem():
-        if len(wins) == 1:
+        if batch is None:
             w = wins[0]
             h.set_problem(w.M, w.cams_init, w.pts_init, w.feats, w.cam_idx, w.pt_idx, w.cam_id, w.calib)
         else:
-            h.set_batch(**synth.concat_windows(wins))
+            h.set_batch(**batch)
 
     set_problem()
     if total_obs is None:  # c3: every rank holds the same number of windows

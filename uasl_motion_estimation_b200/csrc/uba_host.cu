@@ -22,6 +22,7 @@
 #include <iterator>
 #include <numeric>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/uba.h"
@@ -387,6 +388,25 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     }
     close_item(s1);
   }
+  // A handful of shorter tracks in front of (or behind) a long run of full ones — c4 has ~5 four-keyframe tracks per home
+  // keyframe — would cost a CTA and a flush of their own: an item of less than one chunk whose camera range lies inside its
+  // neighbour's joins it (the neighbour's camera list does not change; its masks simply have idle slots for those points).
+  if (h->cfg.linearizer != 2) {
+    std::vector<Item> kept;
+    kept.reserve(items.size());
+    auto covers = [](const Item& a, const Item& b) {
+      return a.w == b.w && a.range && b.range && a.ulo <= b.ulo && a.ulo + a.nl >= b.ulo + b.nl && 2 * b.nl >= a.nl;
+    };
+    for (size_t i = 0; i < items.size(); i++) {
+      const Item& cur = items[i];
+      if (cur.end - cur.begin < 32) {
+        if (i + 1 < items.size() && items[i + 1].begin == cur.end && covers(items[i + 1], cur)) { items[i + 1].begin = cur.begin; continue; }
+        if (!kept.empty() && kept.back().end == cur.begin && covers(kept.back(), cur)) { kept.back().end = cur.end; continue; }
+      }
+      kept.push_back(cur);
+    }
+    items.swap(kept);
+  }
   // slot masks of the tile points (bit i = the point sees the item's i-th camera), items in parallel
   const int n_items = (int)items.size();
 #pragma omp parallel for schedule(dynamic, 1)
@@ -431,7 +451,82 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   // parts: aim at a few CTAs per SM, never less than 2 chunks of points per CTA
   size_t target_parts = 2 * 148 * (256 / nt);
   if (const char* e = std::getenv("UBA_TILE_PARTS")) target_parts = (size_t)std::max(1, std::atoi(e));
+  // k_lin_slot parts are sized per class (up to 5 local cameras: two CTAs per SM; up to 10: one) by a model of the pass:
+  // a part costs its chunks of 32 points plus a fixed c0 (camera records, pipeline fill, flush: ~3 chunk times, fitted on
+  // c4 / c5 part-size sweeps, scripts/part_sweep.py), the CTAs are dispatched longest first onto the class's resident slots.
+  // Candidates: the largest item cut into 1..8 pieces and the ideal load of a slot, the pieces of an item evened out; the
+  // makespan of every candidate is simulated on the histogram of part sizes (list scheduling over groups of equally loaded
+  // slots), cheapest wins.  c3 (512 equal windows on 148 slots = 3.46 rounds) becomes 1024 half windows = 6.92 rounds;
+  // c4 (196 runs of ~33 chunks on 296 slots) becomes 588 parts of ~11 = 1.99 rounds.  "Full pieces + remainder" splits
+  // (e.g. 24 + 9 on c4, one round on paper) measure 15-20 % slower than the model says and are not proposed.
+  struct SlotSplit { int cap = 0; bool even = false; };
+  SlotSplit slot_split[2];
+  if (h->use_slot) {
+    static const double c0 = [] { const char* e = getenv("UBA_SLOT_C0"); return e ? atof(e) : 3.0; }();
+    static const int n_sm = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return std::max(n, 1); }();
+    for (int cls = 0; cls < 2; cls++) {
+      std::map<int, int> ihist;                 // item size in chunks -> items
+      long total = 0; int lmax = 0, nit = 0;
+      for (const Item& it : items) {
+        if (!slot_item(it) || (it.nl > 5) != (cls == 1)) continue;
+        const int ch = (it.end - it.begin + 31) / 32;
+        ihist[ch]++; total += ch; lmax = std::max(lmax, ch); nit++;
+      }
+      if (!nit) continue;
+      const int slots = n_sm * (cls == 0 ? 2 : 1);
+      auto pieces = [](int ch, int cap, bool even, auto&& emit) {       // emit(size, count) for one item of ch chunks
+        const int k = (ch + cap - 1) / cap;
+        if (even) { const int lo = ch / k, hi_n = ch % k; if (hi_n) emit(lo + 1, hi_n); emit(lo, k - hi_n); }
+        else { if (ch / cap) emit(cap, ch / cap); if (ch % cap) emit(ch % cap, 1); }
+      };
+      auto makespan = [&](int cap, bool even) {
+        std::map<int, long, std::greater<int>> phist;                   // part size -> parts, longest first
+        for (const auto& kv : ihist) pieces(kv.first, cap, even, [&](int sz, int n) { phist[sz] += (long)n * kv.second; });
+        std::map<double, long> load{{0.0, slots}};                      // slot load -> slots carrying it
+        for (const auto& kv : phist) {
+          long left = kv.second;
+          const double cost = kv.first + c0;
+          while (left > 0) {
+            auto lo = load.begin();
+            const double at = lo->first; const long n = std::min(left, lo->second);
+            if (n == lo->second) load.erase(lo); else lo->second -= n;
+            load[at + cost] += n; left -= n;
+          }
+        }
+        return load.rbegin()->first;
+      };
+      std::vector<int> caps;
+      for (int k = 1; k <= 8; k++) caps.push_back(std::max(1, (lmax + k - 1) / k));
+      const int ideal = (int)((total + (long)(c0 * nit) + slots - 1) / slots);
+      for (int c : {ideal, ideal + 1, (ideal + 1) / 2}) caps.push_back(std::max(1, c));
+      double best = 1e300;
+      for (int cap : caps) {
+        const double m = makespan(cap, true);
+        if (m < best - 1e-9) { best = m; slot_split[cls].cap = cap; slot_split[cls].even = true; }
+      }
+      if (const char* e = std::getenv("UBA_SLOT_CAP")) {       // experiments: "<chunks>" or "<chunks>e" (evened)
+        slot_split[cls].cap = std::max(1, std::atoi(e)); slot_split[cls].even = std::strchr(e, 'e') != nullptr;
+        best = makespan(slot_split[cls].cap, slot_split[cls].even);
+      }
+      if (getenv("UBA_TRACE")) fprintf(stderr, "  [trace] slot class %d: %d items, %ld chunks on %d slots -> parts of <= %d chunks (%s), modelled makespan %.1f chunk times\n",
+                                       cls, nit, total, slots, slot_split[cls].cap, slot_split[cls].even ? "evened" : "full + remainder", best);
+    }
+  }
   for (const Item& it : items) {
+    if (slot_item(it) && slot_split[it.nl > 5].cap > 0) {
+      const SlotSplit sp = slot_split[it.nl > 5];
+      const int ch = (it.end - it.begin + 31) / 32, k = (ch + sp.cap - 1) / sp.cap;
+      int b = it.begin;
+      for (int q = 0; q < k; q++) {
+        const int sz = sp.even ? ch / k + (q < ch % k ? 1 : 0) : std::min(sp.cap, ch - q * sp.cap);
+        TilePart p{};
+        p.window = it.w; p.pt_begin = b; p.pt_end = std::min(it.end, b + 32 * sz); p.cam_list_off = it.cam_off; p.n_local = it.nl; p.n_fixed = it.nfx;
+        p.pad_[0] = 1;
+        h->parts_h.push_back(p);
+        b = p.pt_end;
+      }
+      continue;
+    }
     const int Pc = slot_item(it) ? 32 : nt / it.nl;
     int part_pts = std::max<size_t>(2 * (size_t)Pc, (tile_points + target_parts - 1) / target_parts);
     part_pts = ((part_pts + Pc - 1) / Pc) * Pc;
@@ -456,13 +551,28 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     const int first = h->tile_cams_h[a.cam_list_off], last = h->tile_cams_h[a.cam_list_off + a.n_local - 1];
     return std::min(first, ncw - 1 - last);
   };
+  static const bool pipe_order = [] { const char* e = getenv("UBA_PIPE_SOLVE"); return e && e[0] == '1'; }();
   std::stable_sort(h->parts_h.begin(), h->parts_h.end(), [&](const TilePart& a, const TilePart& b) {
     const int va = variant(a), vb = variant(b);
-    return va != vb ? va < vb : end_dist(a) < end_dist(b);
+    if (va != vb) return va < vb;
+    if (pipe_order) return end_dist(a) < end_dist(b);
+    if (const char* e = getenv("UBA_PART_ORDER")) {                 // experiments: 0 = item order, 2 = shortest first
+      if (e[0] == '0') return false;
+      if (e[0] == '2') return a.pt_end - a.pt_begin < b.pt_end - b.pt_begin;
+    }
+    return a.pt_end - a.pt_begin > b.pt_end - b.pt_begin;          // longest first: the hardware hands CTAs out in this order
   });
   h->cam_expect_h.assign(h->NC, 0);
   for (const TilePart& p : h->parts_h)
     for (int q = 0; q < p.n_local; q++) h->cam_expect_h[h->w_cam_off[p.window] + h->tile_cams_h[p.cam_list_off + q]]++;
+  if (getenv("UBA_TRACE")) {
+    std::map<std::pair<int, int>, int> hist;     // (local cameras, chunks of 32 points) -> parts
+    for (const TilePart& p : h->parts_h) hist[{p.n_local, (p.pt_end - p.pt_begin + 31) / 32}]++;
+    fprintf(stderr, "  [trace] tile plan: %zu items, %zu parts, %zu generic points;", items.size(), h->parts_h.size(), h->gen_pts_h.size());
+    int shown = 0;
+    for (const auto& kv : hist) if (shown++ < 40) fprintf(stderr, " nl%d x %dch: %d,", kv.first.first, kv.first.second, kv.second);
+    fprintf(stderr, "\n");
+  }
   for (int v = 0; v <= kLinVariants; v++) h->variant_off[v] = 0;
   for (const TilePart& p : h->parts_h) h->variant_off[variant(p) + 1]++;
   for (int v = 0; v < kLinVariants; v++) h->variant_off[v + 1] += h->variant_off[v];
@@ -622,6 +732,7 @@ int prepare(uba_handle* h, int fixed_frames) {
   // lineariser choice: 1 = generic only; otherwise the tiled kernel plus the generic one for leftovers
   h->use_tile = h->cfg.linearizer != 1;
 #ifdef UBA_EMU
+  if (getenv("UBA_EMU_PLAN")) build_tile_plan(h, fixed_frames);   // host-only look at the planner (UBA_TRACE prints it)
   h->use_tile = false;  // the tiled kernel needs real thread blocks
 #endif
   if (h->use_tile) {

@@ -1188,13 +1188,40 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
   double* scratch = Zm;
   __shared__ int s_free[NLMAX];
   __shared__ int s_gc[NLMAX];
-  for (int i = t; i < nl * kCamSm; i += nall) {
-    const int sl2 = i / kCamSm, k = i - sl2 * kCamSm;
+  // the first chunk's mask / observation offset: issued ahead of the camera records so that the two chains of dependent
+  // misses (part -> camera list -> camera record, part -> mask / offset -> point / features) run side by side
+  unsigned mask_first = 0;
+  int off_first = 0;
+  if (!pt_warp && part.pt_begin + lane < part.pt_end) { mask_first = V.pt_mask[part.pt_begin + lane]; off_first = V.pt_obs_off[part.pt_begin + lane]; }
+  __shared__ double s_G[NLMAX * 9];                                // G = J_l(r) of every slot's camera, for the flush
+  for (int i = t; i < nl * 22; i += nall) {
+    const int sl2 = i / 22, k = i - sl2 * 22;
     const int gc = cbase + V.tile_cams[part.cam_list_off + sl2];
-    camS[i] = V.camR[cur][(size_t)gc * kCamStride + (k < 12 ? k : 21)];   // R (9), t (3), small-angle flag
+    const double v = V.camR[cur][(size_t)gc * kCamStride + k];             // R (9), t (3), G (9), small-angle flag
+    if (k < 12) camS[sl2 * kCamSm + k] = v; else if (k < 21) s_G[sl2 * 9 + k - 12] = v; else camS[sl2 * kCamSm + 12] = v;
     if (k == 0) { s_gc[sl2] = gc; s_free[sl2] = V.free_cam[gc]; }
   }
   for (int i = t; i < 8 * T * kSlotLdz; i += nall) Zm[i] = 0.0;     // padding rows / columns stay zero for the whole part
+  // prefetch pipeline (cp.async, no registers held): while chunk k is processed, the point and features of my observation in
+  // chunk k+1 and the mask / first-observation offset of my point in chunk k+2 are in flight into my staging column
+  constexpr int NS = 32 * NLMAX;
+  auto prefetch = [&](int b, int pa_, unsigned m, int off) {
+    double* sd = stageD + (size_t)b * kSlotStageD * NS + t;
+    int* si = stageI + (size_t)b * kSlotStageI * NS + t;
+    if ((m >> sl) & 1u) {
+      const double* px = V.pts[cur] + (size_t)pa_ * 3;
+      cp_async8(sd, px); cp_async8(sd + NS, px + 1); cp_async8(sd + 2 * NS, px + 2);
+      const int o = off + __popc(m & ((1u << sl) - 1u));
+#pragma unroll
+      for (int q = 0; q < M; q++) cp_async8(sd + (3 + q) * NS, V.feat + (size_t)q * V.NO + o);
+      if (M == 2) cp_async4(si + 2 * NS, V.obs_cam + o);
+    }
+    const int pb_ = pa_ + 32;
+    if (pb_ < part.pt_end) { cp_async4(si, V.pt_mask + pb_); cp_async4(si + NS, V.pt_obs_off + pb_); }
+    else si[0] = 0;
+    cp_async_commit();
+  };
+  if (!pt_warp) prefetch(0, part.pt_begin + lane, mask_first, off_first);
   named_bar<1>(nall);
 
   if (pt_warp) {
@@ -1323,32 +1350,7 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
   for (int i = 0; i < 6; i++) { Br[i] = 0.0; vq[i] = 0.0; zq[i] = 0.0; }
   double cost = 0.0;
 
-  // prefetch pipeline (cp.async, no registers held): while chunk k is processed, the point and features of my observation in
-  // chunk k+1 and the mask / first-observation offset of my point in chunk k+2 are in flight into my staging column
-  constexpr int NS = 32 * NLMAX;
-  auto prefetch = [&](int b, int pa_, unsigned m, int off) {
-    double* sd = stageD + (size_t)b * kSlotStageD * NS + t;
-    int* si = stageI + (size_t)b * kSlotStageI * NS + t;
-    if ((m >> sl) & 1u) {
-      const double* px = V.pts[cur] + (size_t)pa_ * 3;
-      cp_async8(sd, px); cp_async8(sd + NS, px + 1); cp_async8(sd + 2 * NS, px + 2);
-      const int o = off + __popc(m & ((1u << sl) - 1u));
-#pragma unroll
-      for (int q = 0; q < M; q++) cp_async8(sd + (3 + q) * NS, V.feat + (size_t)q * V.NO + o);
-      if (M == 2) cp_async4(si + 2 * NS, V.obs_cam + o);
-    }
-    const int pb_ = pa_ + 32;
-    if (pb_ < part.pt_end) { cp_async4(si, V.pt_mask + pb_); cp_async4(si + NS, V.pt_obs_off + pb_); }
-    else si[0] = 0;
-    cp_async_commit();
-  };
-  unsigned mask_cur = 0;
-  {
-    const int pa_ = part.pt_begin + lane;
-    int off0 = 0;
-    if (pa_ < part.pt_end) { mask_cur = V.pt_mask[pa_]; off0 = V.pt_obs_off[pa_]; }
-    prefetch(0, pa_, mask_cur, off0);
-  }
+  unsigned mask_cur = mask_first;
   const double* R = camS + sl * kCamSm;
   int buf = 0;
   bool have_prev = false;
@@ -1362,6 +1364,9 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
     int cid = 0;
     {
       cp_async_wait_all();
+#ifdef UBA_BAND_TIMING
+      if (t == 0 && c0 == part.pt_begin && blockIdx.x < 1000) { long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); V.Zbuf[2100 + blockIdx.x] = (double)(g_ % 1000000000ll); }
+#endif
       const double* sd = stageD + (size_t)buf * kSlotStageD * NS + t;
       const int* si = stageI + (size_t)buf * kSlotStageI * NS + t;
       if (seen) {
@@ -1464,15 +1469,19 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
   named_bar<3>(nslot);                        // from here on only the slot warps
 
   // ---- flush: Schur tiles -> shared memory, S_ab = D_a S'_ab D_b^T per camera-pair block, one red.add per entry ------
+#ifdef UBA_BAND_TIMING
+  if (t == 0 && blockIdx.x < 1000) { long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); V.Zbuf[3100 + blockIdx.x] = (double)(g_ % 1000000000ll); }
+#endif
+  //      One barrier: every slot warp stores its tiles and (free slots) the lane sums of its B', v', Z' h; then one thread
+  //      per block row brings it to the real frame (G from shared memory) and adds it to the accumulators directly.
   const int n = 6 * (V.w_free_off[w + 1] - V.w_free_off[w]);
   double* S = V.Sacc + V.w_red_off[w];
   const int sbeta = V.w_beta[w];
-  const int nloc = 6 * nlf;
-  const double* camG = V.camR[cur];
+  const int LDS2 = 8 * T + 1;
+  double* Sl = scratch;                           // [8 T][LDS2]
+  double* Bs = scratch + ROWS * (ROWS + 1);       // [nlf][32]: packed upper triangle of B' (without the zero at (0,1)), v', Z' h
   if (nlf > 0) {
     const int frow = lane >> 2, fc = (lane & 3) * 2;
-    const int LDS2 = 8 * T + 1;
-    double* Sl = scratch;                         // [8 T][LDS2]
 #pragma unroll
     for (int i = 0; i < TPW; i++) {
       if (tI[i] >= 0) {
@@ -1480,107 +1489,90 @@ __device__ __forceinline__ void slot_part(const DevView& V, const TilePart& part
         d[0] = acc[i][0]; d[1] = acc[i][1];
       }
     }
-    named_bar<3>(nslot);
-    const int nblk = nlf * (nlf + 1) / 2;
-    const int per = (nslot / 6) * 6;              // a block's six rows never straddle two passes
-    for (int base = 0; base < nblk * 6; base += per) {
-      const int idx = base + t;
-      const bool mine = t < per && idx < nblk * 6;
-      double out[6] = {0, 0, 0, 0, 0, 0};
-      int a = 0, b = 0, r = 0;
-      if (mine) {
-        int blk = idx / 6; r = idx - blk * 6;
-        while (blk >= nlf - a) { blk -= nlf - a; a++; }
-        b = a + blk;
-        const double* Ga = camG + (size_t)s_gc[nfx + a] * kCamStride + 12;
-        const double* Gb = camG + (size_t)s_gc[nfx + b] * kCamStride + 12;
-        auto X = [&](int i, int j) -> double {
-          return (a == b && j < i) ? Sl[(size_t)(6 * a + j) * LDS2 + 6 * a + i] : Sl[(size_t)(6 * a + i) * LDS2 + 6 * b + j];
-        };
-        double row[6];
-        if (r < 3) {
-#pragma unroll
-          for (int j = 0; j < 6; j++) row[j] = X(r, j);
-        } else {
-          const double g0 = Ga[r - 3], g1 = Ga[3 + r - 3], g2 = Ga[6 + r - 3];
-#pragma unroll
-          for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
-        }
-        out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
-#pragma unroll
-        for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], Gb[j], fma(row[4], Gb[3 + j], row[5] * Gb[6 + j]));
-      }
-      named_bar<3>(nslot);
-      if (mine) {
-#pragma unroll
-        for (int j = 0; j < 6; j++) if (a != b || j >= r) Sl[(size_t)(6 * a + r) * LDS2 + 6 * b + j] = out[j];
-      }
-      named_bar<3>(nslot);
-    }
-    for (int idx = t; idx < nloc * nloc; idx += nslot) {
-      const int row = idx / nloc, colx = idx - row * nloc;
-      if (colx < row) continue;
-      const double v = Sl[(size_t)row * LDS2 + colx];
-      if (v == 0.0) continue;
-      const int a = row / 6, b = colx / 6;
-      const int fa = s_free[nfx + a], fb = s_free[nfx + b];
-      atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + row - 6 * a, 6 * fb + (colx - 6 * b))], v);
-    }
-    named_bar<3>(nslot);
   }
-  // ---- flush: B', v', Z' h of my slot summed over the lanes (butterfly), packed, brought to the real frame ------------
-  double* Bs = scratch;                           // [nlf][33]: packed upper triangle of B', v', Z' h
   if (my_free) {
-    double val[33];
-    val[ut6(0, 0)] = Bt[0]; val[ut6(0, 1)] = 0.0; val[ut6(0, 2)] = Bt[1]; val[ut6(1, 1)] = Bt[2]; val[ut6(1, 2)] = Bt[3]; val[ut6(2, 2)] = Bt[4];
+    // 32 values summed over 32 lanes by a transposing reduction (31 exchanges instead of 5 x 32): round h keeps, on the
+    // lanes with bit h set, the values whose index has bit h set; lane l ends up with the total of value l
+    double val[32];
+    auto E = [](int e) { return e ? e - 1 : 0; };                     // packed index without ut6(0, 1)
+    val[E(ut6(0, 0))] = Bt[0]; val[E(ut6(0, 2))] = Bt[1]; val[E(ut6(1, 1))] = Bt[2]; val[E(ut6(1, 2))] = Bt[3]; val[E(ut6(2, 2))] = Bt[4];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
-      for (int c = 0; c < 3; c++) val[ut6(r, 3 + c)] = -Bu[r * 3 + c];
-    val[ut6(3, 3)] = Br[0]; val[ut6(3, 4)] = Br[1]; val[ut6(3, 5)] = Br[2]; val[ut6(4, 4)] = Br[3]; val[ut6(4, 5)] = Br[4]; val[ut6(5, 5)] = Br[5];
+      for (int c = 0; c < 3; c++) val[E(ut6(r, 3 + c))] = -Bu[r * 3 + c];
+    val[E(ut6(3, 3))] = Br[0]; val[E(ut6(3, 4))] = Br[1]; val[E(ut6(3, 5))] = Br[2]; val[E(ut6(4, 4))] = Br[3]; val[E(ut6(4, 5))] = Br[4]; val[E(ut6(5, 5))] = Br[5];
 #pragma unroll
-    for (int i = 0; i < 6; i++) { val[21 + i] = vq[i]; val[27 + i] = zq[i]; }
+    for (int i = 0; i < 6; i++) { val[E(21 + i)] = vq[i]; val[E(27 + i)] = zq[i]; }
 #pragma unroll
-    for (int e = 0; e < 33; e++) {
-      if (e == ut6(0, 1)) continue;
-      double v = val[e];
+    for (int hh = 16; hh >= 1; hh >>= 1) {
+      const bool up = (lane & hh) != 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-      val[e] = v;
+      for (int e = 0; e < hh; e++) {
+        const double keep = up ? val[e + hh] : val[e];
+        const double give = up ? val[e] : val[e + hh];
+        val[e] = keep + __shfl_xor_sync(FULL, give, hh);
+      }
     }
-    if (lane == 0) {
-      double* o = Bs + (size_t)(sl - nfx) * 33;
-#pragma unroll
-      for (int e = 0; e < 33; e++) o[e] = val[e];
-    }
+    Bs[(size_t)(sl - nfx) * 32 + lane] = val[0];
   }
   named_bar<3>(nslot);
-  for (int idx = t; idx < nlf * 6; idx += nslot) {
-    const int a = idx / 6, r = idx - a * 6;
-    const int gc = s_gc[nfx + a];
-    const double* Bp = Bs + (size_t)a * 33;
-    const double* G = camG + (size_t)gc * kCamStride + 12;
-    auto X = [&](int i, int j) -> double { return i <= j ? Bp[ut6(i, j)] : Bp[ut6(j, i)]; };
-    double row[6], vr, zr;
-    if (r < 3) {
+  const int nS = 3 * nlf * (nlf + 1), nB = 6 * nlf;                   // block rows of S' (upper block triangle), rows of B'
+  for (int idx = t; idx < nS + nB; idx += nslot) {
+    if (idx < nS) {
+      int blk = idx / 6, a = 0;
+      const int r = idx - blk * 6;
+      while (blk >= nlf - a) { blk -= nlf - a; a++; }
+      const int b = a + blk;
+      const double* Ga = s_G + (nfx + a) * 9;
+      const double* Gb = s_G + (nfx + b) * 9;
+      auto X = [&](int i, int j) -> double {
+        return (a == b && j < i) ? Sl[(size_t)(6 * a + j) * LDS2 + 6 * a + i] : Sl[(size_t)(6 * a + i) * LDS2 + 6 * b + j];
+      };
+      double row[6];
+      if (r < 3) {
 #pragma unroll
-      for (int j = 0; j < 6; j++) row[j] = X(r, j);
-      vr = Bp[21 + r]; zr = Bp[27 + r];
+        for (int j = 0; j < 6; j++) row[j] = X(r, j);
+      } else {
+        const double g0 = Ga[r - 3], g1 = Ga[3 + r - 3], g2 = Ga[6 + r - 3];
+#pragma unroll
+        for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
+      }
+      double out[6];
+      out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], Gb[j], fma(row[4], Gb[3 + j], row[5] * Gb[6 + j]));
+      const int fa = s_free[nfx + a], fb = s_free[nfx + b];
+#pragma unroll
+      for (int j = 0; j < 6; j++)
+        if ((a != b || j >= r) && out[j] != 0.0) atomicAdd(&S[sacc_index(n, sbeta, 6 * fa + r, 6 * fb + j)], out[j]);
     } else {
-      const double g0 = G[r - 3], g1 = G[3 + r - 3], g2 = G[6 + r - 3];
+      const int a = (idx - nS) / 6, r = (idx - nS) - a * 6;
+      const int gc = s_gc[nfx + a];
+      const double* Bp = Bs + (size_t)a * 32;
+      const double* G = s_G + (nfx + a) * 9;
+      auto P = [&](int e) -> double { return Bp[e ? e - 1 : 0]; };
+      auto X = [&](int i, int j) -> double { const int e = i <= j ? ut6(i, j) : ut6(j, i); return e == 1 ? 0.0 : P(e); };
+      double row[6], vr, zr;
+      if (r < 3) {
 #pragma unroll
-      for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
-      vr = fma(g0, Bp[24], fma(g1, Bp[25], g2 * Bp[26]));
-      zr = fma(g0, Bp[30], fma(g1, Bp[31], g2 * Bp[32]));
+        for (int j = 0; j < 6; j++) row[j] = X(r, j);
+        vr = P(21 + r); zr = P(27 + r);
+      } else {
+        const double g0 = G[r - 3], g1 = G[3 + r - 3], g2 = G[6 + r - 3];
+#pragma unroll
+        for (int j = 0; j < 6; j++) row[j] = fma(g0, X(3, j), fma(g1, X(4, j), g2 * X(5, j)));
+        vr = fma(g0, P(24), fma(g1, P(25), g2 * P(26)));
+        zr = fma(g0, P(30), fma(g1, P(31), g2 * P(32)));
+      }
+      double out[6];
+      out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
+#pragma unroll
+      for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], G[j], fma(row[4], G[3 + j], row[5] * G[6 + j]));
+#pragma unroll
+      for (int j = 0; j < 6; j++) if (j >= r && out[j] != 0.0) atomicAdd(&V.Bacc[(size_t)gc * 36 + r * 6 + j], out[j]);
+      if (vr != 0.0) atomicAdd(&V.vacc[(size_t)gc * 6 + r], vr);
+      if (zr != 0.0) atomicAdd(&V.zh[(size_t)gc * 6 + r], zr);
     }
-    double out[6];
-    out[0] = row[0]; out[1] = row[1]; out[2] = row[2];
-#pragma unroll
-    for (int j = 0; j < 3; j++) out[3 + j] = fma(row[3], G[j], fma(row[4], G[3 + j], row[5] * G[6 + j]));
-#pragma unroll
-    for (int j = 0; j < 6; j++) if (j >= r && out[j] != 0.0) atomicAdd(&V.Bacc[(size_t)gc * 36 + r * 6 + j], out[j]);
-    if (vr != 0.0) atomicAdd(&V.vacc[(size_t)gc * 6 + r], vr);
-    if (zr != 0.0) atomicAdd(&V.zh[(size_t)gc * 6 + r], zr);
   }
   cost = warp_sum(cost);
   if (lane == 0 && cost != 0.0) atomicAdd(&V.w_lin[(size_t)w * WL_COUNT + WL_COST], cost);
