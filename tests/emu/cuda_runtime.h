@@ -75,6 +75,7 @@ inline int atomicSub(int* p, int v) { const int o = *p; *p = o - v; return o; }
 inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; if (v > o) *p = v; return o; }
 inline long long __double_as_longlong(double d) { long long r; memcpy(&r, &d, 8); return r; }
 inline int __shfl_sync(unsigned, int v, int) { return v; }
+inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
 inline bool __all_sync(unsigned, bool p) { return p; }
 using std::isfinite;
 using std::min;

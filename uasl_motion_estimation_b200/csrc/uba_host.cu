@@ -452,8 +452,9 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   size_t target_parts = 2 * 148 * (256 / nt);
   if (const char* e = std::getenv("UBA_TILE_PARTS")) target_parts = (size_t)std::max(1, std::atoi(e));
   // k_lin_slot parts are sized per class (up to 5 local cameras: two CTAs per SM; up to 10: one) by a model of the pass:
-  // a part costs its chunks of 32 points plus a fixed c0 (camera records, pipeline fill, flush: ~3 chunk times, fitted on
-  // c4 / c5 part-size sweeps, scripts/part_sweep.py), the CTAs are dispatched longest first onto the class's resident slots.
+  // a part costs its chunks of 32 points plus a fixed c0 (camera records, pipeline fill, flush: ~1.5 chunk times, from the
+  // per-CTA timeline of scripts/part_timing.py and the part-size sweeps of scripts/part_sweep.py), the CTAs are dispatched
+  // longest first onto the class's resident slots.
   // Candidates: the largest item cut into 1..8 pieces and the ideal load of a slot, the pieces of an item evened out; the
   // makespan of every candidate is simulated on the histogram of part sizes (list scheduling over groups of equally loaded
   // slots), cheapest wins.  c3 (512 equal windows on 148 slots = 3.46 rounds) becomes 1024 half windows = 6.92 rounds;
@@ -462,7 +463,7 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   struct SlotSplit { int cap = 0; bool even = false; };
   SlotSplit slot_split[2];
   if (h->use_slot) {
-    static const double c0 = [] { const char* e = getenv("UBA_SLOT_C0"); return e ? atof(e) : 3.0; }();
+    static const double c0 = [] { const char* e = getenv("UBA_SLOT_C0"); return e ? atof(e) : 1.5; }();
     static const int n_sm = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return std::max(n, 1); }();
     for (int cls = 0; cls < 2; cls++) {
       std::map<int, int> ihist;                 // item size in chunks -> items

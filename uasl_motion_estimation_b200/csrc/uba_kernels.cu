@@ -3426,77 +3426,97 @@ __global__ void __launch_bounds__(128) k_solve_epilogue(DevView V) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// back-substitution + candidate point + candidate cost; one thread per point
+// back-substitution + candidate point + candidate cost; G adjacent lanes per point (G = 1, 2, 4 or 8, chosen by the mean
+// track length).  Lane g of a group takes observations g, g + G, ... of the point: G consecutive feature words per load
+// instead of one word every track-length words, 1 / G of the loads and of the register state per thread, the partial
+// E^T (F y_c) summed over the group by a butterfly (every lane ends with the same bits), the 3x3 solve repeated on every
+// lane, each lane's share of the candidate cost added up by the window reduction.
 // ---------------------------------------------------------------------------------------------
 #ifndef UBA_BACKSUB_MINBLOCKS
 #define UBA_BACKSUB_MINBLOCKS 3
 #endif
-template <int M>
-__global__ void __launch_bounds__(128, UBA_BACKSUB_MINBLOCKS) k_backsub(DevView V) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+template <int M, int G>
+__global__ void __launch_bounds__(128, G == 1 ? UBA_BACKSUB_MINBLOCKS : 4) k_backsub(DevView V) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = tid / G, g = tid % G;
   const bool in_range = p < V.NP;
   int w = in_range ? V.pt_win[p] : V.pt_win[V.NP - 1];
   const WinState* st = &V.ws[w];
   const bool live = in_range && st->done == 0;
   double mc = 0.0, step2 = 0.0, x2 = 0.0, cnew = 0.0;
-  bool active = false;
+  // observations held in registers per lane (the rest of a longer track takes the one-at-a-time path)
+  constexpr int KC = G == 1 ? 6 : (G == 2 ? 4 : 3);
+  int o0 = 0, o1 = 0, cur = 0, cbase = 0, kk = 0;
+  double X[3] = {0, 0, 0}, t3[3] = {0, 0, 0};
+  int occ[KC];
+  double fcc[KC][M];
+  double2 recv[kPtRec / 2];
   if (live) {
-    const int cur = st->cur, nxt = cur ^ 1;
-    const int o0 = V.pt_obs_off[p], o1 = V.pt_obs_off[p + 1];
-    const double X[3] = {V.pts[cur][(size_t)p * 3], V.pts[cur][(size_t)p * 3 + 1], V.pts[cur][(size_t)p * 3 + 2]};
+    cur = st->cur;
+    o0 = V.pt_obs_off[p]; o1 = V.pt_obs_off[p + 1];
+    X[0] = V.pts[cur][(size_t)p * 3]; X[1] = V.pts[cur][(size_t)p * 3 + 1]; X[2] = V.pts[cur][(size_t)p * 3 + 2];
+  }
+  const bool active = live && o1 > o0;
+  if (active) {
+    cbase = V.w_cam_off[w];
+    const double* camR = V.camR[cur];
+    // the point's record is needed only after the observation loop: fetch it now, eight 16-byte loads in flight
+    {
+      const double2* rec2 = reinterpret_cast<const double2*>(V.pt_rec + (size_t)p * kPtRec);
+#pragma unroll
+      for (int i = 0; i < kPtRec / 2; i++) recv[i] = __ldcs(rec2 + i);
+    }
+    // The kernel is bound by the latency of its global loads (ncu: long scoreboard), so the camera words and features of
+    // my first KC observations are fetched up front (KC x (M + 1) independent loads in flight) and kept in registers
+    // for the candidate-cost pass below.
+    const int mine = o1 - o0 > g ? (o1 - o0 - g + G - 1) / G : 0;
+    kk = min(mine, KC);
+#pragma unroll
+    for (int q = 0; q < KC; q++) {
+      if (q < kk) {
+        const int o = o0 + g + q * G;
+        occ[q] = V.obs_cam[o];
+#pragma unroll
+        for (int m = 0; m < M; m++) fcc[q][m] = V.feat[(size_t)m * V.NO + o];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < KC; q++) {
+      if (q < kk) {
+        const int gc = cbase + (occ[q] & 0x3fffffff);
+        if (V.free_cam[gc] >= 0) {
+          const double* ycp = V.cam_y + (size_t)gc * 6;
+          const double yc[6] = {ycp[0], ycp[1], ycp[2], ycp[3], ycp[4], ycp[5]};
+          // t3 += E^T (F y_c), matrix-free (uba_math.h: obs_apply)
+          obs_apply<M>(camR + (size_t)gc * kCamStride, X, fcc[q], (occ[q] >> 30) & 1, V.calib, V.loss, yc, t3);
+        }
+      }
+    }
+    for (int o = o0 + g + KC * G; o < o1; o += G) {
+      const int oc = V.obs_cam[o];
+      const int gc = cbase + (oc & 0x3fffffff);
+      if (V.free_cam[gc] < 0) continue;
+      double f[M];
+#pragma unroll
+      for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
+      const double* ycp = V.cam_y + (size_t)gc * 6;
+      const double yc[6] = {ycp[0], ycp[1], ycp[2], ycp[3], ycp[4], ycp[5]};
+      obs_apply<M>(camR + (size_t)gc * kCamStride, X, f, (oc >> 30) & 1, V.calib, V.loss, yc, t3);
+    }
+  }
+  if constexpr (G > 1) {                          // (groups are aligned inside a warp; idle groups exchange zeros)
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) t3[c] += __shfl_xor_sync(0xffffffffu, t3[c], off);
+    }
+  }
+  if (live) {
     double Xn[3] = {X[0], X[1], X[2]};
-    if (o1 > o0) {
-      active = true;
-      const int cbase = V.w_cam_off[w];
-      const double* camR = V.camR[cur];
-      double t3[3] = {0, 0, 0};
-      // the point's record is needed only after the observation loop: fetch it now, eight 16-byte loads in flight
-      double2 recv[kPtRec / 2];
-      {
-        const double2* rec2 = reinterpret_cast<const double2*>(V.pt_rec + (size_t)p * kPtRec);
-#pragma unroll
-        for (int i = 0; i < kPtRec / 2; i++) recv[i] = __ldcs(rec2 + i);
-      }
-      // The kernel is bound by the latency of its global loads (ncu: long scoreboard), so the camera words and features of
-      // the first KC observations are fetched up front (KC x (M + 1) independent loads in flight) and kept in registers
-      // for the candidate-cost pass below; longer tracks take the one-at-a-time path for the rest.
-      constexpr int KC = 6;
-      int occ[KC];
-      double fcc[KC][M];
-      const int kk = min(o1 - o0, KC);
-#pragma unroll
-      for (int q = 0; q < KC; q++) {
-        if (q < kk) {
-          occ[q] = V.obs_cam[o0 + q];
-#pragma unroll
-          for (int m = 0; m < M; m++) fcc[q][m] = V.feat[(size_t)m * V.NO + o0 + q];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < KC; q++) {
-        if (q < kk) {
-          const int gc = cbase + (occ[q] & 0x3fffffff);
-          if (V.free_cam[gc] >= 0) {
-            const double* ycp = V.cam_y + (size_t)gc * 6;
-            const double yc[6] = {ycp[0], ycp[1], ycp[2], ycp[3], ycp[4], ycp[5]};
-            obs_apply<M>(camR + (size_t)gc * kCamStride, X, fcc[q], (occ[q] >> 30) & 1, V.calib, V.loss, yc, t3);
-          }
-        }
-      }
-      for (int o = o0 + KC; o < o1; o++) {
-        const int oc = V.obs_cam[o];
-        const int gc = cbase + (oc & 0x3fffffff);
-        if (V.free_cam[gc] < 0) continue;
-        double f[M];
-#pragma unroll
-        for (int m = 0; m < M; m++) f[m] = V.feat[(size_t)m * V.NO + o];
-        // t3 += E^T (F y_c), matrix-free (uba_math.h: obs_apply)
-        const double* ycp = V.cam_y + (size_t)gc * 6;
-        const double yc[6] = {ycp[0], ycp[1], ycp[2], ycp[3], ycp[4], ycp[5]};
-        obs_apply<M>(camR + (size_t)gc * kCamStride, X, f, (oc >> 30) & 1, V.calib, V.loss, yc, t3);
-      }
+    if (active) {
+      const int nxt = cur ^ 1;
       const double Li[6] = {recv[0].x, recv[0].y, recv[1].x, recv[1].y, recv[2].x, recv[2].y};
-      const double h[3] = {recv[3].x, recv[3].y, recv[4].x}, g[3] = {recv[4].y, recv[5].x, recv[5].y}, lam[3] = {recv[6].x, recv[6].y, recv[7].x};
+      const double h[3] = {recv[3].x, recv[3].y, recv[4].x}, gr[3] = {recv[4].y, recv[5].x, recv[5].y}, lam[3] = {recv[6].x, recv[6].y, recv[7].x};
       double u[3], yp[3];
       linv_mul(Li, t3, u);
       u[0] = h[0] - u[0]; u[1] = h[1] - u[1]; u[2] = h[2] - u[2];
@@ -3506,11 +3526,13 @@ __global__ void __launch_bounds__(128, UBA_BACKSUB_MINBLOCKS) k_backsub(DevView 
         double v = X[c] - yp[c];
         if (V.cfg.use_bounds) v = clampd(v, V.calib.lo[c], V.calib.hi[c]);
         Xn[c] = v;
-        mc += yp[c] * g[c] + lam[c] * yp[c] * yp[c];
-        step2 += (X[c] - v) * (X[c] - v);
-        x2 += X[c] * X[c];
+        if (g == 0) {
+          mc += yp[c] * gr[c] + lam[c] * yp[c] * yp[c];
+          step2 += (X[c] - v) * (X[c] - v);
+          x2 += X[c] * X[c];
+        }
       }
-      // candidate cost at (candidate cameras, candidate point)
+      // candidate cost at (candidate cameras, candidate point): my observations
       const double* camRn = V.camR[nxt];
 #pragma unroll
       for (int q = 0; q < KC; q++) {
@@ -3521,7 +3543,7 @@ __global__ void __launch_bounds__(128, UBA_BACKSUB_MINBLOCKS) k_backsub(DevView 
           cnew += 0.5 * loss_rho(V.loss, s);
         }
       }
-      for (int o = o0 + KC; o < o1; o++) {
+      for (int o = o0 + g + KC * G; o < o1; o += G) {
         const int oc = V.obs_cam[o];
         const int gc = cbase + (oc & 0x3fffffff);
         double f[M];
@@ -3532,7 +3554,7 @@ __global__ void __launch_bounds__(128, UBA_BACKSUB_MINBLOCKS) k_backsub(DevView 
         cnew += 0.5 * loss_rho(V.loss, s);
       }
     }
-    V.pts[nxt][(size_t)p * 3] = Xn[0]; V.pts[nxt][(size_t)p * 3 + 1] = Xn[1]; V.pts[nxt][(size_t)p * 3 + 2] = Xn[2];
+    if (g == 0) { const int nxt = cur ^ 1; V.pts[nxt][(size_t)p * 3] = Xn[0]; V.pts[nxt][(size_t)p * 3 + 1] = Xn[1]; V.pts[nxt][(size_t)p * 3 + 2] = Xn[2]; }
   }
   win_add(V.w_post, WP_COUNT, w, WP_MCPT, mc, active);
   win_add(V.w_post, WP_COUNT, w, WP_STEP2, step2, active);
@@ -4079,9 +4101,28 @@ int launch_solve(const DevView& V, const int* h_win_n, const int* h_win_beta, in
 
 int launch_backsub(const DevView& V, cudaStream_t st) {
   if (V.NP == 0) return 0;
-  const int grid = (V.NP + 127) / 128;
-  if (V.M == 4) UBA_LAUNCH(k_backsub<4>, grid, 128, 0, st, V);
-  else UBA_LAUNCH(k_backsub<2>, grid, 128, 0, st, V);
+#ifdef UBA_EMU
+  const int G = 1;                               // the emulation runs the threads one after the other: no lane groups
+#else
+  // lanes per point (UBA_BACKSUB_GROUP overrides: 1, 2, 4, 8).  Measured on B200: with enough points to fill the GPU one
+  // thread per point wins (c4: 0.050 ms against 0.074 / 0.126 with 2 / 4 lanes — the per-point work every lane repeats
+  // outweighs the shorter observation loops); small windows gain from the extra parallelism (c2: 0.032 -> 0.021 ms).
+  static const int forced = [] { const char* e = getenv("UBA_BACKSUB_GROUP"); return e ? atoi(e) : 0; }();
+  int G = forced ? forced : (V.NP < 40000 ? 2 : 1);
+  if (G != 1 && G != 2 && G != 4 && G != 8) G = 1;
+#endif
+  const int grid = (int)(((int64_t)V.NP * G + 127) / 128);
+#define UBA_BS(MM, GG) UBA_LAUNCH((k_backsub<MM, GG>), grid, 128, 0, st, V)
+  if (V.M == 4) { if (G == 1) UBA_BS(4, 1);
+#ifndef UBA_EMU
+    else if (G == 2) UBA_BS(4, 2); else if (G == 4) UBA_BS(4, 4); else UBA_BS(4, 8);
+#endif
+  } else { if (G == 1) UBA_BS(2, 1);
+#ifndef UBA_EMU
+    else if (G == 2) UBA_BS(2, 2); else if (G == 4) UBA_BS(2, 4); else UBA_BS(2, 8);
+#endif
+  }
+#undef UBA_BS
   return 1;
 }
 
