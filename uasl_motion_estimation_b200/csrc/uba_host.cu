@@ -1420,6 +1420,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       }
     }
   }
+  TT("staging: features")
   if (canonical) {
 #pragma omp parallel for schedule(static)
     for (int64_t o = 0; o < NO; o++) {
@@ -1427,6 +1428,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       h->h_obs_cam.p[o] = cam_idx[o] | ((cam_id && cam_id[o] != 0) ? (1 << 30) : 0);
     }
   }
+  TT("staging: observation words")
 #pragma omp parallel for schedule(static)
   for (int s = 0; s < NP; s++) {
     const int j = h->pt_order[s];
@@ -1446,7 +1448,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       h->h_obs_cam.p[dst + q] = cam_idx[o] | ((cam_id && cam_id[o] != 0) ? (1 << 30) : 0);
     }
   }
-  TT("staging permute")
+  TT("staging: points")
   // device buffers
   CU(h, h->d_cams.reserve((size_t)NC * 12)); CU(h, h->d_camR.reserve((size_t)NC * kCamStride * 2));
   CU(h, h->d_cam_s2.reserve((size_t)NC * 6)); CU(h, h->d_cam_lam.reserve((size_t)NC * 6)); CU(h, h->d_cam_y.reserve((size_t)NC * 6));
