@@ -189,3 +189,49 @@ def test_features_that_are_not_floats_take_the_double_upload(emu_lib, oracle):
     hb = capi.Handle(cfg, lib=emu_lib)
     hb.set_problem(4, base.cams_init, base.pts_init, base.feats, base.cam_idx, base.pt_idx, base.cam_id, base.calib)
     assert rel(hb.linearize(2, 1e4)["residuals"], g["residuals"]) > 1e-9
+
+
+def _tile_plan(lib, h, fixed):
+    import ctypes as C
+    fn = lib.uba_emu_tile_plan
+    fn.restype = C.c_int
+    parts = np.zeros((8192, 7), np.int32); mask = np.zeros(h.n_pts, np.uint32)
+    n_parts = C.c_int32(0); n_gen = C.c_int32(0)
+    rc = fn(h._h, fixed, parts.ctypes.data_as(C.c_void_p), parts.shape[0], mask.ctypes.data_as(C.c_void_p), C.byref(n_parts), C.byref(n_gen))
+    assert rc == 0 and n_parts.value <= parts.shape[0]
+    return parts[: n_parts.value], mask, n_gen.value
+
+
+@pytest.mark.parametrize("name,scale", [("c4", 1.0), ("c4", 0.05), ("c5", 1.0), ("c1", 1.0), ("c2", 0.2)])
+def test_tile_plan_covers_every_track_once(emu_lib, name, scale):
+    """The lineariser's plan (build_tile_plan): parts are disjoint runs of internal point slots that cover every observed point
+    once; the slot mask of a point has one bit per observation, inside the part's camera list; parts of one kernel are handed
+    out longest first; a slot-kernel part has at most 10 local cameras; and the model's choice on the BASELINE shapes is the
+    one DESIGN.md states (c4: every part within one chunk of the others, about two full rounds of the 296 resident CTAs)."""
+    win, cfg, h = make(emu_lib, name, scale)
+    fixed = 2
+    parts, mask, n_gen = _tile_plan(emu_lib, h, fixed)
+    t = h.tables(fixed)
+    track = np.diff(t["pt_obs_off"]).astype(np.int64)[t["pt_order"]]     # caller order -> internal slots
+    assert n_gen == 0 and len(parts) > 0
+    cover = np.zeros(h.n_pts, np.int32)
+    for w, b, e, nl, nfx, slot, c0 in parts:
+        assert 0 <= b < e <= h.n_pts and 1 <= nl <= 32 and 0 <= nfx <= nl
+        cover[b:e] += 1
+        m = mask[b:e]
+        assert (m >> np.uint32(nl) == 0).all() if nl < 32 else True      # no bit beyond the part's camera list
+        if slot:
+            assert nl <= 10
+    observed = track > 0
+    assert (cover[observed] == 1).all() and (cover <= 1).all()
+    pop = np.array([bin(int(x)).count("1") for x in mask[observed]])
+    assert (pop == track[observed]).all()
+    # longest first inside a kernel class (slot parts: up to 5 cameras, up to 10; the others keep their own classes)
+    slot_parts = parts[parts[:, 5] == 1]
+    for cls in (0, 1):
+        sel = slot_parts[(slot_parts[:, 3] > 5) == (cls == 1)]
+        length = sel[:, 2] - sel[:, 1]
+        assert (np.diff(length) <= 0).all()
+    if name == "c4" and scale == 1.0:
+        chunks = (slot_parts[:, 2] - slot_parts[:, 1] + 31) // 32
+        assert len(slot_parts) == len(parts) and 560 <= len(parts) <= 592 and chunks.max() - chunks.min() <= 3

@@ -553,14 +553,13 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
     return std::min(first, ncw - 1 - last);
   };
   static const bool pipe_order = [] { const char* e = getenv("UBA_PIPE_SOLVE"); return e && e[0] == '1'; }();
+  static const int part_order = [] { const char* e = getenv("UBA_PART_ORDER"); return e ? atoi(e) : 1; }();   // experiments: 0 = item order, 2 = shortest first
   std::stable_sort(h->parts_h.begin(), h->parts_h.end(), [&](const TilePart& a, const TilePart& b) {
     const int va = variant(a), vb = variant(b);
     if (va != vb) return va < vb;
     if (pipe_order) return end_dist(a) < end_dist(b);
-    if (const char* e = getenv("UBA_PART_ORDER")) {                 // experiments: 0 = item order, 2 = shortest first
-      if (e[0] == '0') return false;
-      if (e[0] == '2') return a.pt_end - a.pt_begin < b.pt_end - b.pt_begin;
-    }
+    if (part_order == 0) return false;
+    if (part_order == 2) return a.pt_end - a.pt_begin < b.pt_end - b.pt_begin;
     return a.pt_end - a.pt_begin > b.pt_end - b.pt_begin;          // longest first: the hardware hands CTAs out in this order
   });
   h->cam_expect_h.assign(h->NC, 0);
@@ -2223,6 +2222,26 @@ int uba_time_iteration(uba_handle* h, int fixed_frames, int iterations, int do_f
   *ms_per_iteration = total / iterations;
   return UBA_OK;
 }
+
+#ifdef UBA_EMU
+// host-emulation build only (tests/test_host_logic_emu.py): the lineariser's tile plan as the GPU build would make it.
+// parts: rows of {window, pt_begin, pt_end, n_local, n_fixed, slot kernel?, first camera}; pt_mask: [n_pts] in internal order
+int uba_emu_tile_plan(uba_handle* h, int fixed_frames, int32_t* parts, int max_parts, uint32_t* pt_mask, int32_t* n_parts, int32_t* n_generic) {
+  if (!h || !parts || !pt_mask || !n_parts || !n_generic) return UBA_ERR_INVALID_ARGUMENT;
+  if (h->state < 1) return fail(h, UBA_ERR_STATE, "no problem set");
+  int rc = prepare(h, fixed_frames);
+  if (rc) return rc;
+  build_tile_plan(h, fixed_frames);
+  *n_parts = (int32_t)h->parts_h.size(); *n_generic = (int32_t)h->gen_pts_h.size();
+  for (int i = 0; i < std::min<int>(max_parts, *n_parts); i++) {
+    const TilePart& p = h->parts_h[i];
+    const int32_t row[7] = {p.window, p.pt_begin, p.pt_end, p.n_local, p.n_fixed, p.pad_[0], h->tile_cams_h[p.cam_list_off]};
+    std::memcpy(parts + (size_t)i * 7, row, sizeof(row));
+  }
+  std::memcpy(pt_mask, h->pt_mask_h.data(), sizeof(uint32_t) * h->NP);
+  return UBA_OK;
+}
+#endif
 
 #ifdef UBA_BAND_TIMING
 // instrumentation builds only (scripts/band_timing.py): the clocks the band solver leaves in the generic lineariser's scratch
