@@ -298,6 +298,12 @@ int uba_vo_get_inliers(uba_handle* h, int32_t* idx, int32_t* n_inliers);
 int uba_vo_refine(uba_handle* h, const double init6[6], int n_sel, const int32_t* selection, double state6[6], int32_t* converged,
                   int32_t* iterations);
 
+/* Host-only helpers with the device code's conventions: getMotion() (:331-342) — T16 = row-major [R(euler)^T | t; 0 0 0 1] of
+ * state6 = {roll, pitch, yaw, tx, ty, tz}; reproject() (:116-141) — predicted {left x, left y, right x, right y} of n
+ * homogeneous points pts4 [n][4] (uba_vo_get_points) under state6 (what getPredictions() returns for the inliers). */
+void uba_vo_pose_matrix(const double state6[6], double T16[16]);
+void uba_vo_predict(const uba_vo_params* params, const double state6[6], int n, const double* pts4, double* pred4);
+
 /* ---- synthetic stereo-rig generator; host only, deterministic ---- */
 typedef struct uba_synth_spec {
   int32_t M;               /* 4 stereo, 2 mono/two-camera */

@@ -1,5 +1,5 @@
 // tests/cvstub/core/feature_types.h — a MINIMAL stand-in for the parts of OpenCV and of the
-// reference's core/feature_types.h + core/rotation_utils.h that the drop-in BundleAdjuster.h touches,
+// reference's core/feature_types.h + core/rotation_utils.h that the drop-in BundleAdjuster.h and StereoVisualOdometry.h touch,
 // so the adapter can be compiled and exercised in a container without OpenCV C++ headers.  Written
 // from the interface, not from the reference sources; it is test scaffolding only —
 // a real build includes the reference's own header instead.
@@ -47,12 +47,34 @@ struct Mat {
   Mat(int r, int c, int, double* p) : rows(r), cols(c), d(p, p + r * c) {}
   void copyTo(Mat& o) const { o = *this; }
   bool empty() const { return d.empty(); }
+  // what the drop-in StereoVisualOdometry.h touches
+  int type() const { return CV_64F; }
+  Mat clone() const { return *this; }
+  static Mat zeros(int r, int c, int) { Mat m; m.rows = r; m.cols = c; m.d.assign((size_t)r * c, 0.0); return m; }
+  template <typename T> T& at(int i, int j) { return d[(size_t)i * cols + j]; }
+  template <typename T> const T& at(int i, int j) const { return d[(size_t)i * cols + j]; }
 };
 }  // namespace cv
 
 namespace me {
 typedef cv::Matx31d pt3D;
 typedef cv::Matx41d ptH3D;
+typedef cv::Matx31d ptH2D;
+template <typename T>
+struct StereoMatch {
+  T f1, f2;
+  float m_score;
+  StereoMatch() : m_score(-1) {}
+  StereoMatch(const T& a, const T& b, float score = -1) : f1(a), f2(b), m_score(score) {}
+};
+template <typename T>
+struct StereoOdoMatches : public StereoMatch<T> {
+  T f3, f4;
+  StereoOdoMatches() {}
+  StereoOdoMatches(const T& a, const T& b, const T& c, const T& d, float score = -1) : StereoMatch<T>(a, b, score), f3(c), f4(d) {}
+};
+typedef StereoMatch<cv::Point2f> StereoMatchf;
+typedef StereoOdoMatches<cv::Point2f> StereoOdoMatchesf;
 inline pt3D to_euclidean(const ptH3D& p) { return pt3D{p(0) / p(3), p(1) / p(3), p(2) / p(3)}; }
 
 template <typename T>

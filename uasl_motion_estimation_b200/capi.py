@@ -128,6 +128,8 @@ _SIGNATURES = [
     ("uba_vo_ransac", C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_double_p]),
     ("uba_vo_get_inliers", C.c_int, [C.c_void_p, c_int32_p, c_int32_p]),
     ("uba_vo_refine", C.c_int, [C.c_void_p, c_double_p, C.c_int, c_int32_p, c_double_p, c_int32_p, c_int32_p]),
+    ("uba_vo_pose_matrix", None, [c_double_p, c_double_p]),
+    ("uba_vo_predict", None, [C.POINTER(VoParams), c_double_p, C.c_int, c_double_p, c_double_p]),
     ("uba_shard_points", C.c_int, [C.c_int, C.c_int, C.c_int64, c_int32_p, c_int32_p, C.c_int, c_int32_p, c_int64_p, c_int32_p]),
     ("uba_shard_extract", C.c_int64, [C.c_int, C.c_int, C.c_int64, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
                                        C.c_int, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
@@ -137,7 +139,7 @@ _SIGNATURES = [
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 # the subset libuba_host.so carries as well (same sources, compiled without CUDA)
 HOST_SYMBOLS = ["uba_config_default", "uba_synth_default_calib", "uba_synth_generate", "uba_log_map_quat", "uba_exp_map_quat",
-                "uba_shard_points", "uba_shard_extract", "uba_vo_params_default"]
+                "uba_shard_points", "uba_shard_extract", "uba_vo_params_default", "uba_vo_pose_matrix", "uba_vo_predict"]
 
 
 class UbaError(RuntimeError):

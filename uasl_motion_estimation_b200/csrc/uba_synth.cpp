@@ -156,6 +156,34 @@ void uba_vo_params_default(uba_vo_params* p) {
   p->method = 0; p->max_iter = 100; p->e1 = 1e-3; p->e2 = 1e-12; p->e3 = 1e-12; p->e4 = 1e-15; p->inlier_threshold = 2.0;
 }
 
+// getMotion() (src/vo/StereoVisualOdometry.cpp:331-342): the 4x4 row-major [R(euler)^T | t; 0 0 0 1] of a state
+// {roll, pitch, yaw, tx, ty, tz} — the matrix the device code applies to the points (uba_vo.cu: vo_pose).
+void uba_vo_pose_matrix(const double state6[6], double T16[16]) {
+  if (!state6 || !T16) return;
+  const double sr = std::sin(state6[0]), cr = std::cos(state6[0]), sp = std::sin(state6[1]), cp = std::cos(state6[1]);
+  const double sy = std::sin(state6[2]), cy = std::cos(state6[2]);
+  const double R[3][3] = {{cp * cy, cp * sy, -sp}, {sp * sr * cy - cr * sy, sr * sp * sy + cr * cy, cp * sr}, {cr * sp * cy + sr * sy, cr * sp * sy - sr * cy, cp * cr}};
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) T16[i * 4 + j] = R[j][i]; T16[i * 4 + 3] = state6[3 + i]; }
+  T16[12] = T16[13] = T16[14] = 0.0; T16[15] = 1.0;
+}
+
+// reproject() (:116-141): predicted {left x, left y, right x, right y} of n homogeneous points under `state6`
+void uba_vo_predict(const uba_vo_params* P, const double state6[6], int n, const double* pts4, double* pred4) {
+  if (!P || !state6 || !pts4 || !pred4) return;
+  double T[16];
+  uba_vo_pose_matrix(state6, T);
+  for (int k = 0; k < n; k++) {
+    const double* X = pts4 + (size_t)k * 4;
+    double q[4];
+    for (int i = 0; i < 4; i++) q[i] = T[i * 4] * X[0] + T[i * 4 + 1] * X[1] + T[i * 4 + 2] * X[2] + T[i * 4 + 3] * X[3];
+    const double lz = q[2], rz = q[2];
+    pred4[(size_t)k * 4 + 0] = (P->fu1 * q[0] + P->cu1 * q[2]) / lz;
+    pred4[(size_t)k * 4 + 1] = (P->fv1 * q[1] + P->cv1 * q[2]) / lz;
+    pred4[(size_t)k * 4 + 2] = (P->fu2 * q[0] + P->cu2 * q[2] - P->baseline * P->fu2 * q[3]) / rz;
+    pred4[(size_t)k * 4 + 3] = (P->fv2 * q[1] + P->cv2 * q[2]) / rz;
+  }
+}
+
 // ---- point sharding of one large window ---------------------------------------
 // Points go to ranks by KEYFRAME RANGE: order them by (first keyframe of the track, caller index) and cut that order
 // into n_ranks pieces with equal observation counts.  A rank's tracks then start inside one contiguous camera range,
