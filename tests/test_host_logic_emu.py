@@ -51,6 +51,23 @@ def test_tables_with_shuffled_observations_and_empty_points(emu_lib, oracle):
     assert (np.diff(t["pt_obs_off"])[3::7] == 0).all()
 
 
+def test_tables_of_a_large_window_with_empty_points(emu_lib, oracle):
+    """Above 65536 points the offsets come from chunked parallel passes (backward fill over points without observations,
+    exclusive scan of the counts): same tables as the oracle, with runs of empty points across the chunk borders."""
+    win = synth.config_window("c4", scale=0.5, lib=emu_lib)
+    assert win.n_pts > 65536
+    empty = np.zeros(win.n_pts, bool)
+    empty[::11] = True; empty[12000:13000] = True; empty[win.n_pts - 700:] = True; empty[:3] = True
+    keep = ~empty[win.pt_idx]                                   # point-major order kept: the sorted-input path
+    ci, pi, f = win.cam_idx[keep], win.pt_idx[keep], win.feats[keep]
+    h = capi.Handle(capi.default_config(emu_lib), lib=emu_lib)
+    h.set_problem(4, win.cams_init, win.pts_init, f, ci, pi, None, win.calib)
+    t = h.tables(2); r = oracle.tables(win.n_cams, win.n_pts, ci, pi, 2)
+    for k in t:
+        assert np.array_equal(t[k], r[k]), k
+    assert (np.diff(t["pt_obs_off"])[empty] == 0).all() and (np.diff(t["pt_obs_off"])[~empty] > 0).all()
+
+
 @pytest.mark.parametrize("variant", ["track_order", "camera_descending", "random_points"])
 def test_ingest_paths_give_the_same_tables_and_blocks(emu_lib, oracle, variant):
     """The ingest has a fast path for input that is already canonical (tracks grouped by first/last keyframe, observations

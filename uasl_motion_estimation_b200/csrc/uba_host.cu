@@ -1223,7 +1223,29 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
         if (ident) h->obs_order[o] = (int32_t)o;
       }
       first[np] = o1;
-      for (int j = np - 1; j >= 0; j--) if (first[j] < 0) first[j] = first[j + 1];
+      // points without observations take the offset of the next observed point: a backward fill, done per chunk with the
+      // first defined offset at or after each chunk's end handed down from the chunks behind it
+      if (parallel && np > 65536) {
+        const int T = std::min(omp_get_max_threads(), 64);
+        int64_t head[65];
+#pragma omp parallel for schedule(static) num_threads(T)
+        for (int c = 0; c < T; c++) {
+          const int b = (int)((int64_t)np * c / T), e = (int)((int64_t)np * (c + 1) / T);
+          int64_t v = -1;
+          for (int j = b; j < e; j++) if (first[j] >= 0) { v = first[j]; break; }
+          head[c] = v;
+        }
+        head[T] = o1;
+        for (int c = T - 1; c >= 0; c--) if (head[c] < 0) head[c] = head[c + 1];
+#pragma omp parallel for schedule(static) num_threads(T)
+        for (int c = 0; c < T; c++) {
+          const int b = (int)((int64_t)np * c / T), e = (int)((int64_t)np * (c + 1) / T);
+          int64_t carry = head[c + 1];
+          for (int j = e - 1; j >= b; j--) { if (first[j] < 0) first[j] = carry; else carry = first[j]; }
+        }
+      } else {
+        for (int j = np - 1; j >= 0; j--) if (first[j] < 0) first[j] = first[j + 1];
+      }
 #pragma omp parallel for schedule(static) if (parallel)
       for (int j = 0; j < np; j++) c[j] = (int32_t)(first[j + 1] - first[j]);
     } else {
@@ -1246,7 +1268,28 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
   h->local_cam_lo = NC; h->local_cam_hi = -1;
   for (int c = 0; c < NC; c++) if (h->cam_seen[c]) { h->local_cam_lo = std::min(h->local_cam_lo, c); h->local_cam_hi = std::max(h->local_cam_hi, c); }
   TT("validate+count: passes")
-  for (int j = 0; j < NP; j++) h->pt_obs_off_caller[j + 1] = h->pt_obs_off_caller[j] + cnt[j];
+  if (NP > 65536) {
+    // exclusive scan of the counts in chunks: per-chunk totals, their running sum, then every chunk from its own base
+    const int T = std::min(omp_get_max_threads(), 64);
+    int64_t base[65];
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int c = 0; c < T; c++) {
+      const int b = (int)((int64_t)NP * c / T), e = (int)((int64_t)NP * (c + 1) / T);
+      int64_t sum = 0;
+      for (int j = b; j < e; j++) sum += cnt[j];
+      base[c + 1] = sum;
+    }
+    base[0] = 0;
+    for (int c = 0; c < T; c++) base[c + 1] += base[c];
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int c = 0; c < T; c++) {
+      const int b = (int)((int64_t)NP * c / T), e = (int)((int64_t)NP * (c + 1) / T);
+      int64_t run = base[c];
+      for (int j = b; j < e; j++) { run += cnt[j]; h->pt_obs_off_caller[j + 1] = run; }
+    }
+  } else {
+    for (int j = 0; j < NP; j++) h->pt_obs_off_caller[j + 1] = h->pt_obs_off_caller[j] + cnt[j];
+  }
   TT("validate+count")
   // Canonical order: point-major (stable), camera-ascending inside a point.  The reference's own
   // initialiseObservations already produces it (BundleAdjuster.h:364-374): detect that and skip the sort.
@@ -1360,9 +1403,17 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
       const int t = omp_get_thread_num(), T = omp_get_num_threads();
       const int b = (int)((int64_t)NP * t / T), e = (int)((int64_t)NP * (t + 1) / T);
       int64_t sum = 0;
+      // first sweep: the gathers through the point order (prefetched: they land at random in the caller's arrays), the
+      // track length parked in its slot; second sweep: sequential
       for (int s = b; s < e; s++) {
+        if (!ident && s + 16 < e) {
+          const int j2 = h->pt_order[s + 16];
+          __builtin_prefetch(&cnt[j2]); __builtin_prefetch(&hi_c[j2]); __builtin_prefetch(&lo_c[j2]); __builtin_prefetch(&contig_c[j2]);
+        }
         const int j = ident ? s : h->pt_order[s];
-        sum += h->pt_obs_off_caller[j + 1] - h->pt_obs_off_caller[j];
+        const int32_t len = cnt[j];
+        sum += len;
+        h->pt_obs_off_int[s + 1] = len;
         h->pt_lo[s] = hi_c[j] < 0 ? -1 : lo_c[j]; h->pt_hi[s] = hi_c[j]; h->pt_contig[s] = contig_c[j];
       }
       part[t + 1] = sum;
@@ -1370,11 +1421,7 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
 #pragma omp single
       for (int q = 0; q < T; q++) part[q + 1] += part[q];
       int64_t run = part[t];
-      for (int s = b; s < e; s++) {
-        const int j = ident ? s : h->pt_order[s];
-        run += h->pt_obs_off_caller[j + 1] - h->pt_obs_off_caller[j];
-        h->pt_obs_off_int[s + 1] = (int32_t)run;
-      }
+      for (int s = b; s < e; s++) { run += h->pt_obs_off_int[s + 1]; h->pt_obs_off_int[s + 1] = (int32_t)run; }
     }
   }
   TT("internal csr")
@@ -1428,8 +1475,19 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
     }
   }
   TT("staging: observation words")
+  // (the internal order visits the caller's points, offsets and observation words at random: three prefetch stages, each
+  // one dependent load further down the chain  point -> offset -> first observation -> its camera words)
+  const int32_t* const pt_order_p = h->pt_order.data();
+  const int64_t* const off_caller_p = h->pt_obs_off_caller.data();
+  const int32_t* const obs_order_p = h->obs_order.data();
 #pragma omp parallel for schedule(static)
   for (int s = 0; s < NP; s++) {
+    if (s + 24 < NP) { const int j2 = pt_order_p[s + 24]; __builtin_prefetch(pts3 + (size_t)j2 * 3); __builtin_prefetch(off_caller_p + j2); }
+    if (!canonical && s + 16 < NP) __builtin_prefetch(obs_order_p + off_caller_p[pt_order_p[s + 16]]);
+    if (!canonical && s + 8 < NP) {
+      const int64_t a = off_caller_p[pt_order_p[s + 8]];
+      if (a < NO) { const int32_t o2 = obs_order_p[a]; __builtin_prefetch(cam_idx + o2); if (cam_id) __builtin_prefetch(cam_id + o2); }
+    }
     const int j = h->pt_order[s];
     const double px = pts3[(size_t)j * 3], py = pts3[(size_t)j * 3 + 1], pz = pts3[(size_t)j * 3 + 2];
     h->h_pts.p[(size_t)s * 3] = px; h->h_pts.p[(size_t)s * 3 + 1] = py; h->h_pts.p[(size_t)s * 3 + 2] = pz;
