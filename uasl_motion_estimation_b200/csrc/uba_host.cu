@@ -449,7 +449,9 @@ void build_tile_plan(uba_handle* h, int fixed_frames) {
   }
   h->tile_threads = nt;
   // parts: aim at a few CTAs per SM, never less than 2 chunks of points per CTA
-  size_t target_parts = 2 * 148 * (256 / nt);
+  // (k_lin_wide, which takes the other parts when the slot kernel is on: four parts per SM measured better than two on c2,
+  // 0.089 against 0.100 ms; more than that changes nothing — the two-chunk minimum below takes over)
+  size_t target_parts = (h->use_slot ? 4 : 2) * 148 * (256 / nt);
   if (const char* e = std::getenv("UBA_TILE_PARTS")) target_parts = (size_t)std::max(1, std::atoi(e));
   // k_lin_slot parts are sized per class (up to 5 local cameras: two CTAs per SM; up to 10: one) by a model of the pass:
   // a part costs its chunks of 32 points plus a fixed c0 (camera records, pipeline fill, flush: ~1.5 chunk times, from the
