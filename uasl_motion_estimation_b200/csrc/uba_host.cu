@@ -157,6 +157,8 @@ struct uba_handle {
   // pinned staging (internal order)
   PinBuf<double> h_cams, h_pts, h_feat, h_out;
   PinBuf<int32_t> h_obs_cam;
+  PinBuf<int32_t> h_adv;                      // uba_window_advance: every index table of one advance, in the device's layout
+  PinBuf<double> h_cams_prev;                 // uba_window_advance: the previous window's cameras (fetched while the host plans)
   // device
   DevBuf<double> d_cams, d_camR, d_cam_s2, d_cam_lam, d_cam_y, d_pts, d_pt_s2, d_pt_rec, d_feat, d_acc, d_A, d_rhs, d_Zbuf, d_dbg, d_export, d_flush;
   DevBuf<int32_t> d_w_cam_off, d_w_pt_off, d_w_free_off, d_free_list, d_free_cam, d_cam_win, d_pt_obs_off, d_pt_win, d_obs_cam, d_obs_src, d_n_active, d_pt_order;
@@ -1685,7 +1687,7 @@ void uba_destroy(uba_handle* h) {
 #endif
   if (h->comm && h->nccl.CommDestroy) h->nccl.CommDestroy(h->comm);
   h->d_ctl.release(); h->d_acc_red.release(); h->d_xchg.release(); h->d_stop_local.release();
-  h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release(); h->h_obs_internal.release();
+  h->h_cams.release(); h->h_pts.release(); h->h_feat.release(); h->h_out.release(); h->h_obs_cam.release(); h->h_obs_internal.release(); h->h_adv.release(); h->h_cams_prev.release();
   h->d_cams.release(); h->d_camR.release(); h->d_cam_s2.release(); h->d_cam_lam.release(); h->d_cam_y.release(); h->d_pts.release();
   h->d_pt_s2.release(); h->d_pt_rec.release(); h->d_feat.release(); h->d_acc.release(); h->d_A.release(); h->d_rhs.release();
   h->d_Zbuf.release(); h->d_dbg.release(); h->d_export.release(); h->d_flush.release();
@@ -1739,8 +1741,25 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
   cudaSetDevice(h->device);
   cudaStream_t st = h->stream;
   auto tt_ = std::chrono::steady_clock::now();
+  // Every index table of the advance is built in ONE pinned block laid out like the device scratch (three uploads instead
+  // of ten from pageable vectors), and the previous window's cameras start their way back before the host plans anything:
+  // the call never waits for the stream.
+  CU(h, cudaStreamSynchronize(st));            // the staging block may still feed the previous advance's uploads (idle in practice)
+  const int par0 = h->state == 2 && h->ws_h[0].done != UBA_TERM_FAILURE && !h->device_dirty ? (h->ws_h[0].cur & 1) : 0;
+  const bool fetch_cams = !cams6_all && !h->device_dirty;
+  if (fetch_cams) {
+    CU(h, h->h_cams_prev.reserve((size_t)NCo * 6));
+    CU(h, cudaMemcpyAsync(h->h_cams_prev.p, h->d_cams.p + (size_t)par0 * NCo * 6, sizeof(double) * 6 * NCo, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaEventRecord(h->ev[6], st));
+  }
+  const int NPmax = NPo + n_new_pts;
+  const size_t t_drop = 0, t_map = t_drop + NPo, t_pt = t_map + NPo, t_cam = t_pt + n_new_obs;       // known now
+  const size_t stage_max = t_cam + n_new_obs + (size_t)5 * NPmax + 2 + (size_t)NPmax + 1 + (size_t)(NPmax + 3) / 4 + 4;
+  CU(h, h->h_adv.reserve(stage_max));
+  int32_t* const A = h->h_adv.p;
   // ---- 1. survivors ------------------------------------------------------------------------------------------------
-  std::vector<int32_t> dropped(NPo), id_map(NPo);
+  int32_t* const dropped = A + t_drop;
+  int32_t* const id_map = A + t_map;
   int n_alive = 0;
   for (int j = 0; j < NPo; j++) {
     const int d = std::min(std::max(n_drop - h->tr_lo[j], 0), h->tr_cnt[j]);
@@ -1749,8 +1768,18 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
   }
   const int NPn = n_alive + n_new_pts;
   if (NPn <= 0) return fail(h, UBA_ERR_INVALID_ARGUMENT, "uba_window_advance: the new window has no points");
-  std::vector<int32_t> lo_n(NPn, 0), cnt_n(NPn, 0), old_of(NPn, -1);
-  std::vector<unsigned char> cid_n(NPn, 0);
+  const size_t t_src = t_cam + n_new_obs, t_lo = t_src + NPn, t_order = t_lo + NPn, t_offi = t_order + NPn, t_end = t_offi + NPn + 1;
+  const size_t t_offn = t_end, t_cid = t_offn + NPn + 1;              // behind the device block: the caller-order CSR, the camID bytes
+  int32_t* const src_slot = A + t_src;
+  int32_t* const lo_n = A + t_lo;
+  int32_t* const order = A + t_order;
+  int32_t* const off_i = A + t_offi;
+  int32_t* const off_n = A + t_offn;
+  unsigned char* const cid_n = reinterpret_cast<unsigned char*>(A + t_cid);
+  if (n_new_obs) { std::memcpy(A + t_pt, pt_idx, sizeof(int32_t) * n_new_obs); std::memcpy(A + t_cam, cam_idx, sizeof(int32_t) * n_new_obs); }
+  std::vector<int32_t> cnt_n(NPn, 0), old_of(NPn, -1);
+  std::fill(lo_n, lo_n + NPn, 0);
+  std::memset(cid_n, 0, NPn);
   for (int j = 0; j < NPo; j++) {
     const int nj = id_map[j];
     if (nj < 0) continue;
@@ -1777,12 +1806,11 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
       cnt_n[j] += add[j];
     }
   }
-  std::vector<int32_t> off_n((size_t)NPn + 1, 0);
+  off_n[0] = 0;
   for (int j = 0; j < NPn; j++) off_n[j + 1] = off_n[j] + cnt_n[j];
   const int64_t NOn = off_n[NPn];
   TT("advance: track tables")
   // ---- 3. internal point order: stable by (first keyframe, last keyframe), unobserved points last --------------------
-  std::vector<int32_t> order(NPn), off_i((size_t)NPn + 1, 0);
   {
     int span = 1;
     for (int j = 0; j < NPn; j++) span = std::max(span, cnt_n[j]);
@@ -1793,9 +1821,10 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
     for (int64_t k = 0; k < nk; k++) hist[k + 1] += hist[k];
     for (int j = 0; j < NPn; j++) order[hist[key(j)]++] = j;
   }
-  std::vector<int32_t> old_slot(NPo, -1), src_slot(NPn);
+  std::vector<int32_t> old_slot(NPo, -1);
   for (int s = 0; s < NPo; s++) old_slot[h->pt_order[s]] = s;
   h->pt_lo.resize(NPn); h->pt_hi.resize(NPn); h->pt_contig.assign(NPn, 1);
+  off_i[0] = 0;
   for (int s = 0; s < NPn; s++) {
     const int j = order[s];
     off_i[s + 1] = off_i[s] + cnt_n[j];
@@ -1806,24 +1835,13 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
   // ---- 4. device: shift, append, pack ------------------------------------------------------------------------------
   const int cur = h->rows_cur, nxt = cur ^ 1;
   CU(h, h->d_rows[nxt].reserve((size_t)NOn * M + 1)); CU(h, h->d_tr_off[nxt].reserve((size_t)NPn + 1));
-  const size_t t_drop = 0, t_map = t_drop + NPo, t_pt = t_map + NPo, t_cam = t_pt + n_new_obs, t_src = t_cam + n_new_obs, t_lo = t_src + NPn,
-               t_order = t_lo + NPn, t_offi = t_order + NPn, t_end = t_offi + NPn + 1;
   CU(h, h->d_tr_tmp.reserve(t_end)); CU(h, h->d_tr_cid.reserve(NPn));
   CU(h, h->d_fresh.reserve((size_t)n_new_obs * M + (size_t)n_new_pts * 3 + 1));
   int32_t* T = h->d_tr_tmp.p;
-  CU(h, cudaMemcpyAsync(T + t_drop, dropped.data(), sizeof(int32_t) * NPo, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(T + t_map, id_map.data(), sizeof(int32_t) * NPo, cudaMemcpyHostToDevice, st));
-  if (n_new_obs) {
-    CU(h, cudaMemcpyAsync(T + t_pt, pt_idx, sizeof(int32_t) * n_new_obs, cudaMemcpyHostToDevice, st));
-    CU(h, cudaMemcpyAsync(T + t_cam, cam_idx, sizeof(int32_t) * n_new_obs, cudaMemcpyHostToDevice, st));
-    CU(h, cudaMemcpyAsync(h->d_fresh.p, feats, sizeof(double) * (size_t)n_new_obs * M, cudaMemcpyHostToDevice, st));
-  }
-  CU(h, cudaMemcpyAsync(T + t_src, src_slot.data(), sizeof(int32_t) * NPn, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(T + t_lo, lo_n.data(), sizeof(int32_t) * NPn, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(T + t_order, order.data(), sizeof(int32_t) * NPn, cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(T + t_offi, off_i.data(), sizeof(int32_t) * ((size_t)NPn + 1), cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(h->d_tr_off[nxt].p, off_n.data(), sizeof(int32_t) * ((size_t)NPn + 1), cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(h->d_tr_cid.p, cid_n.data(), NPn, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(T, A, sizeof(int32_t) * t_end, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_tr_off[nxt].p, off_n, sizeof(int32_t) * ((size_t)NPn + 1), cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(h->d_tr_cid.p, cid_n, NPn, cudaMemcpyHostToDevice, st));
+  if (n_new_obs) CU(h, cudaMemcpyAsync(h->d_fresh.p, feats, sizeof(double) * (size_t)n_new_obs * M, cudaMemcpyHostToDevice, st));
   h->timing.kernel_launches += launch_win_shift(h->d_rows[cur].p, h->d_tr_off[cur].p, T + t_drop, T + t_map, h->d_tr_off[nxt].p, NPo, M, h->d_rows[nxt].p, st);
   h->timing.kernel_launches += launch_win_append(h->d_fresh.p, T + t_pt, T + t_cam, T + t_lo, h->d_tr_off[nxt].p, n_new_obs, M, h->d_rows[nxt].p, st);
   // points: what the last solve left (its accepted iterate), re-slotted, plus the newcomers — or the caller's values
@@ -1834,10 +1852,10 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
   h->win_infeasible.assign(1, 0);
   if (h->device_dirty) { const int rcu = upload_state(h); if (rcu) return rcu; h->device_dirty = false; h->state = 1; }
   const int par = h->state == 2 && h->ws_h[0].done != UBA_TERM_FAILURE ? (h->ws_h[0].cur & 1) : 0;
-  std::vector<double> cams_old;
-  if (!cams6_all) {
-    cams_old.resize((size_t)NCo * 6);
-    CU(h, cudaMemcpyAsync(cams_old.data(), h->d_cams.p + (size_t)par * NCo * 6, sizeof(double) * 6 * NCo, cudaMemcpyDeviceToHost, st));
+  if (!cams6_all && !fetch_cams) {             // the benchmark's scratch was on the device: the staged state was just re-uploaded
+    CU(h, h->h_cams_prev.reserve((size_t)NCo * 6));
+    CU(h, cudaMemcpyAsync(h->h_cams_prev.p, h->d_cams.p + (size_t)par * NCo * 6, sizeof(double) * 6 * NCo, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaEventRecord(h->ev[6], st));
   }
   CU(h, h->d_pt_rec.reserve((size_t)std::max(NPn, NPo) * kPtRec));     // scratch for the re-slotted points
   if (pts3_all) {
@@ -1854,19 +1872,22 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
     }
     h->timing.kernel_launches += launch_win_points(h->d_pts.p + (size_t)par * NPo * 3, T + t_src, h->d_fresh.p + (size_t)n_new_obs * M, NPn, h->d_pt_rec.p, st);
   }
-  CU(h, cudaStreamSynchronize(st));            // the gathers above read buffers that are re-sized below; host vectors are free again
+  // No wait for the stream here: the buffers re-sized below are not the ones the kernels above touch (a buffer that does
+  // have to grow is released with cudaFree, which waits for the device), and the uploads above come from pinned staging
+  // that is not written again before the next advance.
   TT("advance: shift + append")
   if (cams6_all) std::memcpy(h->h_cams.p, cams6_all, sizeof(double) * 6 * NCn);
   else {
-    std::memcpy(h->h_cams.p, cams_old.data() + (size_t)n_drop * 6, sizeof(double) * 6 * (NCo - n_drop));
+    CU(h, cudaEventSynchronize(h->ev[6]));     // the previous cameras: on their way since the start of the call
+    std::memcpy(h->h_cams.p, h->h_cams_prev.p + (size_t)n_drop * 6, sizeof(double) * 6 * (NCo - n_drop));
     if (n_new_cams) std::memcpy(h->h_cams.p + (size_t)(NCo - n_drop) * 6, new_cams6, sizeof(double) * 6 * n_new_cams);
   }
   // ---- 5. commit: the handle now describes the new window ------------------------------------------------------------
   h->NC = NCn; h->NP = NPn; h->NO = NOn; h->nW = 1;
   h->w_cam_off = {0, NCn}; h->w_pt_off = {0, NPn}; h->w_obs_off = {0, NOn};
-  h->tr_lo.swap(lo_n); h->tr_cnt.swap(cnt_n); h->tr_cid.swap(cid_n); h->rows_cur = nxt;
-  h->pt_order.swap(order);
-  h->pt_obs_off_int.assign(off_i.begin(), off_i.end());
+  h->tr_lo.assign(lo_n, lo_n + NPn); h->tr_cnt.swap(cnt_n); h->tr_cid.assign(cid_n, cid_n + NPn); h->rows_cur = nxt;
+  h->pt_order.assign(order, order + NPn);
+  h->pt_obs_off_int.assign(off_i, off_i + NPn + 1);
   h->pt_obs_off_caller.resize((size_t)NPn + 1);
   for (int j = 0; j <= NPn; j++) h->pt_obs_off_caller[j] = off_n[j];
   h->cam_seen.assign(NCn, 0);
@@ -1908,7 +1929,7 @@ int uba_window_advance(uba_handle* h, int n_drop, int n_new_cams, const double* 
   h->V.rec_stride = rec_stride;
   h->ws_h.assign(1, WinState{});
   h->state = 1;
-  if (pt_id_map) std::memcpy(pt_id_map, id_map.data(), sizeof(int32_t) * NPo);
+  if (pt_id_map) std::memcpy(pt_id_map, id_map, sizeof(int32_t) * NPo);
   TT("advance: pack (enqueue)")
   return UBA_OK;
 }
