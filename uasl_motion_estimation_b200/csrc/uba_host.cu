@@ -1115,7 +1115,12 @@ int run_iteration_fast(uba_handle* h) {
   // single-GPU one.  On the NCCL fallback path they launch directly: capturing the collectives works (UBA_COMM_GRAPH=1,
   // results identical) but measured SLOWER on 2 B200 (0.44 vs 0.36 ms per iteration)
   static const bool comm_graph = [] { const char* e = getenv("UBA_COMM_GRAPH"); return e && e[0] == '1'; }();
-  if (!h->profiling && (!h->comm || h->peer_on || comm_graph)) {
+  // A solve of a few fixed iterations (the per-frame sliding window runs K = 4) launches its kernels directly: capturing and
+  // instantiating the graph costs ~0.1 ms per problem, more than the launch gaps it removes from four iterations.
+  static const int graph_min_iters = [] { const char* e = getenv("UBA_GRAPH_MIN_ITERS"); return e ? atoi(e) : 6; }();
+  const bool few_iters = h->cfg.fixed_iterations > 0 && h->cfg.fixed_iterations < graph_min_iters && !h->graph_exec &&
+                         !h->pipe_on;   // (the pipelined solve is written for the graph's fork / join)
+  if (!h->profiling && !few_iters && (!h->comm || h->peer_on || comm_graph)) {
     // the graph bakes the device views in by value: any change of them (sizes, pointers, solver settings) invalidates it
     if (h->graph_exec && (std::memcmp(&h->V, &h->graph_V, sizeof(DevView)) != 0 || std::memcmp(&h->Vc, &h->graph_Vc, sizeof(DevView)) != 0 ||
                           std::memcmp(&h->P, &h->graph_P, sizeof(PeerView)) != 0)) drop_graph(h);
