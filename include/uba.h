@@ -90,9 +90,10 @@ typedef struct uba_config {
   int32_t jacobi_scaling;          /* default 1 */
   int32_t use_bounds;              /* default 1: point box of BundleAdjuster.h:442-443,:455-460 */
   int32_t device;                  /* CUDA device ordinal; default 0 (or LOCAL_RANK under torchrun) */
-  int32_t linearizer;              /* 0 auto (tiled: warp-per-camera-slot kernel for tracks of up to 10 keyframes, lane-per-observation
-                                      kernel beyond; Schur products on the FP64 MMA path), 1 generic (thread per point, global
-                                      fp64 atomics), 2 lane-per-observation tiled kernel only */
+  int32_t linearizer;              /* 0 auto (tiled: warp-per-camera-slot kernel, Schur products on the FP64 MMA path, for windows
+                                      whose tracks span up to 10 keyframes; the wide-part tiled kernel for windows with longer
+                                      tracks), 1 generic (thread per point, global fp64 atomics), 2 lane-per-observation tiled
+                                      kernel only */
   int32_t compute_covariance;      /* CalibrationParameters::compute_cov (:40); default 0 */
   int32_t solver;                  /* 0 auto (banded LDL^T for large block-banded systems), 1 dense Cholesky only */
   int32_t sliding_window;          /* 1: keep the window's observation rows resident so that uba_window_advance can slide it
