@@ -1501,10 +1501,10 @@ int build_problem(uba_handle* h, int M, int nW, const int32_t* wc, const int32_t
 #pragma omp parallel for schedule(static)
   for (int s = 0; s < NP; s++) {
     if (s + 24 < NP) { const int j2 = pt_order_p[s + 24]; __builtin_prefetch(pts3 + (size_t)j2 * 3); __builtin_prefetch(off_caller_p + j2); }
-    if (!canonical && s + 16 < NP) __builtin_prefetch(obs_order_p + off_caller_p[pt_order_p[s + 16]]);
+    if (!canonical && !obs_ident && s + 16 < NP) __builtin_prefetch(obs_order_p + off_caller_p[pt_order_p[s + 16]]);
     if (!canonical && s + 8 < NP) {
       const int64_t a = off_caller_p[pt_order_p[s + 8]];
-      if (a < NO) { const int32_t o2 = obs_order_p[a]; __builtin_prefetch(cam_idx + o2); if (cam_id) __builtin_prefetch(cam_id + o2); }
+      if (a < NO) { const int64_t o2 = obs_ident ? a : obs_order_p[a]; __builtin_prefetch(cam_idx + o2); if (cam_id) __builtin_prefetch(cam_id + o2); }
     }
     const int j = h->pt_order[s];
     const double px = pts3[(size_t)j * 3], py = pts3[(size_t)j * 3 + 1], pz = pts3[(size_t)j * 3 + 2];
